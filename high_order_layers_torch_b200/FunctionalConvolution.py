@@ -1,0 +1,85 @@
+"""PiecewisePolynomialConvolution2d on the unfolded fully-connected kernels.
+
+Reference FunctionalConvolution.py: PiecewisePolynomialConvolution (:392-447),
+PiecewisePolynomialConvolution2d (:450-490), conv_wrapper (:53-103),
+constant_random_initialization_conv2d (:17-50).  The reference expands the input to C*V dense
+channels and calls nn.Conv2d; here the conv IS the piecewise layer applied to im2col rows
+(SURVEY 3.3), evaluated by the same CUDA kernels without materialising either tensor.  The
+parameter keeps the reference's name and layout: ``conv.weight [O, C*V, K, K]``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+
+
+def _as_int(v, name: str) -> int:
+    if isinstance(v, (tuple, list)):
+        if len(set(v)) != 1:
+            raise ValueError(f"{name}={v}: only square (equal) values are supported")
+        v = v[0]
+    return int(v)
+
+
+class PiecewisePolynomialConvolution2d(nn.Module):
+    def __init__(self, n: int, segments: int, in_channels: int, out_channels: int, kernel_size: int,
+                 length: float = 2.0, rescale_output: bool = False, periodicity: Optional[float] = None,
+                 weight_magnitude: float = 1.0, device: str = "cpu", *args, stride: int = 1, padding: int = 0,
+                 dilation: int = 1, groups: int = 1, padding_mode: str = "zeros", **kwargs):
+        super().__init__()
+        if groups != 1:
+            raise ValueError("PiecewisePolynomialConvolution2d: groups != 1 is not supported by the CUDA path")
+        if padding_mode != "zeros":
+            raise ValueError("PiecewisePolynomialConvolution2d: only padding_mode='zeros' is supported")
+        if isinstance(padding, str):
+            raise ValueError("PiecewisePolynomialConvolution2d: string padding modes are not supported")
+        self._n = n
+        self._segments = segments
+        self._length = length
+        self._kernel_size = _as_int(kernel_size, "kernel_size")
+        self._stride = _as_int(stride, "stride")
+        self._padding = _as_int(padding, "padding")
+        self._dilation = _as_int(dilation, "dilation")
+        self._in_channels = in_channels
+        self._nodes = (n - 1) * segments + 1
+        self._channels = self._nodes * in_channels
+        self._out_channels = out_channels
+        self.periodicity = periodicity
+        k = self._kernel_size
+        # parameter container with the reference's key (conv.weight); its own forward is never
+        # used.  The three steps below consume the RNG exactly like the reference (conv_wrapper
+        # then constant_random_initialization_conv2d), so equal seeds give equal weights.
+        self.conv = nn.Conv2d(in_channels=self._channels, out_channels=out_channels, kernel_size=k,
+                              stride=self._stride, padding=self._padding, dilation=self._dilation, groups=1,
+                              bias=False, padding_mode="zeros")
+        in_features = self._channels * k * k
+        if rescale_output is False:
+            self.conv.weight.data.uniform_(-weight_magnitude / in_features, weight_magnitude / in_features)
+        elif rescale_output is True:
+            self.conv.weight.data.uniform_(-weight_magnitude, weight_magnitude)
+        self._total_in = in_channels * k * k
+        self._rescale = 1.0 / self._total_in if rescale_output is True else 1.0
+        # one random constant per (out, in, kh, kw) link, identical over the nodes
+        link_features = k * k * self._channels // self._nodes
+        values = torch.rand(out_channels, in_channels, k, k, device=device) * weight_magnitude / link_features
+        with torch.no_grad():
+            self.conv.weight.copy_(values.unsqueeze(2).expand(out_channels, in_channels, self._nodes, k, k)
+                                   .reshape(out_channels, self._channels, k, k))
+        if str(device) != "cpu":
+            self.conv.to(device)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(
+                f"PiecewisePolynomialConvolution2d: input is on {x.device}; this build runs on CUDA (sm_100a) only "
+                "and has no CPU fallback")
+        return ops.piecewise_polynomial_conv2d(x, self.conv.weight, self._n, self._segments, self._kernel_size,
+                                               length=float(self._length), discontinuous=False,
+                                               periodicity=self.periodicity, stride=self._stride,
+                                               padding=self._padding, dilation=self._dilation,
+                                               rescale=self._rescale)

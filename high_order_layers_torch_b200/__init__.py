@@ -1,0 +1,20 @@
+"""B200-native (sm_100a) piecewise Lagrange-polynomial layers.
+
+Drop-in for the hot path of jloveric/high-order-layers-torch: the same constructors
+(`high_order_fc_layers`, `HighOrderMLP`, `high_order_convolution_layers`, `PiecewisePolynomial`,
+`PiecewiseDiscontinuousPolynomial`, `PiecewisePolynomialConvolution2d`), parameter names and
+shapes; forward/backward run hand-written CUDA kernels through a C-ABI library
+(`csrc/libhol_b200.so`, `include/hol_b200.h`).  CUDA only -- there is no CPU fallback.
+"""
+from .layers import (  # noqa: F401
+    MaxAbsNormalization,
+    convolutional_layers,
+    fc_layers,
+    high_order_convolution_layers,
+    high_order_fc_layers,
+)
+from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial  # noqa: F401
+from .FunctionalConvolution import PiecewisePolynomialConvolution2d  # noqa: F401
+from .networks import HighOrderMLP  # noqa: F401
+
+__version__ = "0.1.0"

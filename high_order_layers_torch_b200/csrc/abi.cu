@@ -1,0 +1,256 @@
+// C ABI (include/hol_b200.h): argument validation, planning, workspace carving, launches.
+// Never allocates, never synchronises; everything goes to the caller's stream.
+#include <math.h>
+#include <string.h>
+
+#include "kernels.cuh"
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Fill the plan for one layer call.  Returns HOL_OK / HOL_EINVAL / HOL_EUNSUPPORTED.
+int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, float length, float periodicity,
+               const float* nodes_host) {
+    if (B < 0 || I <= 0 || O <= 0 || n <= 0 || S <= 0) return HOL_EINVAL;
+    if (n > HOL_MAX_N || S > HOL_MAX_SEGMENTS) return HOL_EUNSUPPORTED;
+    memset(&s, 0, sizeof(s));
+    s.B = B;
+    s.Bp = B <= 256 ? round_up64(B > 0 ? B : 1, 32) : round_up64(B, 512);
+    s.I = I;
+    s.O = O;
+    s.n = n;
+    s.S = S;
+    s.disc = disc ? 1 : 0;
+    s.stride = disc ? n : n - 1;
+    s.nb = disc ? n * S : (n - 1) * S + 1;
+    const bool single = !disc && n == 1;  // one weight per link whatever the segment
+    s.RS = single ? 1 : (disc ? S : S + 1);
+    s.R = single ? 1 : (disc ? n * S : (n - 1) * (S + 1));
+    s.Seff = single ? 1 : S;
+    // output tile: wide layers use 64 accumulators per thread; the packed rows of ONE input
+    // (R x (OT+4) floats) must fit the shared-memory budget at least once
+    int OT = O >= 48 ? 64 : (O > 16 ? 32 : 16);
+    while (OT > 16 && (size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) OT >>= 1;
+    if ((size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) return HOL_EUNSUPPORTED;
+    s.OT = OT;
+    s.OTP = OT + 4;
+    s.nOT = (O + OT - 1) / OT;
+    s.srow = single ? 0 : s.OTP;
+    for (int j = 0; j < HOL_MAX_N; ++j) s.jrow[j] = 0;
+    for (int j = 0; j < n; ++j) {
+        int row0;
+        if (single)
+            row0 = 0;
+        else if (disc)
+            row0 = j * S;
+        else
+            row0 = (j < n - 1) ? j * (S + 1) : 1;  // last node of segment s == first node of s+1
+        s.jrow[j] = row0 * s.OTP;
+    }
+    s.length = length;
+    s.half = (float)(0.5 * (double)length);
+    s.periodic = !isnan(periodicity);
+    s.periodicity = s.periodic ? periodicity : 0.0f;
+    s.half_per = (float)(0.5 * (double)s.periodicity);
+    s.two_per = (float)(2.0 * (double)s.periodicity);
+    if (nodes_host) {
+        for (int j = 0; j < n; ++j) s.tab.X[j] = nodes_host[j];
+        for (int j = 0; j < n; ++j) {
+            double prod = 1.0;
+            for (int m = 0; m < n; ++m)
+                if (m != j) prod *= (double)(float)(nodes_host[j] - nodes_host[m]);  // fp32 denominators like the reference
+            s.tab.C[j] = (float)(1.0 / prod);
+        }
+    }
+    return HOL_OK;
+}
+
+size_t carve(const PwShape& s, void* base, PwWorkspace& ws, bool conv) {
+    size_t off = 0;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return p ? p + o : (char*)nullptr;
+    };
+    ws.xl_t = (float*)take((size_t)s.I * s.Bp * sizeof(float));
+    ws.seg_t = (uint16_t*)take((size_t)s.I * s.Bp * sizeof(uint16_t));
+    ws.wk = (float*)take((size_t)s.nOT * s.I * s.R * s.OTP * sizeof(float));
+    ws.order = (uint32_t*)take((size_t)s.I * s.Bp * sizeof(uint32_t));
+    ws.offs = (uint32_t*)take((size_t)s.I * (s.Seff + 1) * sizeof(uint32_t));
+    ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
+    ws.total = off;
+    return off;
+}
+
+int conv_out(int H, int K, int stride, int padding, int dilation) {
+    return (H + 2 * padding - dilation * (K - 1) - 1) / stride + 1;
+}
+
+#define HOL_TRY(expr)               \
+    do {                            \
+        int _e = (expr);            \
+        if (_e != HOL_OK) return _e; \
+    } while (0)
+
+int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int dx_transposed, float* dw,
+                    cudaStream_t st) {
+    if (dx) {
+        if (s.n == 1) {
+            const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
+            cudaError_t e = cudaMemsetAsync(dx, 0, bytes, st);
+            if (e != cudaSuccess) return (int)e;
+        } else {
+            HOL_TRY(launch_backward_dx(s, ws, gy, dx, dx_transposed, st));
+        }
+    }
+    if (dw) {
+        HOL_TRY(launch_bucket_sort(s, ws, st));
+        HOL_TRY(launch_backward_dw(s, ws, gy, dw, st));
+    }
+    return HOL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hol_abi_version(void) { return HOL_ABI_VERSION; }
+
+const char* hol_error_string(int code) {
+    switch (code) {
+        case HOL_OK: return "ok";
+        case HOL_EINVAL: return "hol: invalid argument";
+        case HOL_EUNSUPPORTED: return "hol: shape outside the compiled envelope (n <= 10, segments <= 4096, rows must fit shared memory)";
+        case HOL_EWORKSPACE: return "hol: workspace too small (see hol_pw_workspace_bytes)";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "hol: unknown error";
+}
+
+size_t hol_pw_workspace_bytes(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous) {
+    PwShape s;
+    if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
+    PwWorkspace ws;
+    return carve(s, nullptr, ws, false);
+}
+
+int hol_pw_segment_index_i64(const float* x, int64_t* seg, int64_t count, int32_t S, float length, float periodicity,
+                             void* stream) {
+    if (count < 0 || S <= 0 || (count > 0 && (!x || !seg))) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, 1, 1, 1, 1, S, 1, length, periodicity, nullptr));
+    return launch_segment_index(x, seg, count, s, (cudaStream_t)stream);
+}
+
+int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, float* y, int64_t B, int32_t I,
+                       int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous, float periodicity,
+                       void* ws_ptr, size_t ws_bytes, void* stream) {
+    if (!x || !w || !nodes_host || !y || !ws_ptr) return B == 0 ? HOL_OK : HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
+    if (B == 0) return HOL_OK;
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    HOL_TRY(launch_prep_fc(x, s, ws, st));
+    HOL_TRY(launch_pack(w, s, ws, st));
+    return launch_forward(s, ws, y, st);
+}
+
+int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const float* nodes_host, float* dx, float* dw,
+                        int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
+                        float periodicity, void* ws_ptr, size_t ws_bytes, uint32_t flags, void* stream) {
+    if (!gy || !x || !w || !nodes_host || !ws_ptr) return B == 0 && !dw ? HOL_OK : HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        if (dw) {
+            cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)O * I * s.nb * 4, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return HOL_OK;
+    }
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    if (!(flags & HOL_WS_PREPARED)) {
+        HOL_TRY(launch_prep_fc(x, s, ws, st));
+        if (dx && n > 1) HOL_TRY(launch_pack(w, s, ws, st));
+    }
+    return backward_common(s, ws, gy, dx, 0, dw, st);
+}
+
+size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
+                                     int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
+                                     int32_t discontinuous) {
+    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return 0;
+    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
+    if (Ho <= 0 || Wo <= 0) return 0;
+    PwShape s;
+    if (make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
+    PwWorkspace ws;
+    return carve(s, nullptr, ws, true);
+}
+
+int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
+                              int32_t C, int32_t H, int32_t W, int32_t O, int32_t K, int32_t stride, int32_t padding,
+                              int32_t dilation, int32_t n, int32_t S, float length, int32_t discontinuous,
+                              float periodicity, void* ws_ptr, size_t ws_bytes, void* stream) {
+    if (!x || !w_fc || !nodes_host || !y_rows || !ws_ptr) return HOL_EINVAL;
+    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return HOL_EINVAL;
+    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
+    if (Ho <= 0 || Wo <= 0) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
+    if (s.B == 0) return HOL_OK;
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+    HOL_TRY(launch_pack(w_fc, s, ws, st));
+    return launch_forward(s, ws, y_rows, st);
+}
+
+int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float* w_fc, const float* nodes_host,
+                               float* dx, float* dw_fc, int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O,
+                               int32_t K, int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
+                               float length, int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes,
+                               uint32_t flags, void* stream) {
+    if (!gy_rows || !x || !w_fc || !nodes_host || !ws_ptr) return HOL_EINVAL;
+    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return HOL_EINVAL;
+    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
+    if (Ho <= 0 || Wo <= 0) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.B == 0) {
+        if (dw_fc) {
+            cudaError_t e = cudaMemsetAsync(dw_fc, 0, (size_t)O * s.I * s.nb * 4, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return HOL_OK;
+    }
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
+    if (!(flags & HOL_WS_PREPARED)) {
+        HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+        if (dx && n > 1) HOL_TRY(launch_pack(w_fc, s, ws, st));
+    }
+    HOL_TRY(backward_common(s, ws, gy_rows, dx ? ws.dx_rows : nullptr, 1, dw_fc, st));
+    if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+    return HOL_OK;
+}
+
+int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags) {
+    if (kind == 0) return 3;  // prep, pack, forward
+    int c = 0;
+    if (!(flags & HOL_WS_PREPARED)) c += 1 + ((want_dx && n > 1) ? 1 : 0);
+    if (want_dx && n > 1) c += 1;
+    if (want_dw) c += 2;  // bucket sort + dW (memsets are not kernels of ours)
+    (void)discontinuous;
+    return c;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// Input gradient
+//   dX[b,i] = sigma * length/(eta(s+1)-eta(s)) * sum_j phi'_j(xl) * t_j,
+//   t_j = sum_o gy[b,o] * Wk[i][row(j, s(b,i))][o]
+// (the backward autograd derives for PolynomialLayers.py:329-335 + Basis.py:492-512).
+//
+// Same mapping as the forward: one thread = one sample; a CTA owns BT samples x IT inputs and
+// streams every output tile of those IT inputs through shared memory (the same contiguous
+// packed blocks the forward stages).  The IT*N dot products t_j live in registers as fp32x2
+// pairs, so dX[b,i] has exactly one writer and a fixed summation order (no atomics).
+#include "kernels.cuh"
+
+struct DxParams {
+    const float* xl_t;
+    const uint16_t* seg_t;
+    const float* wk;
+    const float* gy;
+    float* dx;
+    int64_t B, Bp;
+    int I, O, R, nOT, stage_floats, srow, transposed, it_eff, nst;
+    int jrow[HOL_MAX_N];
+    float length, Sf;
+    BasisTab tab;
+};
+
+template <int N, int OT, int IT>
+__global__ void __launch_bounds__(256, 1) pw_dx_kernel(const __grid_constant__ DxParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
+    constexpr int OTP = OT + 4;
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int i0 = blockIdx.y * p.it_eff;  // it_eff <= IT: inputs per CTA that fit in shared memory
+    const int ni = min(p.it_eff, p.I - i0);
+    const int in_floats = p.R * OTP;
+    const uint32_t stage_bytes = (uint32_t)ni * (uint32_t)in_floats * 4u;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        const int stg = c % p.nst;
+        uint64_t* bar = &bars[stg];
+        mbar_expect_tx(bar, stage_bytes);
+        bulk_g2s(slab0 + (size_t)stg * p.stage_floats, p.wk + ((int64_t)c * p.I + i0) * in_floats, stage_bytes, bar);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (p.nst > 1 && p.nOT > 1) issue(1);
+    }
+
+    int rowoff[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        uint32_t sg = 0;
+        if (k < ni) sg = __ldg(p.seg_t + (int64_t)(i0 + k) * p.Bp + b);
+        rowoff[k] = (k < ni ? k : 0) * in_floats + (int)(sg & HOL_SEG_MASK) * p.srow;
+    }
+    float2 acc[IT][N];
+#pragma unroll
+    for (int k = 0; k < IT; ++k)
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[k][j] = make_float2(0.0f, 0.0f);
+
+    const bool rowok = b < p.B;
+    const bool vec = (p.O & 3) == 0;
+    const float* gyrow = p.gy + (rowok ? b : 0) * p.O;
+
+    for (int c = 0; c < p.nOT; ++c) {
+        mbar_wait(&bars[c % p.nst], (uint32_t)((c / p.nst) & 1));
+        const float* slab = slab0 + (size_t)(c % p.nst) * p.stage_floats;
+#pragma unroll 1
+        for (int qb = 0; qb < OT / 16; ++qb) {
+            float4 g[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int o = c * OT + qb * 16 + 4 * t;
+                g[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (rowok) {
+                    if (vec && o + 3 < p.O) {
+                        g[t] = __ldg(reinterpret_cast<const float4*>(gyrow + o));
+                    } else {
+                        if (o + 0 < p.O) g[t].x = __ldg(gyrow + o + 0);
+                        if (o + 1 < p.O) g[t].y = __ldg(gyrow + o + 1);
+                        if (o + 2 < p.O) g[t].z = __ldg(gyrow + o + 2);
+                        if (o + 3 < p.O) g[t].w = __ldg(gyrow + o + 3);
+                    }
+                }
+            }
+            const float* slabq = slab + qb * 16;
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                if (k >= ni) break;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const float4* wp = reinterpret_cast<const float4*>(slabq + rowoff[k] + p.jrow[j]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float4 w = wp[t];
+                        acc[k][j] = ffma2v(make_float2(g[t].x, g[t].y), make_float2(w.x, w.y), acc[k][j]);
+                        acc[k][j] = ffma2v(make_float2(g[t].z, g[t].w), make_float2(w.z, w.w), acc[k][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && c + p.nst < p.nOT) issue(c + p.nst);
+    }
+
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        if (k >= ni) break;
+        const int64_t idx = (int64_t)(i0 + k) * p.Bp + b;
+        const float xl = __ldg(p.xl_t + idx);
+        const uint32_t sg = __ldg(p.seg_t + idx);
+        float dphi[N];
+        lagrange_basis_derivative<N>(xl, p.tab, dphi);
+        float t = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) t = fmaf(dphi[j], acc[k][j].x + acc[k][j].y, t);
+        const int s = (int)(sg & HOL_SEG_MASK);
+        const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
+        const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
+        float chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
+        if (sg & HOL_SEG_MIRROR) chain = -chain;
+        float out = (sg & HOL_SEG_INVALID) ? 0.0f : t * chain;
+        if (p.transposed) {
+            p.dx[idx] = out;
+        } else if (rowok) {
+            p.dx[b * p.I + i0 + k] = out;
+        }
+    }
+}
+
+template <int N>
+struct DxTile {
+    static constexpr int IT = N <= 2 ? 16 : (N <= 5 ? 8 : 4);
+};
+
+template <int N, int OT>
+static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int transposed,
+                       cudaStream_t st) {
+    constexpr int OTP = OT + 4;
+    constexpr int IT = DxTile<N>::IT;
+    const size_t in_bytes = (size_t)s.R * OTP * 4;
+    int it_eff = IT, nst = 2;
+    while (it_eff > 1 && 128 + 2 * (size_t)it_eff * in_bytes > HOL_SMEM_BUDGET) --it_eff;
+    if (128 + 2 * (size_t)it_eff * in_bytes > HOL_SMEM_BUDGET) nst = 1;
+    const size_t smem = 128 + (size_t)nst * it_eff * in_bytes;
+    if (smem > HOL_SMEM_BUDGET) return HOL_EUNSUPPORTED;
+    DxParams p;
+    p.xl_t = ws.xl_t;
+    p.seg_t = ws.seg_t;
+    p.wk = ws.wk;
+    p.gy = gy;
+    p.dx = dx;
+    p.B = s.B;
+    p.Bp = s.Bp;
+    p.I = s.I;
+    p.O = s.O;
+    p.R = s.R;
+    p.nOT = s.nOT;
+    p.stage_floats = it_eff * s.R * OTP;
+    p.it_eff = it_eff;
+    p.nst = nst;
+    p.srow = s.srow;
+    p.transposed = transposed;
+    for (int j = 0; j < HOL_MAX_N; ++j) p.jrow[j] = s.jrow[j];
+    p.length = s.length;
+    p.Sf = (float)s.S;
+    p.tab = s.tab;
+    int BT;
+    if (s.Bp % 512 != 0) {
+        BT = (int)s.Bp;
+    } else {
+        BT = 256;
+        if ((s.Bp / BT) * ((s.I + it_eff - 1) / it_eff) < 2 * 148) BT = 128;
+    }
+    auto kern = pw_dx_kernel<N, OT, IT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)(s.Bp / BT), (unsigned)((s.I + it_eff - 1) / it_eff));
+    kern<<<grid, BT, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <int N>
+static int launch_dx_n(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int transposed,
+                       cudaStream_t st) {
+    switch (s.OT) {
+        case 64: return launch_dx_t<N, 64>(s, ws, gy, dx, transposed, st);
+        case 32: return launch_dx_t<N, 32>(s, ws, gy, dx, transposed, st);
+        case 16: return launch_dx_t<N, 16>(s, ws, gy, dx, transposed, st);
+    }
+    return HOL_EUNSUPPORTED;
+}
+
+int launch_backward_dx(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int transposed,
+                       cudaStream_t st) {
+    switch (s.n) {
+        case 2: return launch_dx_n<2>(s, ws, gy, dx, transposed, st);
+        case 3: return launch_dx_n<3>(s, ws, gy, dx, transposed, st);
+        case 4: return launch_dx_n<4>(s, ws, gy, dx, transposed, st);
+        case 5: return launch_dx_n<5>(s, ws, gy, dx, transposed, st);
+        case 6: return launch_dx_n<6>(s, ws, gy, dx, transposed, st);
+        case 7: return launch_dx_n<7>(s, ws, gy, dx, transposed, st);
+        case 8: return launch_dx_n<8>(s, ws, gy, dx, transposed, st);
+        case 9: return launch_dx_n<9>(s, ws, gy, dx, transposed, st);
+        case 10: return launch_dx_n<10>(s, ws, gy, dx, transposed, st);
+    }
+    return HOL_EUNSUPPORTED;  // n == 1 has dX == 0 and is handled by the caller (memset)
+}

@@ -1,0 +1,212 @@
+// Fused forward contraction  y[b,o] = sum_i sum_j phi_j(xl(b,i)) * Wk[i][row(j, s(b,i))][o].
+//
+// Mapping (sm_100a): one thread = one sample, OT output accumulators in registers (packed
+// fp32x2 FMAs), one CTA = BT samples x one output tile.  The packed weights of IC inputs are
+// staged in shared memory by the TMA engine (1-D bulk copies, double buffered, mbarrier
+// completion).  The lanes of a warp read the SAME basis row j and column chunk of DIFFERENT
+// segments: rows of neighbouring segments are adjacent with a pitch of OT+4 floats, so the (up
+// to 8) distinct 16-byte chunks a warp touches per LDS.128 sit in distinct banks and samples
+// that share a segment are served by the shared-memory broadcast.
+#include "kernels.cuh"
+
+struct FwdParams {
+    const float* xl_t;
+    const uint16_t* seg_t;
+    const float* wk;
+    float* y;
+    int64_t B, Bp;
+    int I, O, R, IC, stage_floats, srow, nst;
+    int jrow[HOL_MAX_N];
+    BasisTab tab;
+};
+
+template <int N, int OT>
+__device__ __forceinline__ void fwd_one(float xl, uint32_t sg, const float* slab_i, float2 (&acc)[OT / 2],
+                                        const FwdParams& p) {
+    float phi[N];
+    lagrange_basis<N>(xl, p.tab, phi);
+    const float keep = (sg & HOL_SEG_INVALID) ? 0.0f : 1.0f;
+    const float* r0 = slab_i + (sg & HOL_SEG_MASK) * p.srow;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float ph = phi[j] * keep;
+        const float4* rj = reinterpret_cast<const float4*>(r0 + p.jrow[j]);
+#pragma unroll
+        for (int q = 0; q < OT / 4; ++q) {
+            const float4 w = rj[q];
+            acc[2 * q] = ffma2(ph, make_float2(w.x, w.y), acc[2 * q]);
+            acc[2 * q + 1] = ffma2(ph, make_float2(w.z, w.w), acc[2 * q + 1]);
+        }
+    }
+}
+
+template <int N, int OT>
+__global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
+    constexpr int OTP = OT + 4;
+    constexpr int G = 4;
+    const int tid = threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int ot = blockIdx.y;
+    const int in_floats = p.R * OTP;
+    const float* wk_ot = p.wk + (int64_t)ot * p.I * in_floats;
+    const int nchunks = (p.I + p.IC - 1) / p.IC;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        const int i0 = c * p.IC;
+        const int ni = min(p.IC, p.I - i0);
+        const uint32_t bytes = (uint32_t)ni * (uint32_t)in_floats * 4u;
+        const int stg = c % p.nst;
+        uint64_t* bar = &bars[stg];
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(slab0 + (size_t)stg * p.stage_floats, wk_ot + (int64_t)i0 * in_floats, bytes, bar);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (p.nst > 1 && nchunks > 1) issue(1);
+    }
+
+    float2 acc[OT / 2];
+#pragma unroll
+    for (int q = 0; q < OT / 2; ++q) acc[q] = make_float2(0.0f, 0.0f);
+
+    const float* xlp = p.xl_t + b;
+    const uint16_t* sgp = p.seg_t + b;
+    float xr[G];
+    uint32_t sr[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        xr[k] = 0.0f;
+        sr[k] = HOL_SEG_INVALID;
+        if (k < p.I) {
+            xr[k] = __ldg(xlp + (int64_t)k * p.Bp);
+            sr[k] = __ldg(sgp + (int64_t)k * p.Bp);
+        }
+    }
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int i0 = c * p.IC;
+        const int ni = min(p.IC, p.I - i0);
+        mbar_wait(&bars[c % p.nst], (uint32_t)((c / p.nst) & 1));
+        const float* slab = slab0 + (size_t)(c % p.nst) * p.stage_floats;
+        for (int g0 = 0; g0 < ni; g0 += G) {
+            // after an input is consumed its registers are refilled with the coordinates of the
+            // same slot of the next group (possibly the head of the next chunk): the loads have a
+            // whole group of compute to land
+            const int nbase = (g0 + G < ni) ? i0 + g0 + G : i0 + ni;
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                if (g0 + k < ni) fwd_one<N, OT>(xr[k], sr[k], slab + (size_t)(g0 + k) * in_floats, acc, p);
+                const int ii = nbase + k;
+                xr[k] = 0.0f;
+                sr[k] = HOL_SEG_INVALID;
+                if (ii < p.I) {
+                    xr[k] = __ldg(xlp + (int64_t)ii * p.Bp);
+                    sr[k] = __ldg(sgp + (int64_t)ii * p.Bp);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage before it is refilled
+        if (tid == 0 && c + p.nst < nchunks) issue(c + p.nst);
+    }
+
+    if (b < p.B) {
+        float* yrow = p.y + b * p.O + (int64_t)ot * OT;
+        const int o0 = ot * OT;
+        const bool vec = (p.O & 3) == 0;
+#pragma unroll
+        for (int q = 0; q < OT / 4; ++q) {
+            const int o = o0 + 4 * q;
+            if (vec && o + 3 < p.O) {
+                *reinterpret_cast<float4*>(yrow + 4 * q) =
+                    make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+            } else {
+                if (o + 0 < p.O) yrow[4 * q + 0] = acc[2 * q].x;
+                if (o + 1 < p.O) yrow[4 * q + 1] = acc[2 * q].y;
+                if (o + 2 < p.O) yrow[4 * q + 2] = acc[2 * q + 1].x;
+                if (o + 3 < p.O) yrow[4 * q + 3] = acc[2 * q + 1].y;
+            }
+        }
+    }
+}
+
+template <int N, int OT>
+static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream_t st) {
+    constexpr int OTP = OT + 4;
+    FwdParams p;
+    p.xl_t = ws.xl_t;
+    p.seg_t = ws.seg_t;
+    p.wk = ws.wk;
+    p.y = y;
+    p.B = s.B;
+    p.Bp = s.Bp;
+    p.I = s.I;
+    p.O = s.O;
+    p.R = s.R;
+    p.srow = s.srow;
+    for (int j = 0; j < HOL_MAX_N; ++j) p.jrow[j] = s.jrow[j];
+    p.tab = s.tab;
+    const size_t in_bytes = (size_t)s.R * OTP * 4;
+    int nst = 2;
+    int IC = (int)((HOL_SMEM_BUDGET - 128) / 2 / in_bytes);
+    if (IC < 1) {
+        nst = 1;
+        IC = (int)((HOL_SMEM_BUDGET - 128) / in_bytes);
+    }
+    if (IC < 1) return HOL_EUNSUPPORTED;
+    if (IC > s.I) IC = s.I;
+    if (IC > 16) IC = 16;
+    if (IC >= 4) IC &= ~3;
+    p.IC = IC;
+    p.stage_floats = IC * s.R * OTP;
+    p.nst = nst;
+    const size_t smem = 128 + (size_t)nst * p.stage_floats * 4;
+    // block = samples per CTA: the largest tile that still gives >= 2 waves on 148 SMs
+    int BT;
+    if (s.Bp % 512 != 0) {
+        BT = (int)s.Bp;  // small batch: Bp <= 256, multiple of 32
+    } else {
+        BT = 512;
+        while (BT > 128 && (s.Bp / BT) * s.nOT < 2 * 148) BT >>= 1;
+    }
+    auto kern = pw_fwd_kernel<N, OT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)(s.Bp / BT), (unsigned)s.nOT);
+    kern<<<grid, BT, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <int N>
+static int launch_fwd_n(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream_t st) {
+    switch (s.OT) {
+        case 64: return launch_fwd_t<N, 64>(s, ws, y, st);
+        case 32: return launch_fwd_t<N, 32>(s, ws, y, st);
+        case 16: return launch_fwd_t<N, 16>(s, ws, y, st);
+    }
+    return HOL_EUNSUPPORTED;
+}
+
+int launch_forward(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream_t st) {
+    switch (s.n) {
+        case 1: return launch_fwd_n<1>(s, ws, y, st);
+        case 2: return launch_fwd_n<2>(s, ws, y, st);
+        case 3: return launch_fwd_n<3>(s, ws, y, st);
+        case 4: return launch_fwd_n<4>(s, ws, y, st);
+        case 5: return launch_fwd_n<5>(s, ws, y, st);
+        case 6: return launch_fwd_n<6>(s, ws, y, st);
+        case 7: return launch_fwd_n<7>(s, ws, y, st);
+        case 8: return launch_fwd_n<8>(s, ws, y, st);
+        case 9: return launch_fwd_n<9>(s, ws, y, st);
+        case 10: return launch_fwd_n<10>(s, ws, y, st);
+    }
+    return HOL_EUNSUPPORTED;
+}

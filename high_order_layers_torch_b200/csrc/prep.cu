@@ -1,0 +1,306 @@
+// HBM-bound helper stages: local-coordinate prep (bit-exact segment index), weight packing,
+// stable per-input bucket sort for dW, col2im for the conv input gradient.
+#include "kernels.cuh"
+
+// ---------------------------------------------------------------------------------------
+// the reference's elementwise recipe, op for op (each fp32 op rounded separately, no FMA
+// contraction: the *_rn intrinsics are never fused)
+//   make_periodic ........ utils.py:74-79
+//   segment index ........ PolynomialLayers.py:299-303
+//   _eta, x_in ........... PolynomialLayers.py:329-344
+// ---------------------------------------------------------------------------------------
+struct PrepConst {
+    float length, half, Sf, half_per, two_per, per;
+    int S, periodic;
+};
+
+static PrepConst make_prep_const(const PwShape& s) {
+    PrepConst c;
+    c.length = s.length;
+    c.half = s.half;
+    c.Sf = (float)s.S;
+    c.half_per = s.half_per;
+    c.two_per = s.two_per;
+    c.per = s.periodicity;
+    c.S = s.S;
+    c.periodic = s.periodic;
+    return c;
+}
+
+__device__ __forceinline__ float fold_periodic(float xv, const PrepConst& c, uint32_t& flags) {
+    float xp = __fadd_rn(xv, c.half_per);
+    float r = fmodf(xp, c.two_per);  // exact; torch.remainder = fmod + sign fix-up
+    if (r != 0.0f && ((r < 0.0f) != (c.two_per < 0.0f))) r = __fadd_rn(r, c.two_per);
+    if (r > c.per) {
+        r = __fsub_rn(c.two_per, r);
+        flags |= HOL_SEG_MIRROR;
+    }
+    return __fsub_rn(r, c.half_per);
+}
+
+__device__ __forceinline__ int segment_of(float xv, const PrepConst& c) {
+    float v = __fmul_rn(__fdiv_rn(__fadd_rn(xv, c.half), c.length), c.Sf);
+    // .long() truncates toward zero, clamp(0, S-1) follows; NaN -> 0 like the reference on CPU
+    return (v >= c.Sf) ? c.S - 1 : (v > 0.0f ? (int)v : 0);
+}
+
+__device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& xl, uint32_t& sg) {
+    uint32_t flags = 0;
+    if (c.periodic) xv = fold_periodic(xv, c, flags);
+    int s = segment_of(xv, c);
+    float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, c.Sf), 2.0f), 1.0f);
+    float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), c.Sf), 2.0f), 1.0f);
+    float de = __fsub_rn(e1, e0);
+    xl = __fsub_rn(__fmul_rn(c.length, __fdiv_rn(__fsub_rn(xv, e0), de)), c.half);
+    sg = (uint32_t)s | flags;
+}
+
+__global__ void __launch_bounds__(256) pw_segment_index_kernel(const float* __restrict__ x, int64_t* __restrict__ seg,
+                                                               int64_t count, PrepConst c) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (; k < count; k += step) {
+        float xv = x[k];
+        uint32_t flags = 0;
+        if (c.periodic) xv = fold_periodic(xv, c, flags);
+        seg[k] = (int64_t)segment_of(xv, c);
+    }
+}
+
+// x[B, I] -> xl_t[I][Bp], seg_t[I][Bp] (transposed so that the contraction kernels, whose
+// lanes are samples, read them coalesced).  32x32 tile through shared memory.
+__global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict__ x, float* __restrict__ xl_t,
+                                                         uint16_t* __restrict__ seg_t, int64_t B, int64_t Bp, int I,
+                                                         PrepConst c) {
+    __shared__ float t_xl[32][33];
+    __shared__ uint16_t t_sg[32][34];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t b = b0 + r;
+        const int i = i0 + tx;
+        float xl = 0.0f;
+        uint32_t sg = HOL_SEG_INVALID;
+        if (i < I && b < B) prep_elem(x[b * I + i], c, xl, sg);
+        t_xl[tx][r] = xl;
+        t_sg[tx][r] = (uint16_t)sg;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r;
+        const int64_t b = b0 + tx;
+        if (i < I) {
+            xl_t[(int64_t)i * Bp + b] = t_xl[r][tx];
+            seg_t[(int64_t)i * Bp + b] = t_sg[r][tx];
+        }
+    }
+}
+
+// Implicit im2col: row = (b, ho, wo), input i = (c, kh, kw).  Taps that fall into the zero
+// padding are flagged invalid (the reference pads the expanded tensor, so they add nothing).
+struct ConvGeom {
+    int C, H, W, K, stride, padding, dilation, Ho, Wo;
+};
+
+__global__ void __launch_bounds__(256) pw_prep_conv_kernel(const float* __restrict__ x, float* __restrict__ xl_t,
+                                                           uint16_t* __restrict__ seg_t, int64_t rows, int64_t Bp,
+                                                           ConvGeom g, PrepConst c) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (row >= Bp) return;
+    float xl = 0.0f;
+    uint32_t sg = HOL_SEG_INVALID;
+    if (row < rows) {
+        const int kw = i % g.K, kh = (i / g.K) % g.K, ch = i / (g.K * g.K);
+        const int wo = (int)(row % g.Wo);
+        const int64_t t = row / g.Wo;
+        const int ho = (int)(t % g.Ho);
+        const int64_t b = t / g.Ho;
+        const int h = ho * g.stride - g.padding + kh * g.dilation;
+        const int w = wo * g.stride - g.padding + kw * g.dilation;
+        if (h >= 0 && h < g.H && w >= 0 && w < g.W) prep_elem(x[((b * g.C + ch) * g.H + h) * g.W + w], c, xl, sg);
+    }
+    xl_t[(int64_t)i * Bp + row] = xl;
+    seg_t[(int64_t)i * Bp + row] = (uint16_t)sg;
+}
+
+// dx[b,c,h,w] = sum over the (kh,kw) taps that read this pixel of dx_t[(c,kh,kw)][row].
+__global__ void __launch_bounds__(256) pw_col2im_kernel(const float* __restrict__ dx_t, float* __restrict__ dx,
+                                                        int64_t total, int64_t Bp, ConvGeom g) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int w = (int)(e % g.W);
+    int64_t t = e / g.W;
+    const int h = (int)(t % g.H);
+    t /= g.H;
+    const int ch = (int)(t % g.C);
+    const int64_t b = t / g.C;
+    float acc = 0.0f;
+    for (int kh = 0; kh < g.K; ++kh) {
+        const int hn = h + g.padding - kh * g.dilation;
+        if (hn < 0 || hn % g.stride) continue;
+        const int ho = hn / g.stride;
+        if (ho >= g.Ho) continue;
+        for (int kw = 0; kw < g.K; ++kw) {
+            const int wn = w + g.padding - kw * g.dilation;
+            if (wn < 0 || wn % g.stride) continue;
+            const int wo = wn / g.stride;
+            if (wo >= g.Wo) continue;
+            const int i = (ch * g.K + kh) * g.K + kw;
+            acc += dx_t[(int64_t)i * Bp + ((b * g.Ho + ho) * g.Wo + wo)];
+        }
+    }
+    dx[e] = acc;
+}
+
+// w[O][I][nb] -> wk[nOT][I][R][OTP].  Packed row r = (c, a) = (r / RS, r % RS) holds reference
+// column v = a*stride + c; for continuous layers the shared end node of segment a-1 / a is the
+// single row (0, a) and rows (c >= 1, a == S) are padding.  Pad rows/columns are zero.
+__global__ void __launch_bounds__(256) pw_pack_kernel(const float* __restrict__ w, float* __restrict__ wk, int I, int O,
+                                                      int nb, int stride, int S, int RS, int R, int OT, int OTP) {
+    __shared__ float tile[64][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x, ot = blockIdx.y, r0 = blockIdx.z * 32;
+    const int o0 = ot * OT;
+    {
+        const int r = r0 + tx;
+        const int cg = r / RS, a = r % RS;
+        const int v = a * stride + cg;
+        const bool ok = r < R && v < nb && (a < S || cg == 0);
+        for (int ol = ty; ol < OT; ol += 8) {
+            float val = 0.0f;
+            if (ok && o0 + ol < O) val = w[((int64_t)(o0 + ol) * I + i) * nb + v];
+            tile[ol][tx] = val;
+        }
+    }
+    __syncthreads();
+    for (int rl = ty; rl < 32; rl += 8) {
+        const int r = r0 + rl;
+        if (r >= R) continue;
+        float* dst = wk + (((int64_t)ot * I + i) * R + r) * OTP;
+        for (int ol = tx; ol < OTP; ol += 32) dst[ol] = ol < OT ? tile[ol][rl] : 0.0f;
+    }
+}
+
+// Stable counting sort of the samples of one input by segment (one CTA per input).  The
+// order inside a bucket is the sample order, so the dW reduction order is fixed run to run.
+__global__ void __launch_bounds__(32 * HOL_WARPS_SORT)
+    pw_bucket_sort_kernel(const uint16_t* __restrict__ seg_t, uint32_t* __restrict__ order, uint32_t* __restrict__ offs,
+                          int64_t B, int64_t Bp, int Seff, int single_bucket) {
+    extern __shared__ uint32_t cnt[];  // [HOL_WARPS_SORT][Seff]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i = blockIdx.x;
+    const uint16_t* sg = seg_t + (int64_t)i * Bp;
+    uint32_t* ord = order + (int64_t)i * Bp;
+    for (int k = tid; k < HOL_WARPS_SORT * Seff; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    const int64_t ngroups = (B + 31) / 32;
+    const int64_t gper = (ngroups + HOL_WARPS_SORT - 1) / HOL_WARPS_SORT;
+    const int64_t g_lo = warp * gper;
+    const int64_t g_hi = g_lo + gper < ngroups ? g_lo + gper : ngroups;
+    uint32_t* mycnt = cnt + warp * Seff;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int64_t gidx = g_lo; gidx < g_hi; ++gidx) {
+        const int64_t b = gidx * 32 + lane;
+        const uint32_t v = b < B ? sg[b] : HOL_SEG_INVALID;
+        const bool valid = !(v & HOL_SEG_INVALID);
+        const uint32_t key = single_bucket ? 0u : (v & HOL_SEG_MASK);
+        const uint32_t mask = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+        if (valid && (mask & lt) == 0) mycnt[key] += __popc(mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t carry = 0;
+        for (int s0 = 0; s0 < Seff; s0 += 32) {
+            const int s = s0 + lane;
+            uint32_t tot = 0;
+            if (s < Seff)
+                for (int w = 0; w < HOL_WARPS_SORT; ++w) tot += cnt[w * Seff + s];
+            uint32_t incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (s < Seff) {
+                uint32_t off = carry + incl - tot;
+                offs[(int64_t)i * (Seff + 1) + s] = off;
+                for (int w = 0; w < HOL_WARPS_SORT; ++w) {
+                    const uint32_t t = cnt[w * Seff + s];
+                    cnt[w * Seff + s] = off;
+                    off += t;
+                }
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) offs[(int64_t)i * (Seff + 1) + Seff] = carry;
+    }
+    __syncthreads();
+    for (int64_t gidx = g_lo; gidx < g_hi; ++gidx) {
+        const int64_t b = gidx * 32 + lane;
+        const uint32_t v = b < B ? sg[b] : HOL_SEG_INVALID;
+        const bool valid = !(v & HOL_SEG_INVALID);
+        const uint32_t key = single_bucket ? 0u : (v & HOL_SEG_MASK);
+        const uint32_t mask = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+        const uint32_t cur = valid ? mycnt[key] : 0u;
+        __syncwarp();
+        if (valid && (mask & lt) == 0) mycnt[key] = cur + __popc(mask);
+        __syncwarp();
+        if (valid) ord[cur + __popc(mask & lt)] = (uint32_t)b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwShape& s, cudaStream_t st) {
+    if (count == 0) return HOL_OK;
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pw_segment_index_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, seg, count, make_prep_const(s));
+    return (int)cudaGetLastError();
+}
+
+int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
+    dim3 grid((unsigned)(s.Bp / 32), (unsigned)((s.I + 31) / 32));
+    pw_prep_fc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s));
+    return (int)cudaGetLastError();
+}
+
+int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int C, int H, int W, int K, int stride,
+                     int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
+    ConvGeom g{C, H, W, K, stride, padding, dilation, Ho, Wo};
+    dim3 grid((unsigned)((s.Bp + 255) / 256), (unsigned)s.I);
+    pw_prep_conv_kernel<<<grid, 256, 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, g, make_prep_const(s));
+    return (int)cudaGetLastError();
+}
+
+int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, int C, int H, int W, int K, int stride,
+                  int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
+    ConvGeom g{C, H, W, K, stride, padding, dilation, Ho, Wo};
+    const int64_t total = Bimg * C * H * W;
+    if (total == 0) return HOL_OK;
+    pw_col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dx_t, dx, total, Bp, g);
+    return (int)cudaGetLastError();
+}
+
+int launch_pack(const float* w, const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
+    dim3 grid((unsigned)s.I, (unsigned)s.nOT, (unsigned)((s.R + 31) / 32));
+    pw_pack_kernel<<<grid, dim3(32, 8), 0, st>>>(w, ws.wk, s.I, s.O, s.nb, s.stride, s.S, s.RS, s.R, s.OT, s.OTP);
+    return (int)cudaGetLastError();
+}
+
+int launch_bucket_sort(const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
+    const size_t smem = (size_t)HOL_WARPS_SORT * s.Seff * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pw_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    pw_bucket_sort_kernel<<<(unsigned)s.I, 32 * HOL_WARPS_SORT, smem, st>>>(ws.seg_t, ws.order, ws.offs, s.B, s.Bp, s.Seff,
+                                                                           (!s.disc && s.n == 1) ? 1 : 0);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,73 @@
+"""Layer registries and factories with the reference's names and error behaviour
+(reference layers.py:258-295, :357-372) restricted to the hot path: the keys ``continuous`` /
+``discontinuous`` (fully connected) and ``continuous2d`` (convolution).  Asking for any other key
+raises the same ValueError the reference raises for an unknown layer type."""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from .FunctionalConvolution import PiecewisePolynomialConvolution2d
+from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial
+from .utils import max_abs_normalization, max_abs_normalization_nd
+
+
+class MaxAbsNormalization(nn.Module):
+    """x / (max|x| + eps) per sample, the normalisation HighOrderMLP puts between layers
+    (reference layers.py:70-81)."""
+
+    def __init__(self, eps: float = 1e-6, dim: int = 1):
+        super().__init__()
+        self._eps = eps
+        self._dim = dim
+
+    def forward(self, x):
+        return max_abs_normalization(x, eps=self._eps, dim=self._dim)
+
+
+class MaxAbsNormalizationND(nn.Module):
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self._eps = eps
+
+    def forward(self, x):
+        return max_abs_normalization_nd(x, eps=self._eps)
+
+
+class SumLayer(nn.Module):
+    """Sum of the outputs of several layers on the same input (resnet option of HighOrderMLP)."""
+
+    def __init__(self, layer_list):
+        super().__init__()
+        self.layer_list = nn.ModuleList(layer_list)
+
+    def forward(self, x):
+        out = self.layer_list[0](x)
+        for layer in self.layer_list[1:]:
+            out = out + layer(x)
+        return out
+
+
+normalization_layers = {"max_abs": MaxAbsNormalization}
+
+fc_layers = {
+    "continuous": PiecewisePolynomial,
+    "discontinuous": PiecewiseDiscontinuousPolynomial,
+}
+
+convolutional_layers = {
+    "continuous2d": PiecewisePolynomialConvolution2d,
+}
+
+
+def high_order_fc_layers(layer_type: str, **kwargs):
+    if layer_type in fc_layers.keys():
+        return fc_layers[layer_type](**kwargs)
+    raise ValueError(
+        f"Fully connected layer type {layer_type} not recognized.  Must be one of {list(fc_layers.keys())}")
+
+
+def high_order_convolution_layers(layer_type: str, **kwargs):
+    if layer_type in convolutional_layers.keys():
+        return convolutional_layers[layer_type](**kwargs)
+    raise ValueError(
+        f"Convolutional layer type {layer_type} not recognized.  Must be one of {list(convolutional_layers.keys())}")

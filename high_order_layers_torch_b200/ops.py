@@ -1,0 +1,300 @@
+"""torch.library custom ops (namespace ``hol``) over the C-ABI CUDA library.
+
+These replace, for CUDA tensors, the chain of ATen calls the reference issues in
+``Piecewise.forward`` (reference PolynomialLayers.py:294-336, :639-676 -> Basis.py:492-512)
+and ``PiecewisePolynomialConvolution.forward`` (FunctionalConvolution.py:441-447), and the
+backward autograd derives for them.  CUDA dispatch only: there is no CPU kernel.
+
+PyTorch is plumbing here (device memory from the caching allocator, the current stream);
+the arithmetic happens in csrc/*.cu.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_NAN = float("nan")
+_node_cache: dict = {}
+
+
+def lobatto_nodes(n: int, length: float = 2.0) -> Tensor:
+    """Interpolation nodes as the reference builds them (LagrangePolynomial.py:9-22, :191-195):
+    ``(length/2) * -cos(pi*arange(n)/(n-1))`` evaluated by torch in fp32 on the CPU (n == 1 -> [0]).
+    Cached host tensor; the kernels receive it as a plain ``const float*``."""
+    key = (int(n), float(length))
+    t = _node_cache.get(key)
+    if t is None:
+        if n == 1:
+            base = torch.tensor([0.0], dtype=torch.float32, device="cpu")
+        else:
+            base = -torch.cos(torch.pi * torch.arange(n, device="cpu") / (n - 1))
+        t = ((length / 2.0) * base).to(torch.float32).contiguous()
+        _node_cache[key] = t
+    return t
+
+
+def _check_inputs(x: Tensor, w: Tensor, what: str):
+    if not x.is_cuda or not w.is_cuda:
+        raise RuntimeError(f"{what}: tensors must live on a CUDA device (this build has no CPU path)")
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise TypeError(f"{what}: float32 tensors required, got {x.dtype} / {w.dtype}")
+    if x.device != w.device:
+        raise RuntimeError(f"{what}: x on {x.device} but weights on {w.device}")
+
+
+def _stream(t: Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _per(periodicity: Optional[float]) -> float:
+    return _NAN if periodicity is None else float(periodicity)
+
+
+def _nb(n: int, segments: int, discontinuous: bool) -> int:
+    return n * segments if discontinuous else (n - 1) * segments + 1
+
+
+# ------------------------------------------------------------------------------------------
+# segment index (Piecewise.which_segment)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("hol::pw_segment_index", mutates_args=(), device_types="cuda")
+def pw_segment_index(x: Tensor, segments: int, length: float, periodicity: Optional[float]) -> Tensor:
+    if x.dtype != torch.float32:
+        raise TypeError("pw_segment_index: float32 input required")
+    lib = _lib.load()
+    xc = x.contiguous()
+    out = torch.empty(xc.shape, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_segment_index_i64(_ptr(xc), _ptr(out), xc.numel(), segments, length,
+                                                _per(periodicity), _stream(x)), "hol_pw_segment_index_i64")
+    return out
+
+
+@pw_segment_index.register_fake
+def _(x, segments, length, periodicity):
+    return torch.empty(x.shape, dtype=torch.int64, device=x.device)
+
+
+# ------------------------------------------------------------------------------------------
+# fully connected layer
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("hol::pw_forward", mutates_args=(), device_types="cuda")
+def pw_forward(x: Tensor, w: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+               periodicity: Optional[float]) -> Tuple[Tensor, Tensor]:
+    """-> (y[B, O], workspace).  The workspace keeps the prepared state (transposed local
+    coordinates, packed weights) for ``hol::pw_backward``."""
+    _check_inputs(x, w, "pw_forward")
+    if x.dim() != 2:
+        raise ValueError(f"pw_forward: x must be [batch, in_features], got {tuple(x.shape)}")
+    B, I = x.shape
+    O = w.shape[0]
+    if tuple(w.shape) != (O, I, _nb(n, segments, discontinuous)):
+        raise ValueError(f"pw_forward: weight shape {tuple(w.shape)} does not match "
+                         f"[out, {I}, {_nb(n, segments, discontinuous)}]")
+    lib = _lib.load()
+    xc, wc = x.contiguous(), w.contiguous()
+    nbytes = lib.hol_pw_workspace_bytes(B, I, O, n, segments, int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2 if (n > _lib.HOL_MAX_N or segments > _lib.HOL_MAX_SEGMENTS) else -1, "hol_pw_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    nodes = lobatto_nodes(n, 2.0)  # FC layers always build LagrangePoly(n) with length 2 (PolynomialLayers.py:234)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, I, O, n, segments, length,
+                                          int(discontinuous), _per(periodicity), _ptr(ws), nbytes, _stream(x)),
+                   "hol_pw_forward_f32")
+    return y, ws
+
+
+@pw_forward.register_fake
+def _(x, w, n, segments, length, discontinuous, periodicity):
+    return (torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device),
+            torch.empty((0,), dtype=torch.uint8, device=x.device))
+
+
+@torch.library.custom_op("hol::pw_backward", mutates_args=("ws",), device_types="cuda")
+def pw_backward(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, n: int, segments: int, length: float,
+                discontinuous: bool, periodicity: Optional[float], need_dx: bool, need_dw: bool,
+                ws_prepared: bool) -> Tuple[Tensor, Tensor]:
+    _check_inputs(x, w, "pw_backward")
+    B, I = x.shape
+    O = w.shape[0]
+    lib = _lib.load()
+    gyc, xc, wc = gy.contiguous(), x.contiguous(), w.contiguous()
+    dx = torch.empty_like(xc) if need_dx else torch.empty((0,), dtype=torch.float32, device=x.device)
+    dw = torch.empty_like(wc) if need_dw else torch.empty((0,), dtype=torch.float32, device=x.device)
+    nodes = lobatto_nodes(n, 2.0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes), _ptr(dx if need_dx else None),
+                                           _ptr(dw if need_dw else None), B, I, O, n, segments, length,
+                                           int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
+                                           _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                   "hol_pw_backward_f32")
+    return dx, dw
+
+
+@pw_backward.register_fake
+def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, need_dw, ws_prepared):
+    e = torch.empty((0,), dtype=torch.float32, device=x.device)
+    return (torch.empty_like(x) if need_dx else e, torch.empty_like(w) if need_dw else e)
+
+
+def _pw_setup(ctx, inputs, output):
+    x, w, n, segments, length, discontinuous, periodicity = inputs
+    _, ws = output
+    ctx.save_for_backward(x, w, ws)
+    ctx.args = (n, segments, length, discontinuous, periodicity)
+
+
+def _pw_bwd(ctx, gy, _gws):
+    x, w, ws = ctx.saved_tensors
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dx = dw = None
+    if need_dx or need_dw:
+        rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True)
+        dx = rdx if need_dx else None
+        dw = rdw if need_dw else None
+    return dx, dw, None, None, None, None, None
+
+
+pw_forward.register_autograd(_pw_bwd, setup_context=_pw_setup)
+
+
+def piecewise_polynomial(x: Tensor, w: Tensor, n: int, segments: int, length: float = 2.0,
+                         discontinuous: bool = False, periodicity: Optional[float] = None) -> Tensor:
+    """Functional form of the layer: y = Piecewise(n, segments)(x) with weights w[O, I, nb]."""
+    return pw_forward(x, w, n, segments, float(length), bool(discontinuous), periodicity)[0]
+
+
+# ------------------------------------------------------------------------------------------
+# unfolded 2-d convolution (rows = B*Ho*Wo, inputs = C*K*K)
+# ------------------------------------------------------------------------------------------
+def conv_out_size(h: int, k: int, stride: int, padding: int, dilation: int) -> int:
+    return (h + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+
+
+@torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=(), device_types="cuda")
+def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+                   periodicity: Optional[float], kernel_size: int, stride: int, padding: int,
+                   dilation: int) -> Tuple[Tensor, Tensor]:
+    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> (y_rows[B*Ho*Wo, O], workspace)."""
+    _check_inputs(x, w_fc, "pw_conv2d_rows")
+    if x.dim() != 4:
+        raise ValueError(f"pw_conv2d_rows: x must be [B, C, H, W], got {tuple(x.shape)}")
+    B, C, H, W = x.shape
+    O = w_fc.shape[0]
+    K = kernel_size
+    if tuple(w_fc.shape) != (O, C * K * K, _nb(n, segments, discontinuous)):
+        raise ValueError(f"pw_conv2d_rows: weight shape {tuple(w_fc.shape)} does not match the layer")
+    Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
+    if Ho <= 0 or Wo <= 0:
+        raise ValueError("pw_conv2d_rows: kernel does not fit the input")
+    lib = _lib.load()
+    xc, wc = x.contiguous(), w_fc.contiguous()
+    nbytes = lib.hol_pw_conv2d_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments,
+                                               int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((B * Ho * Wo, O), dtype=torch.float32, device=x.device)
+    nodes = lobatto_nodes(n, length)  # conv builds its basis with the layer's length (LagrangePolynomial.py:242-246)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_conv2d_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, C, H, W, O, K, stride,
+                                                 padding, dilation, n, segments, length, int(discontinuous),
+                                                 _per(periodicity), _ptr(ws), nbytes, _stream(x)),
+                   "hol_pw_conv2d_forward_f32")
+    return y, ws
+
+
+@pw_conv2d_rows.register_fake
+def _(x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
+    B, C, H, W = x.shape
+    Ho = conv_out_size(H, kernel_size, stride, padding, dilation)
+    Wo = conv_out_size(W, kernel_size, stride, padding, dilation)
+    return (torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device),
+            torch.empty((0,), dtype=torch.uint8, device=x.device))
+
+
+@torch.library.custom_op("hol::pw_conv2d_rows_backward", mutates_args=("ws",), device_types="cuda")
+def pw_conv2d_rows_backward(gy: Tensor, x: Tensor, w_fc: Tensor, ws: Tensor, n: int, segments: int, length: float,
+                            discontinuous: bool, periodicity: Optional[float], kernel_size: int, stride: int,
+                            padding: int, dilation: int, need_dx: bool, need_dw: bool,
+                            ws_prepared: bool) -> Tuple[Tensor, Tensor]:
+    _check_inputs(x, w_fc, "pw_conv2d_rows_backward")
+    B, C, H, W = x.shape
+    O = w_fc.shape[0]
+    lib = _lib.load()
+    gyc, xc, wc = gy.contiguous(), x.contiguous(), w_fc.contiguous()
+    dx = torch.empty_like(xc) if need_dx else torch.empty((0,), dtype=torch.float32, device=x.device)
+    dw = torch.empty_like(wc) if need_dw else torch.empty((0,), dtype=torch.float32, device=x.device)
+    nodes = lobatto_nodes(n, length)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_conv2d_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes),
+                                                  _ptr(dx if need_dx else None), _ptr(dw if need_dw else None), B, C,
+                                                  H, W, O, kernel_size, stride, padding, dilation, n, segments, length,
+                                                  int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
+                                                  _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                   "hol_pw_conv2d_backward_f32")
+    return dx, dw
+
+
+@pw_conv2d_rows_backward.register_fake
+def _(gy, x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation,
+      need_dx, need_dw, ws_prepared):
+    e = torch.empty((0,), dtype=torch.float32, device=x.device)
+    return (torch.empty_like(x) if need_dx else e, torch.empty_like(w_fc) if need_dw else e)
+
+
+def _conv_setup(ctx, inputs, output):
+    x, w_fc = inputs[0], inputs[1]
+    _, ws = output
+    ctx.save_for_backward(x, w_fc, ws)
+    ctx.args = tuple(inputs[2:])
+
+
+def _conv_bwd(ctx, gy, _gws):
+    x, w_fc, ws = ctx.saved_tensors
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dx = dw = None
+    if need_dx or need_dw:
+        rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ws, *ctx.args, need_dx, need_dw, True)
+        dx = rdx if need_dx else None
+        dw = rdw if need_dw else None
+    return (dx, dw) + (None,) * 9
+
+
+pw_conv2d_rows.register_autograd(_conv_bwd, setup_context=_conv_setup)
+
+
+def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
+                                length: float = 2.0, discontinuous: bool = False,
+                                periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
+                                dilation: int = 1, rescale: float = 1.0) -> Tensor:
+    """conv.weight[O, C*nb, K, K] layout in, NCHW out: the unfolded path of SURVEY 3.3."""
+    B, C, H, W = x.shape
+    O = weight.shape[0]
+    K = kernel_size
+    nb = _nb(n, segments, discontinuous)
+    w_fc = weight.view(O, C, nb, K, K).permute(0, 1, 3, 4, 2).reshape(O, C * K * K, nb)
+    y_rows, _ = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K, stride,
+                               padding, dilation)
+    Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
+    y = y_rows.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
+    if rescale != 1.0:
+        y = y * rescale
+    return y
+
+
+def launch_count(kind: int, n: int, discontinuous: bool, want_dx: bool, want_dw: bool, prepared: bool) -> int:
+    return _lib.load().hol_pw_launch_count(kind, n, int(discontinuous), int(want_dx), int(want_dw),
+                                           _lib.HOL_WS_PREPARED if prepared else 0)

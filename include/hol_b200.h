@@ -1,0 +1,127 @@
+/*
+ * hol_b200.h -- C ABI of the B200-native piecewise Lagrange-polynomial layer kernels.
+ *
+ * Drop-in boundary for the hot path of jloveric/high-order-layers-torch v2.6.0.  The
+ * reference is pure Python; the "FFI" these entry points replace is the chain of ATen
+ * calls issued by (paths relative to the reference checkout)
+ *
+ *   Piecewise.forward / PiecewiseDiscontinuous.forward
+ *       high_order_layers_torch/PolynomialLayers.py:294-336, :639-676
+ *   Basis.interpolate                   high_order_layers_torch/Basis.py:492-512
+ *   LagrangeBasis.__call__              high_order_layers_torch/LagrangePolynomial.py:205-211
+ *   make_periodic                       high_order_layers_torch/utils.py:74-79
+ *   PiecewiseExpand.__call__ + Expansion2d + nn.Conv2d
+ *       Basis.py:67-127, FunctionalConvolution.py:123-139, :441-447
+ *
+ * and their autograd-generated backward.  The binding a maintainer adds on the reference
+ * side (ctypes + torch.library) is shown in INTEGRATION.md and shipped in
+ * high_order_layers_torch_b200/_lib.py and ops.py.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success, a HOL_E* code (< 0) or a cudaError_t (> 0) otherwise;
+ *     hol_error_string() explains either;
+ *   - never throw, never allocate device memory, never synchronise, never touch the
+ *     default stream: every launch goes to `stream` (a cudaStream_t passed as void*);
+ *   - every buffer is a caller-owned DEVICE pointer, contiguous row-major, 16-byte aligned
+ *     (torch's caching allocator gives 512-byte alignment);
+ *   - re-entrant, no mutable global state (the node table is an argument); safe to call
+ *     from several host threads on different streams;
+ *   - fp32 arithmetic, fp32 accumulation, no fast-math; segment indices follow the
+ *     reference's three separately rounded fp32 ops + truncation + clamp bit for bit
+ *     (CPU semantics: true divisions), finite inputs only (NaN -> segment 0; +-inf is
+ *     undefined behaviour in the reference).
+ *
+ * Shapes: x[B, I], w[O, I, nb], y / gy[B, O], dx[B, I], dw[O, I, nb] with
+ *   nb = (n-1)*S + 1 (continuous: neighbouring segments share their end node) or
+ *   nb = n*S         (discontinuous),   1 <= n <= HOL_MAX_N, 1 <= S <= HOL_MAX_SEGMENTS.
+ * `nodes` are the n fp32 interpolation nodes built on the host with the reference's own
+ * expression (LagrangePolynomial.py:9-22, :191-195); they stay a HOST pointer.
+ * `periodicity` is NaN for "None".
+ */
+#ifndef HOL_B200_H
+#define HOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOL_ABI_VERSION 1
+#define HOL_MAX_N 10
+#define HOL_MAX_SEGMENTS 4096
+
+#define HOL_OK 0
+#define HOL_EINVAL (-1)        /* bad argument (null pointer, non-positive size, ...)      */
+#define HOL_EUNSUPPORTED (-2)  /* valid request outside the compiled envelope (n, S, smem) */
+#define HOL_EWORKSPACE (-3)    /* workspace too small (see hol_pw_workspace_bytes)          */
+
+/* flags for hol_pw_backward_f32 */
+#define HOL_WS_PREPARED 1u     /* `ws` still holds the forward's prepared state for the very
+                                  same (x, w, shape): skip the prep + pack stages           */
+
+int hol_abi_version(void);
+const char* hol_error_string(int code);
+
+/* Bytes of scratch the forward/backward pair needs for one layer call (same for both). */
+size_t hol_pw_workspace_bytes(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
+                              int32_t discontinuous);
+
+/* Piecewise.which_segment (PolynomialLayers.py:259-275): seg[k] = clamp(trunc(((x+half)/
+ * length)*S), 0, S-1) as int64, after the optional mirror-periodic fold.  Elementwise. */
+int hol_pw_segment_index_i64(const float* x, int64_t* seg, int64_t count, int32_t S,
+                             float length, float periodicity, void* stream);
+
+/* Piecewise.forward: y = sum_i sum_j phi_j(x_in(b,i)) * w[o, i, s(b,i)*stride + j].
+ * Leaves the prepared state (transposed local coordinates, packed weights) in `ws`. */
+int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, float* y,
+                       int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, float length,
+                       int32_t discontinuous, float periodicity, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* Backward of the above.  dx and/or dw may be NULL (gradient not needed).  dw is written
+ * densely (exact zeros where no sample touched a weight), dx includes the chain factors
+ * length/(eta(s+1)-eta(s)) and the +-1 of the periodic fold; dx == 0 for n == 1. */
+int hol_pw_backward_f32(const float* gy, const float* x, const float* w,
+                        const float* nodes_host, float* dx, float* dw, int64_t B, int32_t I,
+                        int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
+                        float periodicity, void* ws, size_t ws_bytes, uint32_t flags,
+                        void* stream);
+
+/* ---- unfolded PiecewisePolynomialConvolution2d (FunctionalConvolution.py:441-447) -------
+ * The convolution is the layer above applied to im2col rows: rows = Bimg*Ho*Wo,
+ * I = C*K*K (column c*K*K + kh*K + kw), w_fc[O, I, nb] = conv.weight[O, C*nb, K, K] viewed
+ * as [O, C, nb, K, K] and permuted to [O, C, K, K, nb].  The im2col matrix is never
+ * materialised: the prep stage reads x[Bimg, C, H, W] directly; zero-padded taps contribute
+ * nothing (the reference pads the *expanded* tensor).  y_rows[rows, O] / gy_rows[rows, O]
+ * are row-major over (b, ho, wo); dx is NCHW like x. */
+size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O,
+                                     int32_t K, int32_t stride, int32_t padding,
+                                     int32_t dilation, int32_t n, int32_t S,
+                                     int32_t discontinuous);
+
+int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* nodes_host,
+                              float* y_rows, int64_t Bimg, int32_t C, int32_t H, int32_t W,
+                              int32_t O, int32_t K, int32_t stride, int32_t padding,
+                              int32_t dilation, int32_t n, int32_t S, float length,
+                              int32_t discontinuous, float periodicity, void* ws,
+                              size_t ws_bytes, void* stream);
+
+int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float* w_fc,
+                               const float* nodes_host, float* dx, float* dw_fc, int64_t Bimg,
+                               int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
+                               int32_t stride, int32_t padding, int32_t dilation, int32_t n,
+                               int32_t S, float length, int32_t discontinuous,
+                               float periodicity, void* ws, size_t ws_bytes, uint32_t flags,
+                               void* stream);
+
+/* Number of kernel launches the last call of each kind issues for the given shape
+ * (what bench.py reports as gpu_launches).  kind: 0 forward, 1 backward(dx+dw). */
+int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx,
+                        int32_t want_dw, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOL_B200_H */

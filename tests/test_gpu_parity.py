@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C-ABI library) with the reference: committed golden
+fixtures (outputs of the unmodified reference), the numpy oracle on seeded inputs, and
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): segment indices bit-exact; fp32 outputs and gradients within
+1e-5 relative, measured as max|a-b| / max|b| per tensor."""
+import numpy as np
+import pytest
+import torch
+
+import high_order_layers_torch_b200 as hol
+from high_order_layers_torch_b200 import ops
+from oracle import pw_oracle as orc
+from tests.conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+MLP_TOL = 1e-4  # network level: the reference's own MLP-level rtol (tests/test_refinement.py:55-92)
+DEV = "cuda"
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def run_fc(x, w, gy, n, S, disc, length=2.0, per=None):
+    xt = t(x).requires_grad_(True)
+    wt = t(w).requires_grad_(True)
+    y = ops.piecewise_polynomial(xt, wt, n, S, length, disc, per)
+    y.backward(t(gy))
+    torch.cuda.synchronize()
+    dx = xt.grad if xt.grad is not None else torch.zeros_like(xt)
+    return y.detach().cpu().numpy(), dx.cpu().numpy(), wt.grad.cpu().numpy()
+
+
+def test_extension_is_loaded_and_native():
+    from high_order_layers_torch_b200 import _lib
+    lib = _lib.load()
+    assert lib.hol_abi_version() == 1
+    assert torch.cuda.get_device_capability()[0] >= 10
+
+
+def test_segment_index_bit_exact_vs_golden():
+    g = load_golden("segment_index.npz")
+    for name in g["cases"]:
+        name = str(name)
+        S = int(name.split("_")[0][1:])
+        length = float(name.split("_")[1][1:])
+        per = name.split("_")[2][1:]
+        per = None if per == "None" else float(per)
+        idx = ops.pw_segment_index(t(g[name + "_x"]), S, length, per).cpu().numpy()
+        assert idx.dtype == np.int64
+        assert np.array_equal(idx, g[name + "_idx"]), name
+    nan = ops.pw_segment_index(torch.tensor([float("nan")], device=DEV), 4, 2.0, None).cpu().numpy()
+    assert np.array_equal(nan, g["nan_idx"])
+
+
+@pytest.mark.parametrize("S,length,per", [(4, 2.0, None), (7, 2.0, None), (64, 2.0, None), (5, 3.0, None),
+                                          (8, 2.0, 2.0), (3, 1.0, 2.0)])
+def test_segment_index_bit_exact_vs_oracle_dense_sweep(S, length, per):
+    rng = np.random.default_rng(S)
+    half = 0.5 * length
+    x = rng.uniform(-1.3 * half, 1.3 * half, size=1 << 20).astype(np.float32)
+    if per is not None:
+        x = rng.uniform(-4 * per, 4 * per, size=1 << 20).astype(np.float32)
+    # every boundary and its ulp neighbours
+    b = (-half + np.arange(S + 1) * length / S).astype(np.float32)
+    x[: 3 * (S + 1)] = np.concatenate([b, np.nextafter(b, np.float32(9)), np.nextafter(b, np.float32(-9))])
+    idx = ops.pw_segment_index(t(x), S, length, per).cpu().numpy()
+    assert np.array_equal(idx, orc.segment_index(x, S, length, per))
+    layer = hol.PiecewisePolynomial(n=2, in_features=1, out_features=1, segments=S, length=length, periodicity=per)
+    assert np.array_equal(layer.which_segment(t(x).reshape(-1, 1)).cpu().numpy().reshape(-1), idx)
+
+
+def test_fc_golden_all_cases():
+    g = load_golden("fc_layers.npz")
+    for name in g["cases"]:
+        name = str(name)
+        n, S, I, O, B, disc = (int(v) for v in g[name + "_meta"])
+        length, per = (float(v) for v in g[name + "_fmeta"])
+        per = None if np.isnan(per) else per
+        y, dx, dw = run_fc(g[name + "_x"], g[name + "_w"], g[name + "_gy"], n, S, bool(disc), length, per)
+        assert rel_err(y, g[name + "_y"]) < TOL, name
+        assert rel_err(dw, g[name + "_dw"]) < TOL, name
+        assert np.array_equal(dw == 0, g[name + "_dw"] == 0), name   # dense dW, exact zeros where untouched
+        if n == 1:
+            assert not dx.any(), name
+        else:
+            assert rel_err(dx, g[name + "_dx"]) < TOL, name
+
+
+FC_ORACLE_CASES = [
+    # kind, n, S, I, O, B, per
+    ("cont", 4, 4, 784, 128, 256, None),     # config-3 layer 1
+    ("cont", 4, 4, 128, 10, 256, 2.0),       # config-3 output layer, invariant_mnist periodicity
+    ("disc", 5, 8, 1024, 1024, 48, None),    # config-2 layer, reduced batch
+    ("cont", 3, 2, 10, 10, 1024, None),      # config-1 hidden layer
+    ("cont", 3, 2, 1, 10, 33, None),
+    ("disc", 2, 64, 70, 130, 513, None),     # odd sizes, many segments, batch just over one tile
+    ("cont", 8, 32, 33, 65, 300, None),
+    ("disc", 10, 3, 7, 5, 2, None),
+    ("cont", 1, 4, 9, 6, 40, None),
+    ("disc", 1, 4, 9, 6, 40, None),
+    ("cont", 2, 1, 3, 2, 1, None),
+]
+
+
+@pytest.mark.parametrize("kind,n,S,I,O,B,per", FC_ORACLE_CASES)
+def test_fc_vs_oracle(kind, n, S, I, O, B, per):
+    rng = np.random.default_rng(n * 1000 + S * 10 + I)
+    disc = kind == "disc"
+    nb = orc.weights_per_link(n, S, disc)
+    x = rng.uniform(-1.25, 1.25, size=(B, I)).astype(np.float32)
+    if per is not None:
+        x = rng.uniform(-5, 5, size=(B, I)).astype(np.float32)
+    bnd = (-1 + np.arange(S + 1) * 2.0 / S).astype(np.float32)
+    flat = x.reshape(-1)
+    k = min(bnd.size, flat.size)
+    flat[rng.choice(flat.size, size=k, replace=False)] = bnd[:k]
+    w = rng.uniform(-1, 1, size=(O, I, nb)).astype(np.float32)
+    gy = rng.standard_normal(size=(B, O)).astype(np.float32)
+    nodes = ops.lobatto_nodes(n, 2.0).numpy()
+    y, dx, dw = run_fc(x, w, gy, n, S, disc, 2.0, per)
+    y64 = orc.pw_forward(x, w, n, S, 2.0, disc, per, nodes=nodes)
+    dx64, dw64 = orc.pw_backward(gy, x, w, n, S, 2.0, disc, per, nodes=nodes)
+    assert rel_err(y, y64) < TOL
+    assert rel_err(dw, dw64) < TOL
+    assert np.array_equal(dw == 0, dw64 == 0)
+    if n == 1:
+        assert not dx.any()
+    else:
+        assert rel_err(dx, dx64) < TOL
+    seg = ops.pw_segment_index(t(x), S, 2.0, per).cpu().numpy()
+    assert np.array_equal(seg, orc.segment_index(x, S, 2.0, per))
+
+
+def test_reference_value_pins_through_modules():
+    p = load_golden("reference_pins.npz")
+    # tests/test_layers.py:108-131 and tests/test_sparse_optimizer.py:24-58
+    layer = hol.PiecewiseDiscontinuousPolynomial(n=2, in_features=1, out_features=1, segments=10, device=DEV)
+    with torch.no_grad():
+        layer.w.copy_(t(p["act_w"]))
+    out = layer(torch.ones(1, 1, device=DEV) * 0.5)
+    loss = torch.nn.functional.mse_loss(out, torch.ones(1, 1, device=DEV) * 0.2)
+    loss.backward()
+    grad = layer.w.grad
+    assert grad.shape == torch.Size([1, 1, 20])
+    assert grad[grad != 0.0].shape == torch.Size([2])
+    assert rel_err(out.detach().cpu().numpy(), p["act_out"]) < TOL
+    assert rel_err(grad.cpu().numpy(), p["act_dw"]) < TOL
+    # tests/test_layers.py:88-105 (identity through 5 nodes, constant n=1)
+    ident = hol.PiecewiseDiscontinuousPolynomial(n=5, in_features=1, out_features=1, segments=1, device=DEV)
+    with torch.no_grad():
+        ident.w.copy_(ops.lobatto_nodes(5).to(DEV).reshape(1, 1, 5))
+    assert abs(ident(torch.tensor([[0.5]], device=DEV)).item() - 0.5) < 1e-6
+    const = hol.PiecewisePolynomial(n=1, in_features=1, out_features=1, segments=3, device=DEV)
+    with torch.no_grad():
+        const.w.fill_(0.25)
+    assert abs(const(torch.tensor([[0.5]], device=DEV)).item() - 0.25) < 1e-6
+    # tests/test_refinement.py:21-44: p-refined weights reproduce the function
+    for name in p["interp_cases"]:
+        name = str(name)
+        n_in, n_out, I, O, S, disc = (int(v) for v in p[name + "_meta"])
+        cls = hol.PiecewiseDiscontinuousPolynomial if disc else hol.PiecewisePolynomial
+        li = cls(n=n_in, in_features=I, out_features=O, segments=S, device=DEV)
+        lo = cls(n=n_out, in_features=I, out_features=O, segments=S, device=DEV)
+        with torch.no_grad():
+            li.w.copy_(t(p[name + "_w_in"]))
+            lo.w.copy_(t(p[name + "_w_out"]))
+        x = t(p[name + "_x"])
+        yi, yo = li(x), lo(x)
+        assert rel_err(yi.detach().cpu().numpy(), p[name + "_y_in"]) < TOL
+        assert rel_err(yo.detach().cpu().numpy(), p[name + "_y_out"]) < TOL
+        if n_in <= n_out:
+            assert torch.allclose(yi, yo, rtol=1e-5, atol=1e-6)
+
+
+def test_conv_golden_all_cases():
+    g = load_golden("conv2d.npz")
+    for name in g["cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, stride, padding, dilation, rescale = (int(v) for v in g[name + "_meta"])
+        length, per = (float(v) for v in g[name + "_fmeta"])
+        per = None if np.isnan(per) else per
+        layer = hol.PiecewisePolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K,
+                                                     length=length, rescale_output=bool(rescale), periodicity=per,
+                                                     device=DEV, stride=stride, padding=padding, dilation=dilation)
+        assert layer.conv.weight.shape == g[name + "_w"].shape
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        assert tuple(y.shape) == g[name + "_y"].shape, name
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+
+
+def test_mlp_golden():
+    g = load_golden("mlp.npz")
+    for name in g["cases"]:
+        name = str(name)
+        n, in_w, out_w, hl, hw, S, B, nl, norm, disc = (int(v) for v in g[name + "_meta"])
+        net = hol.HighOrderMLP(layer_type="discontinuous" if disc else "continuous", n=n, in_width=in_w,
+                               out_width=out_w, hidden_layers=hl, hidden_width=hw, in_segments=S, out_segments=S,
+                               hidden_segments=S, normalization=hol.MaxAbsNormalization if norm else None,
+                               device=DEV)
+        mods = [m for m in net.model if hasattr(m, "w")]
+        assert len(mods) == nl
+        with torch.no_grad():
+            for k, m in enumerate(mods):
+                m.w.copy_(t(g[name + f"_w{k}"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = net(xt)
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < MLP_TOL, name
+        assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < MLP_TOL, name
+        for k, m in enumerate(mods):
+            assert rel_err(m.w.grad.cpu().numpy(), g[name + f"_dw{k}"]) < MLP_TOL, (name, k)
+
+
+def test_backward_is_bit_reproducible():
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, size=(777, 40)).astype(np.float32)
+    w = rng.uniform(-1, 1, size=(70, 40, 13)).astype(np.float32)
+    gy = rng.standard_normal(size=(777, 70)).astype(np.float32)
+    a = run_fc(x, w, gy, 4, 4, False)
+    b = run_fc(x, w, gy, 4, 4, False)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("kind,n,S,I,O,B", [("disc", 5, 8, 1024, 1024, 65536),      # BASELINE config 2, full size
+                                            ("cont", 4, 4, 784, 128, 8192)])       # config 3 layer 1, per-GPU batch
+def test_full_size_properties(kind, n, S, I, O, B):
+    """Size-independent checks at the benchmark sizes (the reference cannot run these shapes):
+    partition of unity (sum_j phi_j = 1, sum_j phi'_j = 0), linearity in w, and the column sums
+    of dW against gy."""
+    disc = kind == "disc"
+    nb = orc.weights_per_link(n, S, disc)
+    gen = torch.Generator(device=DEV).manual_seed(1234)
+    x = (torch.rand(B, I, device=DEV, generator=gen) * 2.5 - 1.25).requires_grad_(True)
+    gy = torch.randn(B, O, device=DEV, generator=gen)
+    # (1) node-constant weights: every link is a constant function -> y = row sums, dX = 0
+    c = torch.rand(O, I, device=DEV, generator=gen) * 2 - 1
+    w_const = c.unsqueeze(2).expand(O, I, nb).contiguous().requires_grad_(True)
+    y = ops.piecewise_polynomial(x, w_const, n, S, 2.0, disc, None)
+    want = c.double().sum(dim=1).float()
+    assert (y - want.unsqueeze(0)).abs().max().item() < 2e-4 * want.abs().max().item() + 1e-4
+    y.backward(gy)
+    scale = (gy.abs().max() * c.abs().max() * O).item()
+    assert x.grad.abs().max().item() < 1e-4 * scale
+    # (2) for a discontinuous layer each sample adds phi (summing to 1) times gy to one segment:
+    #     summing dW over the nodes gives gy summed over the batch
+    if disc:
+        col = w_const.grad.double().sum(dim=2)                      # [O, I]
+        ref = gy.double().sum(dim=0).unsqueeze(1).expand(O, I)
+        assert (col - ref).abs().max().item() < 2e-6 * gy.abs().sum(dim=0).max().item()
+    # (3) linearity in w on a slice of the batch
+    xs = x.detach()[:4096]
+    w1 = torch.rand(O, I, nb, device=DEV, generator=gen) - 0.5
+    w2 = torch.rand(O, I, nb, device=DEV, generator=gen) - 0.5
+    y1 = ops.piecewise_polynomial(xs, w1, n, S, 2.0, disc, None)
+    y2 = ops.piecewise_polynomial(xs, w2, n, S, 2.0, disc, None)
+    y12 = ops.piecewise_polynomial(xs, w1 + w2, n, S, 2.0, disc, None)
+    assert rel_err((y1 + y2).cpu().numpy(), y12.cpu().numpy()) < 5e-5
+    # (4) a 64-sample slice against the fp64 oracle
+    y64 = orc.pw_forward(xs[-64:].cpu().numpy(), w1.cpu().numpy(), n, S, 2.0, disc, None,
+                         nodes=ops.lobatto_nodes(n).numpy())
+    assert rel_err(y1[-64:].cpu().numpy(), y64) < TOL

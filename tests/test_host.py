@@ -1,0 +1,134 @@
+"""CPU-side checks: module API mirrors the reference (constructor arguments, parameter names and
+shapes, RNG consumption, registry errors), the C-ABI library loads and exports every declared
+symbol, and the product refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import high_order_layers_torch_b200 as hol
+from high_order_layers_torch_b200 import _build, _lib, ops
+from high_order_layers_torch_b200.LagrangePolynomial import LagrangePoly, chebyshevLobatto
+from tests.conftest import ROOT, load_golden
+
+
+def test_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hol_b200.h")).read()
+    declared = set(re.findall(r"\b(hol_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_build.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.hol_abi_version() == 1
+    assert loaded.hol_error_string(-2).startswith(b"hol:")
+    assert loaded.hol_error_string(0) == b"ok"
+
+
+def test_workspace_queries_need_no_gpu():
+    lib = _lib.load()
+    c2 = lib.hol_pw_workspace_bytes(65536, 1024, 1024, 5, 8, 1)
+    assert 5e8 < c2 < 2e9
+    assert lib.hol_pw_workspace_bytes(8, 4, 4, 11, 2, 0) == 0          # n above the compiled envelope
+    assert lib.hol_pw_workspace_bytes(8, 4, 4, 3, 5000, 0) == 0        # too many segments
+    assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 32, 32, 6, 5, 1, 0, 1, 3, 4, 0) > 0
+    assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 4, 4, 6, 5, 1, 0, 1, 3, 4, 0) == 0   # kernel larger than image
+    assert lib.hol_pw_launch_count(0, 5, 1, 1, 1, 0) == 3
+    assert lib.hol_pw_launch_count(1, 5, 1, 1, 1, 1) == 3
+
+
+def test_node_table_is_the_reference_table():
+    g = load_golden("nodes.npz")
+    for n in range(1, 17):
+        assert np.array_equal(chebyshevLobatto(n).numpy().view(np.int32), g[f"X_{n}"].view(np.int32)), n
+        assert np.array_equal(LagrangePoly(n).basis.X.numpy(), g[f"X_{n}"])
+    for n in (2, 3, 5):
+        assert np.array_equal(ops.lobatto_nodes(n, 4.0).numpy(), g[f"X_{n}_len4"])
+    for n in range(2, 11):
+        assert np.array_equal(LagrangePoly(n).basis.denominators.numpy(), g[f"denom_{n}"])
+
+
+def test_same_seed_same_initial_weights():
+    p = load_golden("reference_pins.npz")
+    torch.manual_seed(1234)
+    a = hol.PiecewisePolynomial(n=4, in_features=6, out_features=5, segments=3, weight_magnitude=2.0)
+    assert a.w.shape == (5, 6, 10) and a.w.requires_grad
+    assert np.array_equal(a.w.detach().numpy(), p["init_cont_w"])
+    torch.manual_seed(1234)
+    b = hol.PiecewiseDiscontinuousPolynomial(n=4, in_features=6, out_features=5, segments=3, weight_magnitude=2.0)
+    assert b.w.shape == (5, 6, 12)
+    assert np.array_equal(b.w.detach().numpy(), p["init_disc_w"])
+    torch.manual_seed(1234)
+    c = hol.PiecewisePolynomialConvolution2d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3)
+    assert c.conv.weight.shape == (3, 18, 3, 3)
+    assert np.array_equal(c.conv.weight.detach().numpy(), p["init_conv_w"])
+
+
+def test_factories_and_errors():
+    layer = hol.high_order_fc_layers("continuous", n=3, in_features=2, out_features=4, segments=5,
+                                     rescale_output=False, scale=2.0, initialization="constant_random")
+    assert isinstance(layer, hol.PiecewisePolynomial) and layer.w.shape == (4, 2, 11)
+    layer = hol.high_order_fc_layers("discontinuous", n=3, in_features=2, out_features=4, segments=5)
+    assert isinstance(layer, hol.PiecewiseDiscontinuousPolynomial) and layer.w.shape == (4, 2, 15)
+    assert layer.n == 3 and layer._segments == 5 and layer._length == 2.0 and layer._half == 1.0
+    conv = hol.high_order_convolution_layers("continuous2d", n=3, segments=4, in_channels=2, out_channels=2,
+                                             kernel_size=4, stride=1, device="cpu")
+    assert conv.conv.weight.shape == (2, 18, 4, 4)
+    with pytest.raises(ValueError, match="not recognized"):
+        hol.high_order_fc_layers("fourier", n=3, in_features=2, out_features=4, segments=5)
+    with pytest.raises(ValueError, match="not recognized"):
+        hol.high_order_convolution_layers("fourier2d", n=3, in_channels=2, out_channels=2, kernel_size=3)
+    with pytest.raises(ValueError):
+        hol.PiecewisePolynomialConvolution2d(n=3, segments=2, in_channels=2, out_channels=2, kernel_size=3, groups=2)
+
+
+def test_high_order_mlp_structure_matches_reference():
+    g = load_golden("mlp.npz")
+    net = hol.HighOrderMLP(layer_type="continuous", n=3, in_width=1, out_width=1, hidden_layers=1, hidden_width=10,
+                           in_segments=2, out_segments=2, hidden_segments=2, normalization=hol.MaxAbsNormalization)
+    assert sorted(net.state_dict().keys()) == [str(k) for k in g["c1_function_keys"]]
+    shapes = [tuple(m.w.shape) for m in net.model if hasattr(m, "w")]
+    assert shapes == [g[f"c1_function_w{k}"].shape for k in range(3)]
+    assert net.input_layer is net.model[0] and net.output_layer is net.model[-1]
+
+
+def test_no_cpu_fallback():
+    layer = hol.PiecewisePolynomial(n=3, in_features=2, out_features=2, segments=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.zeros(4, 2))
+    conv = hol.PiecewisePolynomialConvolution2d(n=3, segments=2, in_channels=1, out_channels=1, kernel_size=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv(torch.zeros(1, 1, 4, 4))
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.pw_forward(torch.zeros(4, 2), layer.w, 3, 2, 2.0, False, None)
+
+
+def test_cpu_helpers_match_reference_segment_index():
+    g = load_golden("segment_index.npz")
+    for name in g["cases"]:
+        name = str(name)
+        S = int(name.split("_")[0][1:])
+        length = float(name.split("_")[1][1:])
+        per = name.split("_")[2][1:]
+        per = None if per == "None" else float(per)
+        layer = hol.PiecewisePolynomial(n=3, in_features=1, out_features=1, segments=S, length=length,
+                                        periodicity=per)
+        x = torch.from_numpy(g[name + "_x"]).reshape(-1, 1)
+        idx = layer.which_segment(x)
+        assert idx.dtype == torch.int64
+        assert np.array_equal(idx.numpy().reshape(-1), g[name + "_idx"]), name
+
+
+def test_fake_tensor_shapes():
+    # register_fake: shape/dtype propagation without a device
+    x = torch.empty(7, 5, device="meta")
+    w = torch.empty(3, 5, 9, device="meta")
+    y, ws = ops.pw_forward(x, w, 3, 4, 2.0, False, None)
+    assert y.shape == (7, 3) and y.dtype == torch.float32
+    xi = torch.empty(2, 3, 8, 8, device="meta")
+    wf = torch.empty(4, 27, 9, device="meta")
+    yr, _ = ops.pw_conv2d_rows(xi, wf, 3, 4, 2.0, False, None, 3, 1, 0, 1)
+    assert yr.shape == (2 * 6 * 6, 4)
