@@ -1,0 +1,633 @@
+#!/usr/bin/env python
+"""Benchmark of the piecewise-polynomial hot path (fwd+bwd samples/s) -- see DESIGN.md "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5|c1] [--impl ours|reference]
+
+Default workload (N=1 and every N of the scaling run): BASELINE.json configs[1] ("c2"), one
+PiecewiseDiscontinuousPolynomial layer, batch 65536 per GPU, in=out=1024, n=5, segments=8, fp32.
+A step = zero grads, forward, backward with a supplied upstream gradient (dX and dW), and for
+N>1 the NCCL sum-allreduce of dW (weak scaling: per-GPU batch fixed).  One JSON line on rank 0.
+
+`--impl reference` times the reference's own CPU implementation of the same path on the host
+cores (the unmodified reference from baseline/_ref when it is present, otherwise the numpy
+oracle port) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: SIMT FMA issue peak at the max SM clock
+
+
+# ------------------------------------------------------------------------------------------
+# workload definitions
+# ------------------------------------------------------------------------------------------
+CONFIGS = {
+    "c2": dict(kind="layer", layer="discontinuous", n=5, S=8, I=1024, O=1024, B=65536,
+               name="c2: PiecewiseDiscontinuousPolynomial 1024->1024 n=5 segments=8, batch 65536/GPU, fwd+bwd(dX,dW)"),
+    "c5": dict(kind="layer", layer="continuous", n=4, S=8, I=4096, O=4096, B=32768,
+               name="c5: PiecewisePolynomial 4096->4096 sweep point (n, segments from --n/--segments), batch 32768/GPU"),
+    "c3": dict(kind="mlp", layer="continuous", n=4, S=4, widths=(784, 128, 128, 10), B=8192,
+               name="c3: HighOrderMLP 784->128->128->10 continuous n=4 segments=4 max_abs, batch 8192/GPU, CE loss"),
+    "c1": dict(kind="mlp", layer="continuous", n=3, S=2, widths=(1, 10, 10, 1), B=1024,
+               name="c1: HighOrderMLP 1->10->10->1 continuous n=3 segments=2 max_abs, batch 1024, MSE loss"),
+    "c4": dict(kind="conv", n=3, S=4, B=1024,
+               name="c4: LeNet-style continuous2d net (3->6 k5, pool, 6->16 k5, pool, fc 400->100), n=3 segments=4, "
+                    "32x32x3, batch 1024/GPU, CE loss"),
+}
+
+
+def nb_of(n, S, disc):
+    return n * S if disc else (n - 1) * S + 1
+
+
+def layer_bytes_flops(B, I, O, n, S, disc, first_layer=False):
+    """Algorithmic bytes / flops of one layer-step."""
+    nb = nb_of(n, S, disc)
+    by = 4 * (3 * B * I + 2 * B * O + 3 * I * O * nb) - (4 * B * I if first_layer else 0)
+    fl = 6 * B * I * O * n
+    return by, fl
+
+
+def kernel_bytes_flops(kernel, B, I, O, n, S, disc):
+    nb = nb_of(n, S, disc)
+    if kernel == "forward":
+        return 4 * (B * I + I * O * nb + B * O), 2 * B * I * O * n
+    if kernel == "dx":
+        return 4 * (B * O + 2 * B * I + I * O * nb), 2 * B * I * O * n
+    if kernel == "dw":
+        return 4 * (B * O + B * I + I * O * nb), 2 * B * I * O * n
+    raise KeyError(kernel)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def make_inputs(torch, shape, gen, device):
+    """x = 2*rand-1 with 1 % of the entries drawn from uniform(-1.25, 1.25)."""
+    x = torch.rand(shape, generator=gen, device=device) * 2 - 1
+    wide = torch.rand(shape, generator=gen, device=device) * 2.5 - 1.25
+    pick = torch.rand(shape, generator=gen, device=device) < 0.01
+    return torch.where(pick, wide, x)
+
+
+def build_workload(torch, cfg, device, rank, args):
+    import high_order_layers_torch_b200 as hol
+    from high_order_layers_torch_b200.parallel import FlatGradients
+
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    wl = {"cfg": cfg}
+    if cfg["kind"] == "layer":
+        n, S, I, O, B = cfg["n"], cfg["S"], cfg["I"], cfg["O"], cfg["B"]
+        disc = cfg["layer"] == "discontinuous"
+        torch.manual_seed(1234)  # identical replicas on every rank
+        layer = hol.high_order_fc_layers(cfg["layer"], n=n, in_features=I, out_features=O, segments=S,
+                                         device=str(device))
+        with torch.no_grad():
+            layer.w.uniform_(-1, 1)
+        x = make_inputs(torch, (B, I), gen, device).requires_grad_(True)
+        gy = torch.randn(B, O, generator=gen, device=device)
+        flat = FlatGradients(layer.parameters())
+
+        def step():
+            flat.zero_()
+            x.grad = None
+            y = layer(x)
+            y.backward(gy)
+            flat.allreduce(average=True)
+
+        def e2e_step(host):
+            xd = host["x"].to(device, non_blocking=True).requires_grad_(True)
+            gd = host["gy"].to(device, non_blocking=True)
+            flat.zero_()
+            y = layer(xd)
+            loss = (y * gd).sum()            # d loss / d y = gy: the same backward as the device-resident step
+            loss.backward()
+            flat.allreduce(average=True)
+            host["loss"].copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host["loss"])
+
+        by, fl = layer_bytes_flops(B, I, O, n, S, disc)
+        wl.update(model=layer, flat=flat, step=step, e2e_step=e2e_step, samples=B,
+                  host=dict(x=x.detach().cpu().pin_memory(), gy=gy.cpu().pin_memory(),
+                            loss=torch.zeros((), dtype=torch.float32).pin_memory()),
+                  h2d=4 * B * I + 4 * B * O, d2h=4, bytes=by, flops=fl,
+                  launches=3 + 1 + 2,  # prep, pack, forward | dX | bucket sort, dW  (csrc kernels per step)
+                  layers=[(B, I, O, n, S, disc)], x=x, gy=gy)
+        return wl
+
+    if cfg["kind"] == "mlp":
+        n, S, B = cfg["n"], cfg["S"], cfg["B"]
+        wd = cfg["widths"]
+        torch.manual_seed(1234)
+        net = hol.HighOrderMLP(layer_type=cfg["layer"], n=n, in_width=wd[0], out_width=wd[-1],
+                               hidden_layers=len(wd) - 3, hidden_width=wd[1], in_segments=S, out_segments=S,
+                               hidden_segments=S, normalization=hol.MaxAbsNormalization, device=str(device))
+        with torch.no_grad():
+            for p in net.parameters():
+                p.uniform_(-1, 1)
+        x = make_inputs(torch, (B, wd[0]), gen, device)
+        classify = wd[-1] > 1
+        target = (torch.randint(0, wd[-1], (B,), generator=gen, device=device) if classify
+                  else torch.randn(B, wd[-1], generator=gen, device=device))
+        lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
+        flat = FlatGradients(net.parameters())
+
+        def step():
+            flat.zero_()
+            loss = lossf(net(x), target)
+            loss.backward()
+            flat.allreduce(average=True)
+            return loss
+
+        def e2e_step(host):
+            xd = host["x"].to(device, non_blocking=True)
+            td = host["t"].to(device, non_blocking=True)
+            flat.zero_()
+            loss = lossf(net(xd), td)
+            loss.backward()
+            flat.allreduce(average=True)
+            host["loss"].copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host["loss"])
+
+        dims = list(zip(wd[:-1], wd[1:]))
+        by = fl = 0
+        for k, (i_, o_) in enumerate(dims):
+            b_, f_ = layer_bytes_flops(B, i_, o_, n, S, False, first_layer=(k == 0))
+            by += b_; fl += f_
+        nl = len(dims)
+        wl.update(model=net, flat=flat, step=step, e2e_step=e2e_step, samples=B,
+                  host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory(),
+                            loss=torch.zeros((), dtype=torch.float32).pin_memory()),
+                  h2d=x.numel() * 4 + target.numel() * target.element_size(), d2h=4, bytes=by, flops=fl,
+                  launches=3 * nl + (nl - 1) + 2 * nl,
+                  layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x)
+        return wl
+
+    if cfg["kind"] == "conv":
+        n, S, B = cfg["n"], cfg["S"], cfg["B"]
+        nn = torch.nn
+        torch.manual_seed(1234)
+
+        class Net(nn.Module):  # topology of the reference's examples/cifar10.py:54-102 with 100 classes
+            def __init__(self):
+                super().__init__()
+                self.conv1 = hol.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=3,
+                                                               out_channels=6, kernel_size=5, device=str(device))
+                self.conv2 = hol.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=6,
+                                                               out_channels=16, kernel_size=5, device=str(device))
+                self.pool = nn.MaxPool2d(2, 2)
+                self.fc = nn.Linear(16 * 5 * 5, 100)
+
+            def forward(self, x):
+                x = self.pool(self.conv1(x))
+                x = self.pool(self.conv2(x))
+                return self.fc(x.flatten(1))
+
+        net = Net().to(device)
+        with torch.no_grad():
+            net.conv1.conv.weight.uniform_(-0.2, 0.2)
+            net.conv2.conv.weight.uniform_(-0.2, 0.2)
+        x = make_inputs(torch, (B, 3, 32, 32), gen, device)
+        target = torch.randint(0, 100, (B,), generator=gen, device=device)
+        flat = FlatGradients(net.parameters())
+
+        def step():
+            flat.zero_()
+            loss = torch.nn.functional.cross_entropy(net(x), target)
+            loss.backward()
+            flat.allreduce(average=True)
+            return loss
+
+        def e2e_step(host):
+            xd = host["x"].to(device, non_blocking=True)
+            td = host["t"].to(device, non_blocking=True)
+            flat.zero_()
+            loss = torch.nn.functional.cross_entropy(net(xd), td)
+            loss.backward()
+            flat.allreduce(average=True)
+            host["loss"].copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host["loss"])
+
+        rows1, rows2 = B * 28 * 28, B * 10 * 10
+        b1, f1 = layer_bytes_flops(rows1, 75, 6, n, S, False, first_layer=True)
+        b2, f2 = layer_bytes_flops(rows2, 150, 16, n, S, False)
+        wl.update(model=net, flat=flat, step=step, e2e_step=e2e_step, samples=B,
+                  host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory(),
+                            loss=torch.zeros((), dtype=torch.float32).pin_memory()),
+                  h2d=x.numel() * 4 + target.numel() * 8, d2h=4, bytes=b1 + b2, flops=f1 + f2,
+                  launches=3 + 3 + (2 + 2) + (1 + 1 + 2),  # fwd x2; conv2 bwd: dX, col2im, sort, dW; conv1 bwd: sort, dW
+                  layers=[(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)], x=x)
+        return wl
+    raise KeyError(cfg["kind"])
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this build has no CPU path; use --impl reference for the CPU baseline)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    cfg = dict(CONFIGS[args.config])
+    if args.n:
+        cfg["n"] = args.n
+    if args.segments:
+        cfg["S"] = args.segments
+    if args.batch:
+        cfg["B"] = args.batch
+    wl = build_workload(torch, cfg, device, rank, args)
+    step = wl["step"]
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public module API: pinned host inputs -> H2D -> fwd+bwd -> loss D2H
+    e2e_steps = max(1, min(steps, 10))
+    wl["e2e_step"](wl["host"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wl["e2e_step"](wl["host"])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = (float(v) for v in tm.tolist())
+    ms_per_step = ms_total / steps
+    value = wl["samples"] * world / (ms_per_step / 1e3)
+    e2e_value = wl["samples"] * world / (e2e_ms / e2e_steps / 1e3)
+
+    roof = None
+    cpu = None
+    if rank == 0:
+        roof = measure_roofline(torch, wl, ms_per_step)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(cfg, budget_s=args.cpu_budget)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        peaks = load_peaks()
+        out = {
+            "metric": "fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world,
+                       "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)"
+                       if wl["bytes"] > 3 * 126e6 else "working set fits L2; no flush between steps",
+                       "allreduce": "one flat fp32 NCCL sum-allreduce of dW per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": wl["h2d"],
+                    "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps},
+            "gpu_launches": wl["launches"] * steps,
+            "gpu_launches_per_step": wl["launches"],
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "step_algorithmic": {"bytes": wl["bytes"], "flops": wl["flops"],
+                                 "hbm_frac_of_measured": wl["bytes"] / (ms_per_step / 1e3) / (peaks["hbm_gbs"] * 1e9),
+                                 "fp32_frac_of_74.4TF": wl["flops"] / (ms_per_step / 1e3) / (FP32_PEAK_TFLOPS * 1e12),
+                                 "binding_roof": "fp32 (SIMT FMA issue / shared-memory bandwidth), not HBM"},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        p["source"] = "measured (MEASURED_PEAKS.json)"
+        return p
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def measure_roofline(torch, wl, ms_per_step):
+    """Per-kernel CUDA-event times of the widest layer of the workload (hol_pw_profile_f32 records
+    events between the kernels on the launching stream); the dominant kernel is reported against
+    the measured HBM peak with its ALGORITHMIC bytes (and, because this path is FMA/shared-memory
+    bound, its flops against the 74.4 TFLOP/s fp32 SIMT peak)."""
+    from high_order_layers_torch_b200 import ops
+
+    peaks = load_peaks()
+    B, I, O, n, S, disc = max(wl["layers"], key=lambda t: t[0] * t[1] * t[2] * t[3])
+    dev = wl["x"].device
+    gen = torch.Generator(device=dev).manual_seed(99)
+    x = make_inputs(torch, (B, I), gen, dev)
+    w = torch.rand(O, I, nb_of(n, S, disc), generator=gen, device=dev) * 2 - 1
+    gy = torch.randn(B, O, generator=gen, device=dev)
+    acc = {}
+    reps = 3
+    ops.profile_layer(x, w, gy, n, S, 2.0, disc, None)  # warm
+    for _ in range(reps):
+        for k, v in ops.profile_layer(x, w, gy, n, S, 2.0, disc, None).items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    dom = max(("forward", "dx", "dw"), key=lambda k: acc[k])
+    by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
+    t = acc[dom] / 1e3
+    achieved = by / t / 1e9
+    return {"bound": "hbm", "kernel": {"forward": "pw_fwd_kernel", "dx": "pw_dx_kernel", "dw": "pw_dw_kernel"}[dom],
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "peak_source": peaks["source"], "traffic": None,
+            "algorithmic_bytes_per_launch": by, "launch_ms": acc[dom],
+            "fp32": {"achieved_tflops": fl / t / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
+                     "frac": fl / t / 1e12 / FP32_PEAK_TFLOPS, "flops_per_launch": fl},
+            "kernel_ms": acc, "layer": {"B": B, "I": I, "O": O, "n": n, "segments": S, "discontinuous": disc},
+            "note": "this contraction is bound by fp32 FMA issue / shared-memory bandwidth (arithmetic intensity "
+                    ">> ridge), so the HBM fraction is small by construction; see fp32.frac"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------
+def _reference_modules():
+    """The unmodified reference from baseline/_ref (pip --target install, git-ignored), or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "high_order_layers_torch")):
+        return None
+    import types
+    import torch
+    if "pytorch_lightning" not in sys.modules:
+        stub = types.ModuleType("pytorch_lightning")
+        stub.LightningModule = type("LightningModule", (torch.nn.Module,), {})
+        sys.modules["pytorch_lightning"] = stub
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import high_order_layers_torch.layers as L  # noqa
+        import high_order_layers_torch.networks as N  # noqa
+        return types.SimpleNamespace(layers=L, networks=N)
+    except Exception as e:  # pragma: no cover
+        print(f"bench.py: reference import failed ({e}); using the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_step_factory(cfg, chunk):
+    """One bounded CPU step (fwd+bwd on `chunk` samples) of the workload; returns (fn, kind, samples)."""
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    R = _reference_modules()
+    rng = np.random.default_rng(0)
+    if cfg["kind"] == "layer":
+        n, S, I, O = cfg["n"], cfg["S"], cfg["I"], cfg["O"]
+        disc = cfg["layer"] == "discontinuous"
+        x = rng.uniform(-1, 1, size=(chunk, I)).astype(np.float32)
+        gy = rng.standard_normal(size=(chunk, O)).astype(np.float32)
+        if R is not None:
+            layer = R.layers.high_order_fc_layers(cfg["layer"], n=n, in_features=I, out_features=O, segments=S)
+            xt = torch.from_numpy(x).requires_grad_(True)
+            gt = torch.from_numpy(gy)
+
+            def fn():
+                layer.w.grad = None
+                xt.grad = None
+                layer(xt).backward(gt)
+            return fn, "reference", chunk
+        from oracle import pw_oracle as orc
+        w = rng.uniform(-1, 1, size=(O, I, nb_of(n, S, disc))).astype(np.float32)
+
+        def fn():
+            orc.pw_forward(x, w, n, S, 2.0, disc, dtype=np.float32)
+            orc.pw_backward(gy, x, w, n, S, 2.0, disc, dtype=np.float32)
+        return fn, "port", chunk
+    if cfg["kind"] == "mlp":
+        n, S, wd = cfg["n"], cfg["S"], cfg["widths"]
+        x = rng.uniform(-1, 1, size=(chunk, wd[0])).astype(np.float32)
+        if R is not None:
+            net = R.networks.HighOrderMLP(layer_type=cfg["layer"], n=n, in_width=wd[0], out_width=wd[-1],
+                                          hidden_layers=len(wd) - 3, hidden_width=wd[1], in_segments=S, out_segments=S,
+                                          hidden_segments=S, normalization=R.layers.MaxAbsNormalization)
+            xt = torch.from_numpy(x)
+            classify = wd[-1] > 1
+            tgt = torch.randint(0, wd[-1], (chunk,)) if classify else torch.randn(chunk, wd[-1])
+            lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
+
+            def fn():
+                net.zero_grad(set_to_none=True)
+                lossf(net(xt), tgt).backward()
+            return fn, "reference", chunk
+        from oracle import pw_oracle as orc
+        ws = [rng.uniform(-1, 1, size=(o, i, nb_of(n, S, False))).astype(np.float32) for i, o in zip(wd[:-1], wd[1:])]
+        gy = rng.standard_normal(size=(chunk, wd[-1])).astype(np.float32)
+
+        def fn():
+            orc.mlp_forward_backward(x, ws, gy, n, S, dtype=np.float32)
+        return fn, "port", chunk
+    if cfg["kind"] == "conv":
+        n, S = cfg["n"], cfg["S"]
+        x = rng.uniform(-1, 1, size=(chunk, 3, 32, 32)).astype(np.float32)
+        if R is not None:
+            nn = torch.nn
+            c1 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=3, out_channels=6,
+                                                        kernel_size=5)
+            c2 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=6,
+                                                        out_channels=16, kernel_size=5)
+            pool, fc = nn.MaxPool2d(2, 2), nn.Linear(400, 100)
+            xt = torch.from_numpy(x)
+            tgt = torch.randint(0, 100, (chunk,))
+            params = list(c1.parameters()) + list(c2.parameters()) + list(fc.parameters())
+
+            def fn():
+                for p in params:
+                    p.grad = None
+                out = fc(pool(c2(pool(c1(xt)))).flatten(1))
+                torch.nn.functional.cross_entropy(out, tgt).backward()
+            return fn, "reference", chunk
+        from oracle import pw_oracle as orc
+        w1 = rng.uniform(-1, 1, size=(6, 3 * nb_of(n, S, False), 5, 5)).astype(np.float32)
+
+        def fn():
+            orc.pw_conv2d_forward(x, w1, n, S, dtype=np.float32)
+        return fn, "port", chunk
+    raise KeyError(cfg["kind"])
+
+
+CPU_CHUNK = {"c2": 64, "c5": 8, "c3": 256, "c1": 1024, "c4": 128}
+
+
+def cpu_baseline(cfg, budget_s=15.0, key=None):
+    """Time the CPU implementation on a bounded sample of the workload (about `budget_s` seconds)."""
+    key = key or [k for k, v in CONFIGS.items() if v["name"] == cfg["name"]][0]
+    chunk = CPU_CHUNK[key]
+    fn, kind, samples = cpu_step_factory(cfg, chunk)
+    fn()  # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        fn()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or reps >= 50:
+            break
+    import torch
+    return {"value": samples * reps / el, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{reps} micro-batches of {samples} samples of the same layer shape (fwd+bwd, fp32, "
+                      f"{'unmodified reference modules on torch CPU' if kind == 'reference' else 'numpy oracle port'}), "
+                      f"{el:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cfg = dict(CONFIGS[args.config])
+    if args.n:
+        cfg["n"] = args.n
+    if args.segments:
+        cfg["S"] = args.segments
+    chunk = CPU_CHUNK[args.config]
+    fn, kind, samples = cpu_step_factory(cfg, chunk)
+    import torch
+    warmup = max(1, min(args.warmup, 3))
+    steps = max(1, args.steps)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        fn()
+        done += 1
+        if time.perf_counter() - t0 > 150:  # keep the whole run within a few minutes
+            break
+    el = time.perf_counter() - t0
+    value = samples * done / el
+    sample = (f"each step = one micro-batch of {samples} samples of the workload's layer shapes, fwd+bwd fp32 on the "
+              f"host CPU ({'unmodified reference via baseline/_ref' if kind == 'reference' else 'numpy oracle port'})")
+    print(json.dumps({
+        "impl": "reference", "metric": "fwd+bwd samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": done, "warmup": warmup, "ms_per_step": el / done * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world,
+                   "parallelism": "cpu", "note": "CPU reference arm; rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override n (c5 sweep)")
+    ap.add_argument("--segments", type=int, default=0, help="override segments (c5 sweep)")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,8 @@ SIGNATURES = {
     "hol_pw_conv2d_backward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                                   _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _sz, _u32,
                                                   _vp]),
+    "hol_pw_profile_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
+                                          _f32, _vp, _sz, _vp, _vp]),
     "hol_pw_launch_count": (ctypes.c_int, [ctypes.c_int, _i32, _i32, _i32, _i32, _u32]),
 }
 

@@ -243,6 +243,50 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
     return HOL_OK;
 }
 
+int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const float* nodes_host, float* y, float* dx,
+                       float* dw, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, float length,
+                       int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes, float* ms_out_host,
+                       void* stream) {
+    if (!gy || !x || !w || !nodes_host || !y || !dx || !dw || !ws_ptr || !ms_out_host || B <= 0) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[7];
+    for (int k = 0; k < 7; ++k)
+        if (cudaEventCreate(&ev[k]) != cudaSuccess) return (int)cudaGetLastError();
+    int rc = HOL_OK;
+    auto mark = [&](int k) { cudaEventRecord(ev[k], st); };
+    mark(0);
+    rc = launch_prep_fc(x, s, ws, st);
+    mark(1);
+    if (rc == HOL_OK) rc = launch_pack(w, s, ws, st);
+    mark(2);
+    if (rc == HOL_OK) rc = launch_forward(s, ws, y, st);
+    mark(3);
+    if (rc == HOL_OK) {
+        if (n == 1)
+            cudaMemsetAsync(dx, 0, (size_t)B * I * 4, st);
+        else
+            rc = launch_backward_dx(s, ws, gy, dx, 0, st);
+    }
+    mark(4);
+    if (rc == HOL_OK) rc = launch_bucket_sort(s, ws, st);
+    mark(5);
+    if (rc == HOL_OK) rc = launch_backward_dw(s, ws, gy, dw, st);
+    mark(6);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == HOL_OK && e != cudaSuccess) rc = (int)e;
+    for (int k = 0; k < 6; ++k) {
+        float ms = 0.0f;
+        if (rc == HOL_OK) cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+        ms_out_host[k] = ms;
+    }
+    for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
+    return rc;
+}
+
 int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags) {
     if (kind == 0) return 3;  // prep, pack, forward
     int c = 0;

@@ -116,6 +116,15 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
                                float periodicity, void* ws, size_t ws_bytes, uint32_t flags,
                                void* stream);
 
+/* DIAGNOSTIC entry (the only one that synchronises): runs forward + backward once on `stream`
+ * with CUDA events between the kernels and returns their durations in milliseconds in
+ * ms_out_host[6] = {prep, pack, forward, dx, bucket_sort, dw}.  Used by bench.py for the
+ * per-kernel roofline numbers; not part of the drop-in path. */
+int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const float* nodes_host,
+                       float* y, float* dx, float* dw, int64_t B, int32_t I, int32_t O, int32_t n,
+                       int32_t S, float length, int32_t discontinuous, float periodicity, void* ws,
+                       size_t ws_bytes, float* ms_out_host, void* stream);
+
 /* Number of kernel launches the last call of each kind issues for the given shape
  * (what bench.py reports as gpu_launches).  kind: 0 forward, 1 backward(dx+dw). */
 int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx,

@@ -1,0 +1,76 @@
+"""Data-parallel host logic on CPU: world_size-2 gloo processes exercise the flat-gradient
+allreduce and the batch sharding used by bench.py / the N>1 path (the kernels themselves need a GPU)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import high_order_layers_torch_b200 as hol
+from high_order_layers_torch_b200.parallel import FlatGradients, shard_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(1234)  # identical replicas
+        net = hol.HighOrderMLP(layer_type="continuous", n=4, in_width=20, out_width=10, hidden_layers=1,
+                               hidden_width=16, in_segments=4, out_segments=4, hidden_segments=4,
+                               normalization=hol.MaxAbsNormalization)
+        flat = FlatGradients(net.parameters())
+        # first/last layers are registered twice in HighOrderMLP: they must be counted once
+        assert flat.numel == sum(p.numel() for p in {id(p): p for p in net.parameters()}.values())
+        assert len(flat.params) == 3
+        flat.zero_()
+        # emulate the dW kernels writing rank-dependent gradients (accumulated in place into the views)
+        for k, p in enumerate(flat.params):
+            assert p.grad.data_ptr() >= flat.flat.data_ptr()
+            p.grad.add_(torch.full_like(p, float(rank + 1) * (k + 1)))
+        flat.allreduce(average=True)
+        for k, p in enumerate(flat.params):
+            want = (k + 1) * sum(r + 1 for r in range(world)) / world
+            assert torch.allclose(p.grad, torch.full_like(p, want)), (rank, k)
+        # a second step reuses the same buffer
+        flat.zero_()
+        assert not flat.flat.any()
+        flat.params[0].grad.add_(1.0)
+        flat.allreduce(average=False)
+        assert torch.allclose(flat.params[0].grad, torch.full_like(flat.params[0], float(world)))
+        lo, hi = shard_range(65536 + 3, rank, world)
+        t = torch.tensor([hi - lo], dtype=torch.int64)
+        dist.all_reduce(t)
+        assert t.item() == 65536 + 3
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert all(ret.get(r) for r in range(world))
+
+
+def test_shard_range_partitions_batch():
+    for total in (0, 1, 7, 8192, 65536, 65539):
+        for world in (1, 2, 4, 8):
+            covered = []
+            for r in range(world):
+                lo, hi = shard_range(total, r, world)
+                covered += list(range(lo, hi)) if total < 100 else [hi - lo]
+            if total < 100:
+                assert covered == list(range(total))
+            else:
+                assert sum(covered) == total and max(covered) - min(covered) <= 1
