@@ -28,6 +28,21 @@ int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, floa
     s.RS = single ? 1 : (disc ? S : S + 1);
     s.R = single ? 1 : (disc ? n * S : (n - 1) * (S + 1));
     s.Seff = single ? 1 : S;
+    s.nchunks = (int)((B + HOL_SORT_CHUNK - 1) / HOL_SORT_CHUNK);
+    if (s.nchunks < 1) s.nchunks = 1;
+    // dW work decomposition: lanes per sample (4 outputs each) and split over sample chunks so
+    // that narrow/few-bucket layers still fill the machine (>= ~4 warps per SM scheduler)
+    s.dw_lo = 32;
+    while (s.dw_lo > 1 && 4 * (s.dw_lo / 2) >= O) s.dw_lo >>= 1;
+    {
+        const int64_t otw = 4 * s.dw_lo;
+        const int64_t tasks = ((O + otw - 1) / otw) * (int64_t)I * s.Seff;
+        int64_t ks = (148 * 32 + tasks - 1) / tasks;
+        if (ks > s.nchunks) ks = s.nchunks;
+        if (ks > 64) ks = 64;
+        if (ks < 1) ks = 1;
+        s.ksplit = (int)ks;
+    }
     // output tile: wide layers use 64 accumulators per thread; the packed rows of ONE input
     // (R x (OT+4) floats) must fit the shared-memory budget at least once
     int OT = O >= 48 ? 64 : (O > 16 ? 32 : 16);
@@ -78,7 +93,8 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, bool conv) {
     ws.seg_t = (uint16_t*)take((size_t)s.I * s.Bp * sizeof(uint16_t));
     ws.wk = (float*)take((size_t)s.nOT * s.I * s.R * s.OTP * sizeof(float));
     ws.order = (uint32_t*)take((size_t)s.I * s.Bp * sizeof(uint32_t));
-    ws.offs = (uint32_t*)take((size_t)s.I * (s.Seff + 1) * sizeof(uint32_t));
+    ws.offs = (uint32_t*)take((size_t)s.I * s.nchunks * (s.Seff + 1) * sizeof(uint32_t));
+    ws.dw_part = s.ksplit > 1 ? (float*)take((size_t)s.ksplit * s.O * s.I * s.nb * sizeof(float)) : nullptr;
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
     ws.total = off;
     return off;
@@ -292,7 +308,7 @@ int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want
     int c = 0;
     if (!(flags & HOL_WS_PREPARED)) c += 1 + ((want_dx && n > 1) ? 1 : 0);
     if (want_dx && n > 1) c += 1;
-    if (want_dw) c += 2;  // bucket sort + dW (memsets are not kernels of ours)
+    if (want_dw) c += 2;  // bucket sort + dW (memsets are not kernels of ours; +1 reduce when dW is split)
     (void)discontinuous;
     return c;
 }

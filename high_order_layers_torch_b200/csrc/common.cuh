@@ -11,6 +11,7 @@
 #define HOL_SEG_MIRROR 0x8000u   // make_periodic took the mirrored branch: d fold / d x = -1
 
 #define HOL_WARPS_SORT 8
+#define HOL_SORT_CHUNK 8192  // samples per bucket-sort CTA / dW split unit
 
 struct BasisTab {
     float X[HOL_MAX_N];  // interpolation nodes (reference fp32 table)
@@ -27,6 +28,9 @@ struct PwShape {
     int RS;       // rows per basis group in the packed layout: S (disc) or S+1 (cont)
     int R;        // packed rows per input
     int Seff;     // number of dW buckets per input (1 for continuous n == 1)
+    int nchunks;  // ceil(B / HOL_SORT_CHUNK): the bucket sort and the dW split work chunk by chunk
+    int ksplit;   // dW: number of chunk groups reduced separately (deterministic two-stage sum)
+    int dw_lo;    // dW: lanes per sample (power of two; 4 outputs per lane)
     int OT, OTP;  // output tile and its padded pitch (floats) in the packed layout
     int nOT;      // number of output tiles
     int srow;     // packed floats per segment step (0 for continuous n == 1)
@@ -41,7 +45,8 @@ struct PwWorkspace {
     uint16_t* seg_t;  // [I][Bp]  segment index + flags, transposed
     float* wk;        // [nOT][I][R][OTP] packed weights
     uint32_t* order;  // [I][Bp]  sample ids sorted by segment (stable)
-    uint32_t* offs;   // [I][Seff+1] bucket offsets into order
+    uint32_t* offs;   // [I][nchunks][Seff+1] bucket offsets into order
+    float* dw_part;   // [ksplit][O][I][nb] partial weight gradients (ksplit > 1 only)
     float* dx_rows;   // conv only: [rows][I] unfolded input gradient
     size_t total;
 };

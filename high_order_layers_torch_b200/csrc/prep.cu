@@ -185,27 +185,33 @@ __global__ void __launch_bounds__(256) pw_pack_kernel(const float* __restrict__ 
     }
 }
 
-// Stable counting sort of the samples of one input by segment (one CTA per input).  The
-// order inside a bucket is the sample order, so the dW reduction order is fixed run to run.
+// Stable counting sort of the samples of one input by segment, chunk by chunk (one CTA per
+// (input, chunk of HOL_SORT_CHUNK samples)).  The order inside a bucket is the sample order, so
+// the dW reduction order is fixed run to run.  order[i][b] holds sample ids, offs[i][chunk][s]
+// the start of bucket s inside the chunk (absolute position in order[i]).
 __global__ void __launch_bounds__(32 * HOL_WARPS_SORT)
     pw_bucket_sort_kernel(const uint16_t* __restrict__ seg_t, uint32_t* __restrict__ order, uint32_t* __restrict__ offs,
-                          int64_t B, int64_t Bp, int Seff, int single_bucket) {
+                          int64_t B, int64_t Bp, int Seff, int nchunks, int single_bucket) {
     extern __shared__ uint32_t cnt[];  // [HOL_WARPS_SORT][Seff]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i = blockIdx.x;
+    const int i = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int64_t c_lo = (int64_t)chunk * HOL_SORT_CHUNK;
+    const int64_t c_hi = c_lo + HOL_SORT_CHUNK < B ? c_lo + HOL_SORT_CHUNK : B;
     const uint16_t* sg = seg_t + (int64_t)i * Bp;
     uint32_t* ord = order + (int64_t)i * Bp;
+    uint32_t* myoffs = offs + ((int64_t)i * nchunks + chunk) * (Seff + 1);
     for (int k = tid; k < HOL_WARPS_SORT * Seff; k += blockDim.x) cnt[k] = 0;
     __syncthreads();
-    const int64_t ngroups = (B + 31) / 32;
+    const int64_t ngroups = (c_hi - c_lo + 31) / 32;
     const int64_t gper = (ngroups + HOL_WARPS_SORT - 1) / HOL_WARPS_SORT;
     const int64_t g_lo = warp * gper;
     const int64_t g_hi = g_lo + gper < ngroups ? g_lo + gper : ngroups;
     uint32_t* mycnt = cnt + warp * Seff;
     const uint32_t lt = (1u << lane) - 1u;
     for (int64_t gidx = g_lo; gidx < g_hi; ++gidx) {
-        const int64_t b = gidx * 32 + lane;
-        const uint32_t v = b < B ? sg[b] : HOL_SEG_INVALID;
+        const int64_t b = c_lo + gidx * 32 + lane;
+        const uint32_t v = b < c_hi ? sg[b] : HOL_SEG_INVALID;
         const bool valid = !(v & HOL_SEG_INVALID);
         const uint32_t key = single_bucket ? 0u : (v & HOL_SEG_MASK);
         const uint32_t mask = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(32 * HOL_WARPS_SORT)
     }
     __syncthreads();
     if (warp == 0) {
-        uint32_t carry = 0;
+        uint32_t carry = (uint32_t)c_lo;
         for (int s0 = 0; s0 < Seff; s0 += 32) {
             const int s = s0 + lane;
             uint32_t tot = 0;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(32 * HOL_WARPS_SORT)
             }
             if (s < Seff) {
                 uint32_t off = carry + incl - tot;
-                offs[(int64_t)i * (Seff + 1) + s] = off;
+                myoffs[s] = off;
                 for (int w = 0; w < HOL_WARPS_SORT; ++w) {
                     const uint32_t t = cnt[w * Seff + s];
                     cnt[w * Seff + s] = off;
@@ -237,12 +243,12 @@ __global__ void __launch_bounds__(32 * HOL_WARPS_SORT)
             }
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) offs[(int64_t)i * (Seff + 1) + Seff] = carry;
+        if (lane == 0) myoffs[Seff] = carry;
     }
     __syncthreads();
     for (int64_t gidx = g_lo; gidx < g_hi; ++gidx) {
-        const int64_t b = gidx * 32 + lane;
-        const uint32_t v = b < B ? sg[b] : HOL_SEG_INVALID;
+        const int64_t b = c_lo + gidx * 32 + lane;
+        const uint32_t v = b < c_hi ? sg[b] : HOL_SEG_INVALID;
         const bool valid = !(v & HOL_SEG_INVALID);
         const uint32_t key = single_bucket ? 0u : (v & HOL_SEG_MASK);
         const uint32_t mask = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
@@ -300,7 +306,8 @@ int launch_bucket_sort(const PwShape& s, const PwWorkspace& ws, cudaStream_t st)
         cudaError_t e = cudaFuncSetAttribute(pw_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    pw_bucket_sort_kernel<<<(unsigned)s.I, 32 * HOL_WARPS_SORT, smem, st>>>(ws.seg_t, ws.order, ws.offs, s.B, s.Bp, s.Seff,
-                                                                           (!s.disc && s.n == 1) ? 1 : 0);
+    dim3 grid((unsigned)s.nchunks, (unsigned)s.I);
+    pw_bucket_sort_kernel<<<grid, 32 * HOL_WARPS_SORT, smem, st>>>(ws.seg_t, ws.order, ws.offs, s.B, s.Bp, s.Seff, s.nchunks,
+                                                                   (!s.disc && s.n == 1) ? 1 : 0);
     return (int)cudaGetLastError();
 }
