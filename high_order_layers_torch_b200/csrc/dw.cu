@@ -27,7 +27,7 @@ struct DwParams {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256) pw_dw_kernel(const __grid_constant__ DwParams p) {
+__global__ void __launch_bounds__(256, (N <= 5 ? 3 : 2)) pw_dw_kernel(const __grid_constant__ DwParams p) {
     constexpr int PH = (N + 1 + 3) / 4 * 4;  // floats per staged sample: phi[N], sample id, pad
     __shared__ __align__(16) float sc[8][32][PH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
