@@ -78,6 +78,7 @@ int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, floa
             s.tab.C[j] = (float)(1.0 / prod);
         }
     }
+    tc_plan(s, s.tc);
     return HOL_OK;
 }
 
@@ -96,6 +97,9 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, bool conv) {
     ws.offs = (uint32_t*)take((size_t)s.I * s.nchunks * (s.Seff + 1) * sizeof(uint32_t));
     ws.dw_part = s.ksplit > 1 ? (float*)take((size_t)s.ksplit * s.O * s.I * s.nb * sizeof(float)) : nullptr;
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
+    ws.tc_a = s.tc.enabled ? (void*)take(s.tc.a_bytes) : nullptr;
+    ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
+    ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
     ws.total = off;
     return off;
 }
@@ -172,6 +176,7 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_fc(x, s, ws, st));
     HOL_TRY(launch_pack(w, s, ws, st));
+    if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w, y, st);
     return launch_forward(s, ws, y, st);
 }
 
@@ -226,6 +231,7 @@ int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* no
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     HOL_TRY(launch_pack(w_fc, s, ws, st));
+    if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
     return launch_forward(s, ws, y_rows, st);
 }
 
@@ -279,7 +285,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     mark(1);
     if (rc == HOL_OK) rc = launch_pack(w, s, ws, st);
     mark(2);
-    if (rc == HOL_OK) rc = launch_forward(s, ws, y, st);
+    if (rc == HOL_OK) rc = s.tc.enabled ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
     mark(3);
     if (rc == HOL_OK) {
         if (n == 1)

@@ -18,6 +18,16 @@ struct BasisTab {
     float C[HOL_MAX_N];  // C[j] = 1 / prod_{m != j} (X_j - X_m)
 };
 
+// Plan of the tensor-core (tcgen05) forward for layers with few segments (tc.cu).
+struct TcPlan {
+    bool enabled;
+    int Kin;                  // dense columns per input: weights per link padded to 8
+    int BN, nNT;              // output tile width and count
+    int nkc;                  // 64-wide K chunks
+    int64_t rows_per_launch;  // batch rows expanded + multiplied per launch (bounds the Phi tiles)
+    size_t a_bytes, b_bytes;  // Phi tile / W tile storage
+};
+
 // Problem description shared by host planning code and kernels.
 struct PwShape {
     int64_t B;    // rows (samples; im2col rows for conv)
@@ -38,6 +48,7 @@ struct PwShape {
     float length, half, periodicity, half_per, two_per;
     int periodic;
     BasisTab tab;
+    TcPlan tc;
 };
 
 struct PwWorkspace {
@@ -48,6 +59,9 @@ struct PwWorkspace {
     uint32_t* offs;   // [I][nchunks][Seff+1] bucket offsets into order
     float* dw_part;   // [ksplit][O][I][nb] partial weight gradients (ksplit > 1 only)
     float* dx_rows;   // conv only: [rows][I] unfolded input gradient
+    void* tc_a;       // tensor-core path: Phi tiles (fp16 hi/lo shared-memory images)
+    void* tc_b;       // tensor-core path: W tiles
+    void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|)
     size_t total;
 };
 

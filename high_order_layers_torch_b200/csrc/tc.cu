@@ -1,0 +1,410 @@
+// Tensor-core (tcgen05) path for layers with few segments: the segment-expanded dense contraction.
+//
+//   y[b,o] = sum_k Phi[b,k] * Wt[o,k],   k = i*Kin + v,   Phi[b, i*Kin + s(b,i)*stride + j] = phi_j(xl(b,i))
+//
+// Phi has n non-zeros out of Kin (= weights per link, padded to 8) per (sample, input), so the dense
+// form spends Kin/n times the useful MACs -- but on the tensor pipe, which is worth it while
+// Kin <= ~20 n (S <= 8 for the named configs): the gather kernels are pinned to one shared-memory
+// word per FMA (25 % of the fp32 SIMT peak), the tensor pipe is ~20x that peak.
+//
+// fp32 accuracy from fp16 tensor cores: both operands are split a = hi + lo (two fp16 values,
+// 22 significant bits, power-of-two pre-scaling keeps them in the fp16 range) and the kernel issues
+// hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (dropped lo*lo term ~2^-22 relative).
+//
+// Operands are stored in global memory as ready-made shared-memory images (K-major, no-swizzle
+// UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
+// pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> global).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "kernels.cuh"
+
+#define TC_BM 128
+#define TC_BK 64
+#define TC_A_IMG (TC_BM * TC_BK * 2)  // bytes of one fp16 A image (hi or lo)
+
+struct TcScalars {      // device scalars written by pw_absmax_kernel
+    unsigned max_xl;    // bits of max |xl|
+    unsigned max_w;     // bits of max |w|
+};
+
+// power-of-two scale that maps `bound` just below 2^14 (scale >= 1 is allowed: small weights are
+// scaled UP so that their lo parts stay out of the fp16 subnormals)
+__host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
+    if (!(bound > 0.0f) || !(bound < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(bound, &e);  // bound = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, 14 - e);
+}
+// |phi_j(t)| <= max_j |C_j| * prod_m (|t| + |X_m|)
+__device__ __forceinline__ float phi_scale(float max_xl, const BasisTab& tab, int n) {
+    float cmax = 0.0f, prod = 1.0f;
+    for (int j = 0; j < n; ++j) {
+        cmax = fmaxf(cmax, fabsf(tab.C[j]));
+        prod *= (max_xl + fabsf(tab.X[j]));
+    }
+    const float bound = (n == 1) ? 1.0f : cmax * prod;  // conservative: phi_j skips one of the factors
+    const float s = pow2_scale_for(fmaxf(bound, 1.0f));
+    return fminf(s, 1.0f);  // only ever scale phi down (values <= 1 are already well inside fp16)
+}
+
+__global__ void __launch_bounds__(256) pw_absmax_kernel(const float* __restrict__ v, int64_t count, unsigned* out) {
+    float m = 0.0f;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(v[k]);
+        if (a < 3.0e38f) m = fmaxf(m, a);
+    }
+    for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like uints
+}
+
+__device__ __forceinline__ void split_store8(const float (&v)[8], float scale, uint4* hi, uint4* lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float a = v[2 * e] * scale, b = v[2 * e + 1] * scale;
+        const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+        const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+        h[e] = __halves2half2(ha, hb);
+        l[e] = __halves2half2(la, lb);
+    }
+    *hi = *reinterpret_cast<uint4*>(h);
+    *lo = *reinterpret_cast<uint4*>(l);
+}
+
+// Phi tiles: [m-tile][k-chunk][hi|lo][k/8 (8)][row (128)][8 x fp16]
+template <int N>
+__global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restrict__ xl_t, const uint16_t* __restrict__ seg_t,
+                                                           unsigned char* __restrict__ tiles, const TcScalars* sc,
+                                                           int64_t Bp, int64_t row0, int I, int Kin, int nkc, int stride,
+                                                           const __grid_constant__ BasisTab tab) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t mt = blockIdx.x;
+    const int kc = blockIdx.y;
+    const int64_t b = row0 + mt * TC_BM + r;
+    const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
+    unsigned char* base = tiles + ((mt * nkc + kc) * 2) * (int64_t)TC_A_IMG;
+    int cur_i = -1;
+    float phi[N];
+    int a0 = 0;
+    bool ok = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int kgl = half * 4 + q;
+        const int k0 = kc * TC_BK + kgl * 8;
+        const int i = k0 / Kin, v0 = k0 % Kin;
+        if (i != cur_i) {
+            cur_i = i;
+            ok = false;
+            if (i < I && b < Bp) {
+                const uint32_t sg = seg_t[(int64_t)i * Bp + b];
+                ok = !(sg & HOL_SEG_INVALID);
+                a0 = (int)(sg & HOL_SEG_MASK) * stride;
+                lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
+            }
+        }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = v0 + e - a0;
+            float val = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < N; ++jj) val = (j == jj) ? phi[jj] : val;
+            v[e] = ok ? val : 0.0f;
+        }
+        uint4* hi = reinterpret_cast<uint4*>(base + kgl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + kgl * (TC_BM * 16) + r * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// W tiles: [n-tile][k-chunk][hi|lo][k/8 (8)][row (BN)][8 x fp16],  k = i*Kin + v
+__global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
+                                                           const TcScalars* sc, int I, int O, int nb, int Kin, int nkc,
+                                                           int BN) {
+    const int nt = blockIdx.x, kc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * nkc + kc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, kgl = idx / BN;
+        const int o = nt * BN + row;
+        const int k0 = kc * TC_BK + kgl * 8;
+        const int i = k0 / Kin, v0 = k0 % Kin;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = v0 + e;
+            v[e] = (o < O && i < I && col < nb) ? w[((int64_t)o * I + i) * nb + col] : 0.0f;
+        }
+        uint4* hi = reinterpret_cast<uint4*>(base + kgl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + kgl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4, version=1 [46,48), layout NONE
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcGemmParams {
+    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
+    const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
+    float* y;                      // [rows][ldy] fp32, row-major
+    const TcScalars* sc;
+    int64_t row0, rows_valid;      // rows of this launch start at row0; rows >= rows_valid are padding
+    int n_valid, ldy, nkc, nst, n_basis;
+    BasisTab tab;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int B_IMG = BN * TC_BK * 2;
+    constexpr int STAGE_BYTES = 2 * TC_A_IMG + 2 * B_IMG;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32 (BN is 32..256, power of two)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);        // [nst]
+    uint64_t* empty = full + 8;                                    // [nst]
+    uint64_t* accum_full = full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 20);
+    unsigned char* stages = smem_raw + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x;            // n-tile fastest: CTAs that share an A tile run together
+    const int64_t mt = blockIdx.y;
+    const int nst = p.nst;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* a_src = p.a_tiles + (mt * p.nkc) * (int64_t)(2 * TC_A_IMG);
+            const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
+            for (int kc = 0; kc < p.nkc; ++kc) {
+                const int st = kc % nst;
+                mbar_wait(&empty[st], (uint32_t)(((kc / nst) & 1) ^ 1));
+                mbar_expect_tx(&full[st], STAGE_BYTES);
+                unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
+                bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
+                bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), 2 * B_IMG, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+            for (int kc = 0; kc < p.nkc; ++kc) {
+                const int st = kc % nst;
+                mbar_wait(&full[st], (uint32_t)((kc / nst) & 1));
+                tc_fence_after();
+                const uint32_t sa = smem_u32(stages + (size_t)st * STAGE_BYTES);
+                const uint32_t sb = sa + 2 * TC_A_IMG;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                    const uint64_t a_hi = umma_desc_kmajor_noswizzle(sa + kk * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t a_lo = umma_desc_kmajor_noswizzle(sa + TC_A_IMG + kk * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t b_hi = umma_desc_kmajor_noswizzle(sb + kk * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t b_lo = umma_desc_kmajor_noswizzle(sb + B_IMG + kk * 2 * LBO_B, LBO_B, SBO);
+                    umma_f16(tmem_base, a_hi, b_hi, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+                    umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+                }
+                umma_commit(&empty[st]);  // arrives when the MMAs above have finished reading this stage
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // epilogue: TMEM lane quadrant = warp % 4
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int64_t row = mt * TC_BM + q * 32 + lane;  // row inside this launch
+        const float inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) *
+                                  pow2_scale_for(__uint_as_float(p.sc->max_w)));
+        const bool rowok = row < p.rows_valid;
+        float* yrow = p.y + (p.row0 + row) * (int64_t)p.ldy + (int64_t)nt * BN;
+        const bool vec = (p.ldy & 3) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (rowok) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const int col = nt * BN + c0 + e;
+                    const float4 o4 = make_float4(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv,
+                                                  __uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
+                    if (vec && col + 3 < p.n_valid) {
+                        *reinterpret_cast<float4*>(yrow + c0 + e) = o4;
+                    } else {
+                        if (col + 0 < p.n_valid) yrow[c0 + e + 0] = o4.x;
+                        if (col + 1 < p.n_valid) yrow[c0 + e + 1] = o4.y;
+                        if (col + 2 < p.n_valid) yrow[c0 + e + 2] = o4.z;
+                        if (col + 3 < p.n_valid) yrow[c0 + e + 3] = o4.w;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// planning + launch
+// ---------------------------------------------------------------------------------------
+static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32)); }
+
+bool tc_plan(const PwShape& s, TcPlan& t) {
+    t.enabled = false;
+    const char* off = getenv("HOL_DISABLE_TC");
+    if (off && off[0] == '1') return false;
+    t.Kin = (s.nb + 7) / 8 * 8;
+    // the dense form costs 3*Kin tensor MACs per n useful fp32 FMAs
+    if (t.Kin > 20 * s.n) return false;
+    if (s.O < 16 || s.I * (int64_t)t.Kin < 256) return false;   // too small to be worth a tile
+    t.BN = tc_bn_for(s.O);
+    t.nNT = (s.O + t.BN - 1) / t.BN;
+    const int64_t K = (int64_t)s.I * t.Kin;
+    t.nkc = (int)((K + TC_BK - 1) / TC_BK);
+    // rows per launch: bound the Phi tiles to ~8 GiB
+    const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
+    int64_t rows = (int64_t)(8ll << 30) / bytes_per_row / TC_BM * TC_BM;
+    if (rows < TC_BM) return false;
+    if (rows > s.Bp) rows = s.Bp;
+    rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+    t.rows_per_launch = rows;
+    t.a_bytes = (size_t)(rows / TC_BM) * t.nkc * 2 * TC_A_IMG;
+    t.b_bytes = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);
+    t.enabled = true;
+    return true;
+}
+
+template <int N>
+static int expand_n(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, int64_t row0, int64_t rows, cudaStream_t st) {
+    dim3 grid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
+    pw_tc_expand_kernel<N><<<grid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, (const TcScalars*)ws.tc_scalars,
+                                                 s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab);
+    return (int)cudaGetLastError();
+}
+
+template <int BN>
+static int gemm_bn(const TcGemmParams& p, int64_t rows, int nNT, cudaStream_t st) {
+    constexpr int STAGE = 2 * TC_A_IMG + 2 * BN * TC_BK * 2;
+    int nst = (HOL_SMEM_BUDGET - 1024) / STAGE;
+    if (nst > 6) nst = 6;
+    if (nst < 2) return HOL_EUNSUPPORTED;
+    TcGemmParams q = p;
+    q.nst = nst;
+    const size_t smem = 1024 + (size_t)nst * STAGE;
+    auto kern = pw_tc_gemm_kernel<BN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)nNT, (unsigned)(rows / TC_BM));
+    kern<<<grid, 192, smem, st>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(TcScalars), st);
+    if (e != cudaSuccess) return (int)e;
+    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl);
+    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(w, (int64_t)s.O * s.I * s.nb, &sc->max_w);
+    dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc);
+    pw_tc_pack_w_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.nkc, t.BN);
+    int rc = (int)cudaGetLastError();
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        const int64_t rows = (s.Bp - row0 < t.rows_per_launch) ? (s.Bp - row0 + TC_BM - 1) / TC_BM * TC_BM : t.rows_per_launch;
+        switch (s.n) {
+            case 1: rc = expand_n<1>(s, ws, t, row0, rows, st); break;
+            case 2: rc = expand_n<2>(s, ws, t, row0, rows, st); break;
+            case 3: rc = expand_n<3>(s, ws, t, row0, rows, st); break;
+            case 4: rc = expand_n<4>(s, ws, t, row0, rows, st); break;
+            case 5: rc = expand_n<5>(s, ws, t, row0, rows, st); break;
+            case 6: rc = expand_n<6>(s, ws, t, row0, rows, st); break;
+            case 7: rc = expand_n<7>(s, ws, t, row0, rows, st); break;
+            case 8: rc = expand_n<8>(s, ws, t, row0, rows, st); break;
+            case 9: rc = expand_n<9>(s, ws, t, row0, rows, st); break;
+            case 10: rc = expand_n<10>(s, ws, t, row0, rows, st); break;
+            default: rc = HOL_EUNSUPPORTED;
+        }
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        p.a_tiles = (const unsigned char*)ws.tc_a;
+        p.b_tiles = (const unsigned char*)ws.tc_b;
+        p.y = y;
+        p.sc = sc;
+        p.row0 = row0;
+        p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
+        p.n_valid = s.O;
+        p.ldy = s.O;
+        p.nkc = t.nkc;
+        p.nst = 2;
+        p.n_basis = s.n;
+        p.tab = s.tab;
+        switch (t.BN) {
+            case 256: rc = gemm_bn<256>(p, rows, t.nNT, st); break;
+            case 128: rc = gemm_bn<128>(p, rows, t.nNT, st); break;
+            case 64: rc = gemm_bn<64>(p, rows, t.nNT, st); break;
+            case 32: rc = gemm_bn<32>(p, rows, t.nNT, st); break;
+            default: rc = HOL_EUNSUPPORTED;
+        }
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}
