@@ -14,7 +14,7 @@
 // Operands are stored in global memory as ready-made shared-memory images (K-major, no-swizzle
 // UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
 // pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 =
-// MMA issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> global).
+// MMA issuer (one elected lane), warps 2-9 = epilogue (tcgen05.ld -> fp32 register sums -> global).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -184,33 +184,49 @@ struct TcGemmParams {
     float* y;                      // [rows][ldy] fp32, row-major
     const TcScalars* sc;
     int64_t row0, rows_valid;      // rows of this launch start at row0; rows >= rows_valid are padding
-    int n_valid, ldy, nkc, nst, n_basis;
+    int n_valid, ldy, nkc, nst, n_basis, flush_chunks;
     BasisTab tab;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The tensor core accumulates with round-toward-zero: every chained MMA instruction loses on
+// average half an ulp of the running sum, a bias that grows linearly with K (measured 3e-5 at
+// K = 3136).  So the TMEM accumulator only ever holds `flush_chunks` k-chunks (<= 36 instructions,
+// bias <= 2e-6); the epilogue warps drain it into round-to-nearest fp32 register sums while the
+// MMA warp fills the other of the two TMEM accumulators.
 template <int BN>
-__global__ void __launch_bounds__(192, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+__global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int B_IMG = BN * TC_BK * 2;
     constexpr int STAGE_BYTES = 2 * TC_A_IMG + 2 * B_IMG;
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32 (BN is 32..256, power of two)
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators; power of two >= 32
+    constexpr int HALF = BN / 2;                          // columns per epilogue thread
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);        // [nst]
     uint64_t* empty = full + 8;                                    // [nst]
-    uint64_t* accum_full = full + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 20);
+    uint64_t* tmem_full = full + 16;                               // [2]
+    uint64_t* tmem_empty = full + 18;                              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x;            // n-tile fastest: CTAs that share an A tile run together
     const int64_t mt = blockIdx.y;
     const int nst = p.nst;
+    const int FG = p.flush_chunks;
+    const int ngroups = (p.nkc + FG - 1) / FG;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+        }
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -242,60 +258,85 @@ __global__ void __launch_bounds__(192, 1) pw_tc_gemm_kernel(const __grid_constan
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+            int g = 0;
             for (int kc = 0; kc < p.nkc; ++kc) {
                 const int st = kc % nst;
+                const int acc = g & 1;
+                const bool first = (kc % FG) == 0;
+                if (first) {
+                    mbar_wait(&tmem_empty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));  // drained by the epilogue
+                    tc_fence_after();
+                }
                 mbar_wait(&full[st], (uint32_t)((kc / nst) & 1));
                 tc_fence_after();
                 const uint32_t sa = smem_u32(stages + (size_t)st * STAGE_BYTES);
                 const uint32_t sb = sa + 2 * TC_A_IMG;
+                const uint32_t td = tmem_base + (uint32_t)(acc * BN);
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 16; ++kk) {
                     const uint64_t a_hi = umma_desc_kmajor_noswizzle(sa + kk * 2 * LBO_A, LBO_A, SBO);
                     const uint64_t a_lo = umma_desc_kmajor_noswizzle(sa + TC_A_IMG + kk * 2 * LBO_A, LBO_A, SBO);
                     const uint64_t b_hi = umma_desc_kmajor_noswizzle(sb + kk * 2 * LBO_B, LBO_B, SBO);
                     const uint64_t b_lo = umma_desc_kmajor_noswizzle(sb + B_IMG + kk * 2 * LBO_B, LBO_B, SBO);
-                    umma_f16(tmem_base, a_hi, b_hi, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-                    umma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
-                    umma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+                    umma_f16(td, a_hi, b_hi, idesc, (first && kk == 0) ? 0u : 1u);
+                    umma_f16(td, a_hi, b_lo, idesc, 1u);
+                    umma_f16(td, a_lo, b_hi, idesc, 1u);
                 }
                 umma_commit(&empty[st]);  // arrives when the MMAs above have finished reading this stage
+                if ((kc % FG) == FG - 1 || kc == p.nkc - 1) {
+                    umma_commit(&tmem_full[acc]);
+                    ++g;
+                }
             }
-            umma_commit(accum_full);
         }
     } else {
-        // epilogue: TMEM lane quadrant = warp % 4
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
+        // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
         const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        float racc[HALF];
+#pragma unroll
+        for (int e = 0; e < HALF; ++e) racc[e] = 0.0f;
+        for (int g = 0; g < ngroups; ++g) {
+            const int acc = g & 1;
+            mbar_wait(&tmem_full[acc], (uint32_t)((g >> 1) & 1));
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * HALF);
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t0 + (uint32_t)c0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    if (c0 + e < HALF) racc[c0 + e] += __uint_as_float(v[e]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
         const int64_t row = mt * TC_BM + q * 32 + lane;  // row inside this launch
         const float inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) *
                                   pow2_scale_for(__uint_as_float(p.sc->max_w)));
-        const bool rowok = row < p.rows_valid;
-        float* yrow = p.y + (p.row0 + row) * (int64_t)p.ldy + (int64_t)nt * BN;
-        const bool vec = (p.ldy & 3) == 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (rowok) {
+        if (row < p.rows_valid) {
+            const int colbase = nt * BN + h * HALF;
+            float* yrow = p.y + (p.row0 + row) * (int64_t)p.ldy + colbase;
+            const bool vec = (p.ldy & 3) == 0;
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const int col = nt * BN + c0 + e;
-                    const float4 o4 = make_float4(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv,
-                                                  __uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv);
-                    if (vec && col + 3 < p.n_valid) {
-                        *reinterpret_cast<float4*>(yrow + c0 + e) = o4;
-                    } else {
-                        if (col + 0 < p.n_valid) yrow[c0 + e + 0] = o4.x;
-                        if (col + 1 < p.n_valid) yrow[c0 + e + 1] = o4.y;
-                        if (col + 2 < p.n_valid) yrow[c0 + e + 2] = o4.z;
-                        if (col + 3 < p.n_valid) yrow[c0 + e + 3] = o4.w;
-                    }
+            for (int e = 0; e < HALF; e += 4) {
+                const int col = colbase + e;
+                const float4 o4 = make_float4(racc[e] * inv, racc[e + 1] * inv, racc[e + 2] * inv, racc[e + 3] * inv);
+                if (vec && col + 3 < p.n_valid) {
+                    *reinterpret_cast<float4*>(yrow + e) = o4;
+                } else {
+                    if (col + 0 < p.n_valid) yrow[e + 0] = o4.x;
+                    if (col + 1 < p.n_valid) yrow[e + 1] = o4.y;
+                    if (col + 2 < p.n_valid) yrow[e + 2] = o4.z;
+                    if (col + 3 < p.n_valid) yrow[e + 3] = o4.w;
                 }
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -349,12 +390,13 @@ static int gemm_bn(const TcGemmParams& p, int64_t rows, int nNT, cudaStream_t st
     if (nst < 2) return HOL_EUNSUPPORTED;
     TcGemmParams q = p;
     q.nst = nst;
+    q.flush_chunks = BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
     const size_t smem = 1024 + (size_t)nst * STAGE;
     auto kern = pw_tc_gemm_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)nNT, (unsigned)(rows / TC_BM));
-    kern<<<grid, 192, smem, st>>>(q);
+    kern<<<grid, 320, smem, st>>>(q);
     return (int)cudaGetLastError();
 }
 
