@@ -114,20 +114,28 @@ int conv_out(int H, int K, int stride, int padding, int dilation) {
         if (_e != HOL_OK) return _e; \
     } while (0)
 
-int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int dx_transposed, float* dw,
-                    cudaStream_t st) {
+// `packed`: the gather-path weight packing (wk) in the workspace is valid
+int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, const float* w, float* dx,
+                    int dx_transposed, float* dw, bool packed, cudaStream_t st) {
     if (dx) {
         if (s.n == 1) {
             const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
             cudaError_t e = cudaMemsetAsync(dx, 0, bytes, st);
             if (e != cudaSuccess) return (int)e;
+        } else if (s.tc.enabled) {
+            HOL_TRY(launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, dx_transposed, st));
         } else {
+            if (!packed) HOL_TRY(launch_pack(w, s, ws, st));
             HOL_TRY(launch_backward_dx(s, ws, gy, dx, dx_transposed, st));
         }
     }
     if (dw) {
-        HOL_TRY(launch_bucket_sort(s, ws, st));
-        HOL_TRY(launch_backward_dw(s, ws, gy, dw, st));
+        if (s.tc.enabled) {
+            HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, st));
+        } else {
+            HOL_TRY(launch_bucket_sort(s, ws, st));
+            HOL_TRY(launch_backward_dw(s, ws, gy, dw, st));
+        }
     }
     return HOL_OK;
 }
@@ -175,8 +183,8 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_fc(x, s, ws, st));
-    HOL_TRY(launch_pack(w, s, ws, st));
     if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w, y, st);
+    HOL_TRY(launch_pack(w, s, ws, st));
     return launch_forward(s, ws, y, st);
 }
 
@@ -198,9 +206,8 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
     if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_fc(x, s, ws, st));
-        if (dx && n > 1) HOL_TRY(launch_pack(w, s, ws, st));
     }
-    return backward_common(s, ws, gy, dx, 0, dw, st);
+    return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0, st);
 }
 
 size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
@@ -230,8 +237,8 @@ int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* no
     if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
-    HOL_TRY(launch_pack(w_fc, s, ws, st));
     if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
+    HOL_TRY(launch_pack(w_fc, s, ws, st));
     return launch_forward(s, ws, y_rows, st);
 }
 
@@ -258,9 +265,8 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
     if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
-        if (dx && n > 1) HOL_TRY(launch_pack(w_fc, s, ws, st));
     }
-    HOL_TRY(backward_common(s, ws, gy_rows, dx ? ws.dx_rows : nullptr, 1, dw_fc, st));
+    HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc, (flags & HOL_WS_PREPARED) != 0, st));
     if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     return HOL_OK;
 }
@@ -283,7 +289,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     mark(0);
     rc = launch_prep_fc(x, s, ws, st);
     mark(1);
-    if (rc == HOL_OK) rc = launch_pack(w, s, ws, st);
+    if (rc == HOL_OK && !s.tc.enabled) rc = launch_pack(w, s, ws, st);
     mark(2);
     if (rc == HOL_OK) rc = s.tc.enabled ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
     mark(3);
@@ -291,12 +297,12 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
         if (n == 1)
             cudaMemsetAsync(dx, 0, (size_t)B * I * 4, st);
         else
-            rc = launch_backward_dx(s, ws, gy, dx, 0, st);
+            rc = s.tc.enabled ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, st) : launch_backward_dx(s, ws, gy, dx, 0, st);
     }
     mark(4);
-    if (rc == HOL_OK) rc = launch_bucket_sort(s, ws, st);
+    if (rc == HOL_OK && !s.tc.enabled) rc = launch_bucket_sort(s, ws, st);
     mark(5);
-    if (rc == HOL_OK) rc = launch_backward_dw(s, ws, gy, dw, st);
+    if (rc == HOL_OK) rc = s.tc.enabled ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st);
     mark(6);
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == HOL_OK && e != cudaSuccess) rc = (int)e;

@@ -24,6 +24,8 @@ struct TcPlan {
     int Kin;                  // dense columns per input: weights per link padded to 8
     int BN, nNT;              // output tile width and count
     int nkc;                  // 64-wide K chunks
+    int BNx, nNTx, noc;       // dX: N tile over the dense columns (multiple of 2*Kin), its count, 64-wide output chunks
+    int nMTw;                 // dW: 128-row M tiles over the dense columns
     int64_t rows_per_launch;  // batch rows expanded + multiplied per launch (bounds the Phi tiles)
     size_t a_bytes, b_bytes;  // Phi tile / W tile storage
 };

@@ -22,6 +22,10 @@ int launch_backward_dw(const PwShape& s, const PwWorkspace& ws, const float* gy,
 // tensor-core forward (tc.cu)
 bool tc_plan(const PwShape& s, TcPlan& t);
 int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st);
+int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
+                          cudaStream_t st);
+int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
+                          float* dx, int transposed, cudaStream_t st);
 
 // usable dynamic shared memory per CTA on sm_100 (227 KB) minus a safety margin
 #define HOL_SMEM_BUDGET (220 * 1024)

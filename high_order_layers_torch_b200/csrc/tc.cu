@@ -1,15 +1,23 @@
 // Tensor-core (tcgen05) path for layers with few segments: the segment-expanded dense contraction.
 //
-//   y[b,o] = sum_k Phi[b,k] * Wt[o,k],   k = i*Kin + v,   Phi[b, i*Kin + s(b,i)*stride + j] = phi_j(xl(b,i))
+//   Phi[b, i*Kin + s(b,i)*stride + j] = phi_j(xl(b,i))        (n non-zeros out of Kin per (sample, input))
+//   forward : y[b,o]        = sum_k Phi[b,k]  * W[o,k]         M = batch,  N = O,      K = I*Kin
+//   dW      : dW[o,k]       = sum_b Phi[b,k]  * gy[b,o]        M = I*Kin,  N = O,      K = batch
+//   dX      : T[b,k]        = sum_o gy[b,o]   * W[o,k]         M = batch,  N = I*Kin,  K = O
+//             dX[b,i]       = chain(b,i) * sum_j phi'_j(xl) * T[b, i*Kin + s*stride + j]   (epilogue gather)
 //
-// Phi has n non-zeros out of Kin (= weights per link, padded to 8) per (sample, input), so the dense
-// form spends Kin/n times the useful MACs -- but on the tensor pipe, which is worth it while
+// The dense form spends Kin/n times the useful MACs -- but on the tensor pipe, which pays while
 // Kin <= ~20 n (S <= 8 for the named configs): the gather kernels are pinned to one shared-memory
-// word per FMA (25 % of the fp32 SIMT peak), the tensor pipe is ~20x that peak.
+// word per FMA (25 % of the fp32 SIMT peak); the tensor pipe is ~20x that peak.
 //
-// fp32 accuracy from fp16 tensor cores: both operands are split a = hi + lo (two fp16 values,
-// 22 significant bits, power-of-two pre-scaling keeps them in the fp16 range) and the kernel issues
+// fp32 accuracy from fp16 tensor cores: both operands are split a = hi + lo (two fp16 values, 22
+// significant bits, power-of-two pre-scaling keeps them in the fp16 range) and the kernel issues
 // hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (dropped lo*lo term ~2^-22 relative).
+// The tensor core accumulates with round-toward-zero: every chained MMA instruction loses on
+// average half an ulp of the running sum, a bias that grows linearly with K (measured 3e-5 at
+// K = 3136).  So a TMEM accumulator only ever holds <= 36 chained instructions (bias <= 2e-6); the
+// epilogue warps drain it into round-to-nearest fp32 register sums while the MMA warp fills the
+// other of the two TMEM accumulators.
 //
 // Operands are stored in global memory as ready-made shared-memory images (K-major, no-swizzle
 // UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
@@ -23,13 +31,15 @@
 #define TC_BM 128
 #define TC_BK 64
 #define TC_A_IMG (TC_BM * TC_BK * 2)  // bytes of one fp16 A image (hi or lo)
+#define TC_MAXHALF 128                // register sums per epilogue thread (BN <= 256)
 
-struct TcScalars {      // device scalars written by pw_absmax_kernel
-    unsigned max_xl;    // bits of max |xl|
-    unsigned max_w;     // bits of max |w|
+enum { EPI_Y = 0, EPI_DW = 1, EPI_DX = 2 };
+
+struct TcScalars {      // device scalars written by pw_absmax_kernel (bits of non-negative floats)
+    unsigned max_xl, max_w, max_gy;
 };
 
-// power-of-two scale that maps `bound` just below 2^14 (scale >= 1 is allowed: small weights are
+// power-of-two scale that maps `bound` just below 2^14 (scale >= 1 is allowed: small values are
 // scaled UP so that their lo parts stay out of the fp16 subnormals)
 __host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
     if (!(bound > 0.0f) || !(bound < 3.0e38f)) return 1.0f;
@@ -37,16 +47,15 @@ __host__ __device__ __forceinline__ float pow2_scale_for(float bound) {
     frexpf(bound, &e);  // bound = m * 2^e, m in [0.5, 1)
     return ldexpf(1.0f, 14 - e);
 }
-// |phi_j(t)| <= max_j |C_j| * prod_m (|t| + |X_m|)
+// |phi_j(t)| <= max_j |C_j| * prod_m (|t| + |X_m|)   (conservative: phi_j skips one of the factors)
 __device__ __forceinline__ float phi_scale(float max_xl, const BasisTab& tab, int n) {
     float cmax = 0.0f, prod = 1.0f;
     for (int j = 0; j < n; ++j) {
         cmax = fmaxf(cmax, fabsf(tab.C[j]));
         prod *= (max_xl + fabsf(tab.X[j]));
     }
-    const float bound = (n == 1) ? 1.0f : cmax * prod;  // conservative: phi_j skips one of the factors
-    const float s = pow2_scale_for(fmaxf(bound, 1.0f));
-    return fminf(s, 1.0f);  // only ever scale phi down (values <= 1 are already well inside fp16)
+    const float bound = (n == 1) ? 1.0f : cmax * prod;
+    return fminf(pow2_scale_for(fmaxf(bound, 1.0f)), 1.0f);  // only ever scale phi down
 }
 
 __global__ void __launch_bounds__(256) pw_absmax_kernel(const float* __restrict__ v, int64_t count, unsigned* out) {
@@ -73,7 +82,12 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], float scale, u
     *lo = *reinterpret_cast<uint4*>(l);
 }
 
-// Phi tiles: [m-tile][k-chunk][hi|lo][k/8 (8)][row (128)][8 x fp16]
+// ---------------------------------------------------------------------------------------
+// operand builders (HBM-bound).  Image layout of a tile with R rows: [k/8 (8)][row (R)][8 x fp16],
+// hi image then lo image.
+// ---------------------------------------------------------------------------------------
+
+// forward A: Phi tiles [m-tile (128 samples)][k-chunk], k = i*Kin + v
 template <int N>
 __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restrict__ xl_t, const uint16_t* __restrict__ seg_t,
                                                            unsigned char* __restrict__ tiles, const TcScalars* sc,
@@ -119,7 +133,55 @@ __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restri
     }
 }
 
-// W tiles: [n-tile][k-chunk][hi|lo][k/8 (8)][row (BN)][8 x fp16],  k = i*Kin + v
+// dW A: Phi^T tiles [m-tile (128 rows k = i*Kin+v)][batch chunk (64 samples)]; one thread = one
+// (input, 8 samples): evaluates the basis once and writes the Kin rows of its input.
+template <int N>
+__global__ void __launch_bounds__(256) pw_tc_expand_t_kernel(const float* __restrict__ xl_t,
+                                                             const uint16_t* __restrict__ seg_t,
+                                                             unsigned char* __restrict__ tiles, const TcScalars* sc,
+                                                             int64_t Bp, int64_t row0, int64_t nbg, int I, int Kin,
+                                                             int nbc, int stride, const __grid_constant__ BasisTab tab) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t bg = t % nbg;  // 8-sample group inside this launch (fastest: coalesced xl/seg reads)
+    const int i = (int)(t / nbg);
+    if (i >= I) return;
+    const int64_t b0 = row0 + bg * 8;
+    const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
+    float phi[8][N];
+    int a0[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int64_t b = b0 + e;
+        uint32_t sg = HOL_SEG_INVALID;
+        float xl = 0.0f;
+        if (b < Bp) {
+            sg = seg_t[(int64_t)i * Bp + b];
+            xl = xl_t[(int64_t)i * Bp + b];
+        }
+        lagrange_basis<N>(xl, tab, phi[e]);
+        a0[e] = (sg & HOL_SEG_INVALID) ? -100000 : (int)(sg & HOL_SEG_MASK) * stride;
+    }
+    const int bc = (int)(bg / 8), bgl = (int)(bg % 8);
+    for (int v = 0; v < Kin; ++v) {
+        const int R = i * Kin + v;
+        const int mt = R / TC_BM, r = R % TC_BM;
+        float val[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = v - a0[e];
+            float x = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < N; ++jj) x = (j == jj) ? phi[e][jj] : x;
+            val[e] = x;
+        }
+        unsigned char* base = tiles + (((int64_t)mt * nbc + bc) * 2) * (int64_t)TC_A_IMG;
+        uint4* hi = reinterpret_cast<uint4*>(base + bgl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + bgl * (TC_BM * 16) + r * 16);
+        split_store8(val, scale, hi, lo);
+    }
+}
+
+// forward B: W tiles [n-tile (BN outputs)][k-chunk], k = i*Kin + v
 __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
                                                            const TcScalars* sc, int I, int O, int nb, int Kin, int nkc,
                                                            int BN) {
@@ -144,6 +206,72 @@ __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restri
     }
 }
 
+// dX B: W^T tiles [n-tile (BN rows k = i*Kin+v)][o-chunk (64 outputs)]
+__global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
+                                                            const TcScalars* sc, int I, int O, int nb, int Kin, int noc,
+                                                            int BN) {
+    const int nt = blockIdx.x, oc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * noc + oc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, ogl = idx / BN;
+        const int R = nt * BN + row;
+        const int i = R / Kin, col = R % Kin;
+        const int o0 = oc * TC_BK + ogl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            v[e] = (o0 + e < O && i < I && col < nb) ? w[((int64_t)(o0 + e) * I + i) * nb + col] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + ogl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + ogl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dX A: gy tiles [m-tile (128 samples)][o-chunk]
+__global__ void __launch_bounds__(256) pw_tc_pack_gy_kernel(const float* __restrict__ gy, unsigned char* __restrict__ tiles,
+                                                            const TcScalars* sc, int64_t B, int64_t row0, int O, int noc) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t mt = blockIdx.x;
+    const int oc = blockIdx.y;
+    const int64_t b = row0 + mt * TC_BM + r;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_gy));
+    unsigned char* base = tiles + ((mt * noc + oc) * 2) * (int64_t)TC_A_IMG;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ogl = half * 4 + q;
+        const int o0 = oc * TC_BK + ogl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (b < B && o0 + e < O) ? gy[b * O + o0 + e] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + ogl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + ogl * (TC_BM * 16) + r * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dW B: gy^T tiles [n-tile (BN outputs)][batch chunk (64 samples)]
+__global__ void __launch_bounds__(256) pw_tc_pack_gyt_kernel(const float* __restrict__ gy, unsigned char* __restrict__ tiles,
+                                                             const TcScalars* sc, int64_t B, int64_t row0, int O, int nbc,
+                                                             int BN) {
+    const int nt = blockIdx.x, bc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_gy));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * nbc + bc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, bgl = idx / BN;
+        const int o = nt * BN + row;
+        const int64_t b0 = row0 + (int64_t)bc * TC_BK + bgl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (o < O && b0 + e < B) ? gy[(b0 + e) * O + o] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + bgl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + bgl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // tcgen05 helpers
 // ---------------------------------------------------------------------------------------
@@ -164,6 +292,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -181,42 +312,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct TcGemmParams {
     const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
     const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
-    float* y;                      // [rows][ldy] fp32, row-major
+    float* out;                    // EPI_Y: y[rows][ld]; EPI_DW: dw[O][I][nb]; EPI_DX: dx[B][I] or dx_t[I][Bp]
     const TcScalars* sc;
-    int64_t row0, rows_valid;      // rows of this launch start at row0; rows >= rows_valid are padding
-    int n_valid, ldy, nkc, nst, n_basis, flush_chunks;
+    const float* xl_t;             // EPI_DX
+    const uint16_t* seg_t;         // EPI_DX
+    int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
+    int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
+    int I, nb, Kin, stride, transposed;
+    float length, Sf, inv_extra;
     BasisTab tab;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// The tensor core accumulates with round-toward-zero: every chained MMA instruction loses on
-// average half an ulp of the running sum, a bias that grows linearly with K (measured 3e-5 at
-// K = 3136).  So the TMEM accumulator only ever holds `flush_chunks` k-chunks (<= 36 instructions,
-// bias <= 2e-6); the epilogue warps drain it into round-to-nearest fp32 register sums while the
-// MMA warp fills the other of the two TMEM accumulators.
-template <int BN>
+template <int EPI>
 __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int B_IMG = BN * TC_BK * 2;
-    constexpr int STAGE_BYTES = 2 * TC_A_IMG + 2 * B_IMG;
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators; power of two >= 32
-    constexpr int HALF = BN / 2;                          // columns per epilogue thread
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);        // [nst]
-    uint64_t* empty = full + 8;                                    // [nst]
-    uint64_t* tmem_full = full + 16;                               // [2]
-    uint64_t* tmem_empty = full + 18;                              // [2]
+    const int BN = p.BN;
+    const int B_IMG = BN * TC_BK * 2;
+    const int STAGE_BYTES = 2 * TC_A_IMG + 2 * B_IMG;
+    const int HALF = BN / 2;  // columns per epilogue thread
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [nst]
+    uint64_t* empty = full + 8;                              // [nst]
+    uint64_t* tmem_full = full + 16;                         // [2]
+    uint64_t* tmem_empty = full + 18;                        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x;            // n-tile fastest: CTAs that share an A tile run together
+    const int nt = blockIdx.x;  // n-tile fastest: CTAs that share an A tile run together
     const int64_t mt = blockIdx.y;
     const int nst = p.nst;
     const int FG = p.flush_chunks;
     const int ngroups = (p.nkc + FG - 1) / FG;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;  // two accumulators; power of two >= 32
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) {
@@ -231,7 +359,7 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)TMEM_COLS)
+                     "r"(tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -247,17 +375,17 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
             for (int kc = 0; kc < p.nkc; ++kc) {
                 const int st = kc % nst;
                 mbar_wait(&empty[st], (uint32_t)(((kc / nst) & 1) ^ 1));
-                mbar_expect_tx(&full[st], STAGE_BYTES);
+                mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
                 unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
                 bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
-                bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), 2 * B_IMG, &full[st]);
+                bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+            const uint32_t LBO_A = TC_BM * 16, LBO_B = (uint32_t)BN * 16, SBO = 128;
             int g = 0;
             for (int kc = 0; kc < p.nkc; ++kc) {
                 const int st = kc % nst;
@@ -293,46 +421,115 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
         // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;
-        float racc[HALF];
+        float racc[TC_MAXHALF];
 #pragma unroll
-        for (int e = 0; e < HALF; ++e) racc[e] = 0.0f;
+        for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
         for (int g = 0; g < ngroups; ++g) {
             const int acc = g & 1;
             mbar_wait(&tmem_full[acc], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * HALF);
 #pragma unroll
-            for (int c0 = 0; c0 < HALF; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(t0 + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < TC_MAXHALF; c0 += 32) {
+                if (c0 < HALF) {
+                    uint32_t v[32];
+                    tmem_ld32(t0 + (uint32_t)c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    if (c0 + e < HALF) racc[c0 + e] += __uint_as_float(v[e]);
+                    for (int e = 0; e < 32; ++e) racc[c0 + e] += __uint_as_float(v[e]);  // columns >= HALF: unused
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        const int64_t row = mt * TC_BM + q * 32 + lane;  // row inside this launch
-        const float inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) *
-                                  pow2_scale_for(__uint_as_float(p.sc->max_w)));
-        if (row < p.rows_valid) {
-            const int colbase = nt * BN + h * HALF;
-            float* yrow = p.y + (p.row0 + row) * (int64_t)p.ldy + colbase;
-            const bool vec = (p.ldy & 3) == 0;
+        const int rl = q * 32 + lane;             // row inside the 128-row tile
+        const int64_t row = mt * TC_BM + rl;      // row inside this launch
+        const int colbase = nt * BN + h * HALF;
+
+        if (EPI == EPI_Y) {
+            const float inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) *
+                                      pow2_scale_for(__uint_as_float(p.sc->max_w)));
+            if (row < p.rows_valid) {
+                float* yrow = p.out + (p.row0 + row) * (int64_t)p.ld + colbase;
+                const bool vec = (p.ld & 3) == 0 && (HALF & 3) == 0;
 #pragma unroll
-            for (int e = 0; e < HALF; e += 4) {
-                const int col = colbase + e;
-                const float4 o4 = make_float4(racc[e] * inv, racc[e + 1] * inv, racc[e + 2] * inv, racc[e + 3] * inv);
-                if (vec && col + 3 < p.n_valid) {
-                    *reinterpret_cast<float4*>(yrow + e) = o4;
-                } else {
-                    if (col + 0 < p.n_valid) yrow[e + 0] = o4.x;
-                    if (col + 1 < p.n_valid) yrow[e + 1] = o4.y;
-                    if (col + 2 < p.n_valid) yrow[e + 2] = o4.z;
-                    if (col + 3 < p.n_valid) yrow[e + 3] = o4.w;
+                for (int e = 0; e < TC_MAXHALF; e += 4) {
+                    if (e < HALF) {
+                        const int col = colbase + e;
+                        const float4 o4 = make_float4(racc[e] * inv, racc[e + 1] * inv, racc[e + 2] * inv, racc[e + 3] * inv);
+                        if (vec && col + 3 < p.n_valid) {
+                            *reinterpret_cast<float4*>(yrow + e) = o4;
+                        } else {
+                            if (col + 0 < p.n_valid) yrow[e + 0] = o4.x;
+                            if (col + 1 < p.n_valid) yrow[e + 1] = o4.y;
+                            if (col + 2 < p.n_valid) yrow[e + 2] = o4.z;
+                            if (col + 3 < p.n_valid) yrow[e + 3] = o4.w;
+                        }
+                    }
                 }
+            }
+        } else if (EPI == EPI_DW) {
+            // row = dense column k = i*Kin + v, columns = outputs; write the reference layout dw[o][i][v]
+            const float inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) *
+                                      pow2_scale_for(__uint_as_float(p.sc->max_gy)));
+            const int i = (int)(row / p.Kin), v = (int)(row % p.Kin);
+            if (i < p.I && v < p.nb) {
+                const bool accumulate = p.row0 > 0;
+#pragma unroll
+                for (int e = 0; e < TC_MAXHALF; ++e) {
+                    if (e < HALF) {
+                        const int o = colbase + e;
+                        if (o < p.n_valid) {
+                            float* dst = p.out + ((int64_t)o * p.I + i) * p.nb + v;
+                            *dst = accumulate ? *dst + racc[e] * inv : racc[e] * inv;
+                        }
+                    }
+                }
+            }
+        } else {
+            // EPI_DX: stage T[128][BN] in the (now idle) pipeline buffers, then every thread gathers the
+            // n active columns of each of its inputs.  After the last tmem_full wait all MMAs have
+            // completed, so the stages are no longer read.
+            float* T = reinterpret_cast<float*>(stages);
+            const int pitch = BN + 1;
+#pragma unroll
+            for (int e = 0; e < TC_MAXHALF; ++e)
+                if (e < HALF) T[rl * pitch + h * HALF + e] = racc[e];
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+            const float inv = p.inv_extra / (pow2_scale_for(__uint_as_float(p.sc->max_gy)) *
+                                             pow2_scale_for(__uint_as_float(p.sc->max_w)));
+            const int64_t b = p.row0 + row;
+            const int ninp = HALF / p.Kin;
+            const int n = p.n_basis;
+            for (int ii = 0; ii < ninp; ++ii) {
+                const int i = colbase / p.Kin + ii;
+                if (i >= p.I || b >= p.Bp) continue;
+                const int64_t idx = (int64_t)i * p.Bp + b;
+                const uint32_t sg = p.seg_t[idx];
+                const float t = p.xl_t[idx];
+                const int s = (int)(sg & HOL_SEG_MASK);
+                const float* Trow = T + rl * pitch + h * HALF + ii * p.Kin + s * p.stride;
+                // d phi_j / dt by the product-rule recurrence (see lagrange_basis_derivative)
+                float sum = 0.0f;
+                for (int j = 0; j < n; ++j) {
+                    float P = 1.0f, Ssum = 0.0f;
+                    for (int m = 0; m < n; ++m) {
+                        if (m == j) continue;
+                        const float d = t - p.tab.X[m];
+                        Ssum = fmaf(Ssum, d, P);
+                        P *= d;
+                    }
+                    sum = fmaf(Ssum * p.tab.C[j], Trow[j], sum);
+                }
+                const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
+                const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
+                float chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
+                if (sg & HOL_SEG_MIRROR) chain = -chain;
+                const float outv = (sg & HOL_SEG_INVALID) ? 0.0f : sum * inv * chain;
+                if (p.transposed)
+                    p.out[idx] = outv;
+                else if (row < p.rows_valid)
+                    p.out[b * p.I + i] = outv;
             }
         }
     }
@@ -340,14 +537,14 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // planning + launch
 // ---------------------------------------------------------------------------------------
-static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32)); }
+static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : 64); }
 
 bool tc_plan(const PwShape& s, TcPlan& t) {
     t.enabled = false;
@@ -355,97 +552,210 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     if (off && off[0] == '1') return false;
     t.Kin = (s.nb + 7) / 8 * 8;
     // the dense form costs 3*Kin tensor MACs per n useful fp32 FMAs
-    if (t.Kin > 20 * s.n) return false;
-    if (s.O < 16 || s.I * (int64_t)t.Kin < 256) return false;   // too small to be worth a tile
+    if (t.Kin > 20 * s.n || t.Kin > 128) return false;
+    if (s.O < 32 || s.I * (int64_t)t.Kin < 256) return false;  // too narrow to be worth a tile
     t.BN = tc_bn_for(s.O);
     t.nNT = (s.O + t.BN - 1) / t.BN;
     const int64_t K = (int64_t)s.I * t.Kin;
     t.nkc = (int)((K + TC_BK - 1) / TC_BK);
+    // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kin (and of 16), <= 256
+    t.BNx = (256 / (2 * t.Kin)) * (2 * t.Kin);
+    t.nNTx = (int)((K + t.BNx - 1) / t.BNx);
+    t.noc = (s.O + TC_BK - 1) / TC_BK;
+    // dW: M tiles over the dense columns
+    t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
     // rows per launch: bound the Phi tiles to ~8 GiB
     const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
-    int64_t rows = (int64_t)(8ll << 30) / bytes_per_row / TC_BM * TC_BM;
-    if (rows < TC_BM) return false;
+    int64_t rows = (int64_t)(8ll << 30) / bytes_per_row / 512 * 512;
+    if (rows < 512) return false;
     if (rows > s.Bp) rows = s.Bp;
     rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
     t.rows_per_launch = rows;
-    t.a_bytes = (size_t)(rows / TC_BM) * t.nkc * 2 * TC_A_IMG;
-    t.b_bytes = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);
+    const size_t mtiles = (size_t)(rows / TC_BM);
+    const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
+    size_t a = mtiles * t.nkc * 2 * TC_A_IMG;                                     // Phi
+    const size_t a_t = (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;                   // Phi^T
+    const size_t a_gy = mtiles * t.noc * 2 * TC_A_IMG;                            // gy
+    if (a_t > a) a = a_t;
+    if (a_gy > a) a = a_gy;
+    size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);           // W
+    const size_t b_gyt = (size_t)t.nNT * bchunks * 2 * ((size_t)t.BN * TC_BK * 2);  // gy^T
+    const size_t b_wt = (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2);   // W^T
+    if (b_gyt > bb) bb = b_gyt;
+    if (b_wt > bb) bb = b_wt;
+    t.a_bytes = a;
+    t.b_bytes = bb;
     t.enabled = true;
     return true;
 }
 
-template <int N>
-static int expand_n(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, int64_t row0, int64_t rows, cudaStream_t st) {
-    dim3 grid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
-    pw_tc_expand_kernel<N><<<grid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, (const TcScalars*)ws.tc_scalars,
-                                                 s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab);
+static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws, const TcPlan& t) {
+    p.a_tiles = (const unsigned char*)ws.tc_a;
+    p.b_tiles = (const unsigned char*)ws.tc_b;
+    p.sc = (const TcScalars*)ws.tc_scalars;
+    p.xl_t = ws.xl_t;
+    p.seg_t = ws.seg_t;
+    p.Bp = s.Bp;
+    p.n_basis = s.n;
+    p.I = s.I;
+    p.nb = s.nb;
+    p.Kin = t.Kin;
+    p.stride = s.stride;
+    p.transposed = 0;
+    p.length = s.length;
+    p.Sf = (float)s.S;
+    p.inv_extra = 1.0f;
+    p.tab = s.tab;
+}
+
+template <int EPI>
+static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles, cudaStream_t st) {
+    const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
+    int nst = (HOL_SMEM_BUDGET - 1024) / stage;
+    if (nst > 6) nst = 6;
+    if (nst < 2) return HOL_EUNSUPPORTED;
+    size_t smem = 1024 + (size_t)nst * stage;
+    if (EPI == EPI_DX) {  // the epilogue stages a 128 x (BN+1) fp32 tile in the pipeline buffers
+        const size_t need = 1024 + (size_t)TC_BM * (p.BN + 1) * 4;
+        if (need > smem) smem = need;
+        if (smem > HOL_SMEM_BUDGET) return HOL_EUNSUPPORTED;
+    }
+    p.nst = nst;
+    p.flush_chunks = p.BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
+    auto kern = pw_tc_gemm_kernel<EPI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)ntiles, (unsigned)mtiles);
+    kern<<<grid, 320, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
-template <int BN>
-static int gemm_bn(const TcGemmParams& p, int64_t rows, int nNT, cudaStream_t st) {
-    constexpr int STAGE = 2 * TC_A_IMG + 2 * BN * TC_BK * 2;
-    int nst = (HOL_SMEM_BUDGET - 1024) / STAGE;
-    if (nst > 6) nst = 6;
-    if (nst < 2) return HOL_EUNSUPPORTED;
-    TcGemmParams q = p;
-    q.nst = nst;
-    q.flush_chunks = BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
-    const size_t smem = 1024 + (size_t)nst * STAGE;
-    auto kern = pw_tc_gemm_kernel<BN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define DISPATCH_N(n, CALL)                       \
+    switch (n) {                                  \
+        case 1: rc = CALL(1); break;              \
+        case 2: rc = CALL(2); break;              \
+        case 3: rc = CALL(3); break;              \
+        case 4: rc = CALL(4); break;              \
+        case 5: rc = CALL(5); break;              \
+        case 6: rc = CALL(6); break;              \
+        case 7: rc = CALL(7); break;              \
+        case 8: rc = CALL(8); break;              \
+        case 9: rc = CALL(9); break;              \
+        case 10: rc = CALL(10); break;            \
+        default: rc = HOL_EUNSUPPORTED;           \
+    }
+
+static int tc_absmax(const float* v, int64_t count, unsigned* out, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)nNT, (unsigned)(rows / TC_BM));
-    kern<<<grid, 320, smem, st>>>(q);
+    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(v, count, out);
     return (int)cudaGetLastError();
 }
 
 int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
-    cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(TcScalars), st);
-    if (e != cudaSuccess) return (int)e;
-    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl);
-    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(w, (int64_t)s.O * s.I * s.nb, &sc->max_w);
+    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
+    if (rc != HOL_OK) return rc;
     dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc);
     pw_tc_pack_w_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.nkc, t.BN);
-    int rc = (int)cudaGetLastError();
+    rc = (int)cudaGetLastError();
     if (rc != HOL_OK) return rc;
     for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
-        const int64_t rows = (s.Bp - row0 < t.rows_per_launch) ? (s.Bp - row0 + TC_BM - 1) / TC_BM * TC_BM : t.rows_per_launch;
-        switch (s.n) {
-            case 1: rc = expand_n<1>(s, ws, t, row0, rows, st); break;
-            case 2: rc = expand_n<2>(s, ws, t, row0, rows, st); break;
-            case 3: rc = expand_n<3>(s, ws, t, row0, rows, st); break;
-            case 4: rc = expand_n<4>(s, ws, t, row0, rows, st); break;
-            case 5: rc = expand_n<5>(s, ws, t, row0, rows, st); break;
-            case 6: rc = expand_n<6>(s, ws, t, row0, rows, st); break;
-            case 7: rc = expand_n<7>(s, ws, t, row0, rows, st); break;
-            case 8: rc = expand_n<8>(s, ws, t, row0, rows, st); break;
-            case 9: rc = expand_n<9>(s, ws, t, row0, rows, st); break;
-            case 10: rc = expand_n<10>(s, ws, t, row0, rows, st); break;
-            default: rc = HOL_EUNSUPPORTED;
-        }
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+        dim3 egrid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
+#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab), (int)cudaGetLastError())
+        DISPATCH_N(s.n, EXPAND)
+#undef EXPAND
         if (rc != HOL_OK) return rc;
         TcGemmParams p;
-        p.a_tiles = (const unsigned char*)ws.tc_a;
-        p.b_tiles = (const unsigned char*)ws.tc_b;
-        p.y = y;
-        p.sc = sc;
+        fill_common(p, s, ws, t);
+        p.out = y;
         p.row0 = row0;
         p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
+        p.BN = t.BN;
         p.n_valid = s.O;
-        p.ldy = s.O;
+        p.ld = s.O;
         p.nkc = t.nkc;
-        p.nst = 2;
-        p.n_basis = s.n;
-        p.tab = s.tab;
-        switch (t.BN) {
-            case 256: rc = gemm_bn<256>(p, rows, t.nNT, st); break;
-            case 128: rc = gemm_bn<128>(p, rows, t.nNT, st); break;
-            case 64: rc = gemm_bn<64>(p, rows, t.nNT, st); break;
-            case 32: rc = gemm_bn<32>(p, rows, t.nNT, st); break;
-            default: rc = HOL_EUNSUPPORTED;
+        rc = launch_gemm<EPI_Y>(p, rows / TC_BM, t.nNT, st);
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}
+
+int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
+                          cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
+        const int64_t nbg = (int64_t)nbc * 8;
+        const int64_t threads = nbg * s.I;
+        const unsigned eblocks = (unsigned)((threads + 255) / 256);
+#define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<eblocks, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, nbg, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
+        // rows k >= I*Kin of the last m-tile are never written by the expander: clear the tail tile once
+        if ((int64_t)s.I * t.Kin % TC_BM != 0) {
+            const size_t tile_bytes = (size_t)nbc * 2 * TC_A_IMG;
+            cudaError_t e = cudaMemsetAsync((unsigned char*)ws.tc_a + (size_t)(t.nMTw - 1) * tile_bytes, 0, tile_bytes, st);
+            if (e != cudaSuccess) return (int)e;
         }
+        DISPATCH_N(s.n, EXPANDT)
+#undef EXPANDT
+        if (rc != HOL_OK) return rc;
+        dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
+        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BN);
+        rc = (int)cudaGetLastError();
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.out = dw;
+        p.row0 = row0;  // > 0: accumulate onto the previous batch chunk's result
+        p.rows_valid = 0;
+        p.BN = t.BN;
+        p.n_valid = s.O;
+        p.ld = 0;
+        p.nkc = nbc;
+        rc = launch_gemm<EPI_DW>(p, t.nMTw, t.nNT, st);
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}
+
+int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
+                          float* dx, int transposed, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    int rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
+    if (rc != HOL_OK) return rc;
+    dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc);
+    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc, t.BNx);
+    rc = (int)cudaGetLastError();
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+        dim3 ggrid((unsigned)(rows / TC_BM), (unsigned)t.noc);
+        pw_tc_pack_gy_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_a, sc, s.B, row0, s.O, t.noc);
+        rc = (int)cudaGetLastError();
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.out = dx;
+        p.row0 = row0;
+        p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
+        p.BN = t.BNx;
+        p.n_valid = 0;
+        p.ld = 0;
+        p.nkc = t.noc;
+        p.transposed = transposed;
+        rc = launch_gemm<EPI_DX>(p, rows / TC_BM, t.nNTx, st);
         if (rc != HOL_OK) return rc;
     }
     return HOL_OK;

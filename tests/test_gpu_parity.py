@@ -14,6 +14,16 @@ from oracle import pw_oracle as orc
 from tests.conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["tensor-core", "gather"], autouse=True)
+def contraction_path(request, monkeypatch):
+    """Every parity test runs twice: with the tcgen05 segment-expanded path enabled (it is chosen
+    per shape, see tc_plan in csrc/tc.cu) and with it disabled (gather kernels everywhere)."""
+    monkeypatch.setenv("HOL_DISABLE_TC", "0" if request.param == "tensor-core" else "1")
+    return request.param
+
+
 TOL = 1e-5
 MLP_TOL = 1e-4  # network level: the reference's own MLP-level rtol (tests/test_refinement.py:55-92)
 DEV = "cuda"
