@@ -134,47 +134,49 @@ __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restri
 }
 
 // dW A: Phi^T tiles [m-tile (128 rows k = i*Kin+v)][batch chunk (64 samples)]; one thread = one
-// (input, 8 samples): evaluates the basis once and writes the Kin rows of its input.
+// (tile row, 8 samples) -> one coalesced 16-byte store per image.  Row k of the tile is basis
+// j = v - s*stride of the samples whose segment covers column v (zero otherwise), so each thread
+// evaluates a single phi_j per active sample: C_j * prod_{m != j} (t - X_m).
 template <int N>
 __global__ void __launch_bounds__(256) pw_tc_expand_t_kernel(const float* __restrict__ xl_t,
                                                              const uint16_t* __restrict__ seg_t,
                                                              unsigned char* __restrict__ tiles, const TcScalars* sc,
-                                                             int64_t Bp, int64_t row0, int64_t nbg, int I, int Kin,
-                                                             int nbc, int stride, const __grid_constant__ BasisTab tab) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t bg = t % nbg;  // 8-sample group inside this launch (fastest: coalesced xl/seg reads)
-    const int i = (int)(t / nbg);
-    if (i >= I) return;
-    const int64_t b0 = row0 + bg * 8;
+                                                             int64_t Bp, int64_t row0, int I, int Kin, int nbc, int stride,
+                                                             const __grid_constant__ BasisTab tab) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int mt = blockIdx.x, bc = blockIdx.y;
+    const int R = mt * TC_BM + r;
+    const int i = R / Kin, v = R % Kin;
     const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
-    float phi[8][N];
-    int a0[8];
+    unsigned char* base = tiles + (((int64_t)mt * nbc + bc) * 2) * (int64_t)TC_A_IMG;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int64_t b = b0 + e;
-        uint32_t sg = HOL_SEG_INVALID;
-        float xl = 0.0f;
-        if (b < Bp) {
-            sg = seg_t[(int64_t)i * Bp + b];
-            xl = xl_t[(int64_t)i * Bp + b];
-        }
-        lagrange_basis<N>(xl, tab, phi[e]);
-        a0[e] = (sg & HOL_SEG_INVALID) ? -100000 : (int)(sg & HOL_SEG_MASK) * stride;
-    }
-    const int bc = (int)(bg / 8), bgl = (int)(bg % 8);
-    for (int v = 0; v < Kin; ++v) {
-        const int R = i * Kin + v;
-        const int mt = R / TC_BM, r = R % TC_BM;
+    for (int q = 0; q < 4; ++q) {
+        const int bgl = half * 4 + q;
+        const int64_t b0 = row0 + (int64_t)bc * TC_BK + bgl * 8;
         float val[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = v - a0[e];
-            float x = 0.0f;
+        for (int e = 0; e < 8; ++e) val[e] = 0.0f;
+        if (i < I && b0 < Bp) {  // Bp is a multiple of 32: the 8 samples are all inside or all outside
+            const uint4 sraw = *reinterpret_cast<const uint4*>(seg_t + (int64_t)i * Bp + b0);
+            const float4 x0 = *reinterpret_cast<const float4*>(xl_t + (int64_t)i * Bp + b0);
+            const float4 x1 = *reinterpret_cast<const float4*>(xl_t + (int64_t)i * Bp + b0 + 4);
+            const uint32_t sw[4] = {sraw.x, sraw.y, sraw.z, sraw.w};
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-            for (int jj = 0; jj < N; ++jj) x = (j == jj) ? phi[e][jj] : x;
-            val[e] = x;
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t sg = (sw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                const int j = v - (int)(sg & HOL_SEG_MASK) * stride;
+                if (!(sg & HOL_SEG_INVALID) && j >= 0 && j < N) {
+                    float prod = 1.0f, cj = 0.0f;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        prod *= (m == j) ? 1.0f : (xs[e] - tab.X[m]);
+                        cj = (m == j) ? tab.C[m] : cj;
+                    }
+                    val[e] = (N == 1) ? 1.0f : prod * cj;
+                }
+            }
         }
-        unsigned char* base = tiles + (((int64_t)mt * nbc + bc) * 2) * (int64_t)TC_A_IMG;
         uint4* hi = reinterpret_cast<uint4*>(base + bgl * (TC_BM * 16) + r * 16);
         uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + bgl * (TC_BM * 16) + r * 16);
         split_store8(val, scale, hi, lo);
@@ -695,16 +697,8 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
     for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
         int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
         const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
-        const int64_t nbg = (int64_t)nbc * 8;
-        const int64_t threads = nbg * s.I;
-        const unsigned eblocks = (unsigned)((threads + 255) / 256);
-#define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<eblocks, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, nbg, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
-        // rows k >= I*Kin of the last m-tile are never written by the expander: clear the tail tile once
-        if ((int64_t)s.I * t.Kin % TC_BM != 0) {
-            const size_t tile_bytes = (size_t)nbc * 2 * TC_A_IMG;
-            cudaError_t e = cudaMemsetAsync((unsigned char*)ws.tc_a + (size_t)(t.nMTw - 1) * tile_bytes, 0, tile_bytes, st);
-            if (e != cudaSuccess) return (int)e;
-        }
+        dim3 egrid((unsigned)t.nMTw, (unsigned)nbc);
+#define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
         DISPATCH_N(s.n, EXPANDT)
 #undef EXPANDT
         if (rc != HOL_OK) return rc;
