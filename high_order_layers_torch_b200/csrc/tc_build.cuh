@@ -1,0 +1,196 @@
+// Operand builders of the tensor-core path (HBM-bound): see tc_gemm.cu.
+#pragma once
+#include "tc_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// operand builders (HBM-bound).  Image layout of a tile with R rows: [k/8 (8)][row (R)][8 x fp16],
+// hi image then lo image.
+// ---------------------------------------------------------------------------------------
+
+// forward A: Phi tiles [m-tile (128 samples)][k-chunk], k = i*Kin + v
+template <int N>
+__global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restrict__ xl_t, const uint16_t* __restrict__ seg_t,
+                                                           unsigned char* __restrict__ tiles, const TcScalars* sc,
+                                                           int64_t Bp, int64_t row0, int I, int Kin, int nkc, int stride,
+                                                           const __grid_constant__ BasisTab tab) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t mt = blockIdx.x;
+    const int kc = blockIdx.y;
+    const int64_t b = row0 + mt * TC_BM + r;
+    const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
+    unsigned char* base = tiles + ((mt * nkc + kc) * 2) * (int64_t)TC_A_IMG;
+    int cur_i = -1;
+    float phi[N];
+    int a0 = 0;
+    bool ok = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int kgl = half * 4 + q;
+        const int k0 = kc * TC_BK + kgl * 8;
+        const int i = k0 / Kin, v0 = k0 % Kin;
+        if (i != cur_i) {
+            cur_i = i;
+            ok = false;
+            if (i < I && b < Bp) {
+                const uint32_t sg = seg_t[(int64_t)i * Bp + b];
+                ok = !(sg & HOL_SEG_INVALID);
+                a0 = (int)(sg & HOL_SEG_MASK) * stride;
+                lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
+            }
+        }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = v0 + e - a0;
+            float val = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < N; ++jj) val = (j == jj) ? phi[jj] : val;
+            v[e] = ok ? val : 0.0f;
+        }
+        uint4* hi = reinterpret_cast<uint4*>(base + kgl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + kgl * (TC_BM * 16) + r * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dW A: Phi^T tiles [m-tile (128 rows k = i*Kin+v)][batch chunk (64 samples)]; one thread = one
+// (tile row, 8 samples) -> one coalesced 16-byte store per image.  Row k of the tile is basis
+// j = v - s*stride of the samples whose segment covers column v (zero otherwise), so each thread
+// evaluates a single phi_j per active sample: C_j * prod_{m != j} (t - X_m).
+template <int N>
+__global__ void __launch_bounds__(256) pw_tc_expand_t_kernel(const float* __restrict__ xl_t,
+                                                             const uint16_t* __restrict__ seg_t,
+                                                             unsigned char* __restrict__ tiles, const TcScalars* sc,
+                                                             int64_t Bp, int64_t row0, int I, int Kin, int nbc, int stride,
+                                                             const __grid_constant__ BasisTab tab) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int mt = blockIdx.x, bc = blockIdx.y;
+    const int R = mt * TC_BM + r;
+    const int i = R / Kin, v = R % Kin;
+    const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
+    unsigned char* base = tiles + (((int64_t)mt * nbc + bc) * 2) * (int64_t)TC_A_IMG;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int bgl = half * 4 + q;
+        const int64_t b0 = row0 + (int64_t)bc * TC_BK + bgl * 8;
+        float val[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) val[e] = 0.0f;
+        if (i < I && b0 < Bp) {  // Bp is a multiple of 32: the 8 samples are all inside or all outside
+            const uint4 sraw = *reinterpret_cast<const uint4*>(seg_t + (int64_t)i * Bp + b0);
+            const float4 x0 = *reinterpret_cast<const float4*>(xl_t + (int64_t)i * Bp + b0);
+            const float4 x1 = *reinterpret_cast<const float4*>(xl_t + (int64_t)i * Bp + b0 + 4);
+            const uint32_t sw[4] = {sraw.x, sraw.y, sraw.z, sraw.w};
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t sg = (sw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                const int j = v - (int)(sg & HOL_SEG_MASK) * stride;
+                if (!(sg & HOL_SEG_INVALID) && j >= 0 && j < N) {
+                    float prod = 1.0f, cj = 0.0f;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        prod *= (m == j) ? 1.0f : (xs[e] - tab.X[m]);
+                        cj = (m == j) ? tab.C[m] : cj;
+                    }
+                    val[e] = (N == 1) ? 1.0f : prod * cj;
+                }
+            }
+        }
+        uint4* hi = reinterpret_cast<uint4*>(base + bgl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + bgl * (TC_BM * 16) + r * 16);
+        split_store8(val, scale, hi, lo);
+    }
+}
+
+// forward B: W tiles [n-tile (BN outputs)][k-chunk], k = i*Kin + v
+__global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
+                                                           const TcScalars* sc, int I, int O, int nb, int Kin, int nkc,
+                                                           int BN) {
+    const int nt = blockIdx.x, kc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * nkc + kc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, kgl = idx / BN;
+        const int o = nt * BN + row;
+        const int k0 = kc * TC_BK + kgl * 8;
+        const int i = k0 / Kin, v0 = k0 % Kin;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = v0 + e;
+            v[e] = (o < O && i < I && col < nb) ? w[((int64_t)o * I + i) * nb + col] : 0.0f;
+        }
+        uint4* hi = reinterpret_cast<uint4*>(base + kgl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + kgl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dX B: W^T tiles [n-tile (BN rows k = i*Kin+v)][o-chunk (64 outputs)]
+__global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
+                                                            const TcScalars* sc, int I, int O, int nb, int Kin, int noc,
+                                                            int BN) {
+    const int nt = blockIdx.x, oc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * noc + oc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, ogl = idx / BN;
+        const int R = nt * BN + row;
+        const int i = R / Kin, col = R % Kin;
+        const int o0 = oc * TC_BK + ogl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            v[e] = (o0 + e < O && i < I && col < nb) ? w[((int64_t)(o0 + e) * I + i) * nb + col] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + ogl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + ogl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dX A: gy tiles [m-tile (128 samples)][o-chunk]
+__global__ void __launch_bounds__(256) pw_tc_pack_gy_kernel(const float* __restrict__ gy, unsigned char* __restrict__ tiles,
+                                                            const TcScalars* sc, int64_t B, int64_t row0, int O, int noc) {
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t mt = blockIdx.x;
+    const int oc = blockIdx.y;
+    const int64_t b = row0 + mt * TC_BM + r;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_gy));
+    unsigned char* base = tiles + ((mt * noc + oc) * 2) * (int64_t)TC_A_IMG;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ogl = half * 4 + q;
+        const int o0 = oc * TC_BK + ogl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (b < B && o0 + e < O) ? gy[b * O + o0 + e] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + ogl * (TC_BM * 16) + r * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + ogl * (TC_BM * 16) + r * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+
+// dW B: gy^T tiles [n-tile (BN outputs)][batch chunk (64 samples)]
+__global__ void __launch_bounds__(256) pw_tc_pack_gyt_kernel(const float* __restrict__ gy, unsigned char* __restrict__ tiles,
+                                                             const TcScalars* sc, int64_t B, int64_t row0, int O, int nbc,
+                                                             int BN) {
+    const int nt = blockIdx.x, bc = blockIdx.y;
+    const float scale = pow2_scale_for(__uint_as_float(sc->max_gy));
+    const int img = BN * TC_BK * 2;
+    unsigned char* base = tiles + ((int64_t)(nt * nbc + bc) * 2) * img;
+    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+        const int row = idx % BN, bgl = idx / BN;
+        const int o = nt * BN + row;
+        const int64_t b0 = row0 + (int64_t)bc * TC_BK + bgl * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (o < O && b0 + e < B) ? gy[(b0 + e) * O + o] : 0.0f;
+        uint4* hi = reinterpret_cast<uint4*>(base + bgl * (BN * 16) + row * 16);
+        uint4* lo = reinterpret_cast<uint4*>(base + img + bgl * (BN * 16) + row * 16);
+        split_store8(v, scale, hi, lo);
+    }
+}
+

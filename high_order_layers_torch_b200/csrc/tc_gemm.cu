@@ -1,0 +1,245 @@
+// Tensor-core (tcgen05) path for layers with few segments: the segment-expanded dense contraction.
+//
+//   Phi[b, i*Kin + s(b,i)*stride + j] = phi_j(xl(b,i))        (n non-zeros out of Kin per (sample, input))
+//   forward : y[b,o]        = sum_k Phi[b,k]  * W[o,k]         M = batch,  N = O,      K = I*Kin
+//   dW      : dW[o,k]       = sum_b Phi[b,k]  * gy[b,o]        M = I*Kin,  N = O,      K = batch
+//   dX      : T[b,k]        = sum_o gy[b,o]   * W[o,k]         M = batch,  N = I*Kin,  K = O
+//             dX[b,i]       = chain(b,i) * sum_j phi'_j(xl) * T[b, i*Kin + s*stride + j]   (epilogue gather)
+//
+// The dense form spends Kin/n times the useful MACs -- but on the tensor pipe, which pays while
+// Kin <= ~20 n (S <= 8 for the named configs): the gather kernels are pinned to one shared-memory
+// word per FMA (25 % of the fp32 SIMT peak); the tensor pipe is ~20x that peak.
+//
+// fp32 accuracy from fp16 tensor cores: both operands are split a = hi + lo (two fp16 values, 22
+// significant bits, power-of-two pre-scaling keeps them in the fp16 range) and the kernel issues
+// hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (dropped lo*lo term ~2^-22 relative).
+// The tensor core accumulates with round-toward-zero: every chained MMA instruction loses on
+// average half an ulp of the running sum, a bias that grows linearly with K (measured 3e-5 at
+// K = 3136).  So a TMEM accumulator only ever holds <= 36 chained instructions (bias <= 2e-6); the
+// epilogue warps drain it into round-to-nearest fp32 register sums while the MMA warp fills the
+// other of the two TMEM accumulators.
+//
+// Operands are stored in global memory as ready-made shared-memory images (K-major, no-swizzle
+// UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
+// pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warps 2-9 = epilogue (tcgen05.ld -> fp32 register sums -> global).
+#include "tc_build.cuh"
+
+#include "tc_kernel.cuh"
+
+// ---------------------------------------------------------------------------------------
+// planning + launch
+// ---------------------------------------------------------------------------------------
+static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : 64); }
+
+bool tc_plan(const PwShape& s, TcPlan& t) {
+    t.enabled = false;
+    const char* off = getenv("HOL_DISABLE_TC");
+    if (off && off[0] == '1') return false;
+    t.Kin = (s.nb + 7) / 8 * 8;
+    // the dense form costs 3*Kin tensor MACs per n useful fp32 FMAs
+    if (t.Kin > 20 * s.n || t.Kin > 128) return false;
+    if (s.O < 32 || s.I * (int64_t)t.Kin < 256) return false;  // too narrow to be worth a tile
+    t.BN = tc_bn_for(s.O);
+    t.nNT = (s.O + t.BN - 1) / t.BN;
+    const int64_t K = (int64_t)s.I * t.Kin;
+    t.nkc = (int)((K + TC_BK - 1) / TC_BK);
+    // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kin (and of 16), <= 256
+    t.BNx = (256 / (2 * t.Kin)) * (2 * t.Kin);
+    t.nNTx = (int)((K + t.BNx - 1) / t.BNx);
+    t.noc = (s.O + TC_BK - 1) / TC_BK;
+    // dW: M tiles over the dense columns
+    t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
+    // rows per launch: bound the Phi tiles to ~8 GiB
+    const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
+    int64_t rows = (int64_t)(8ll << 30) / bytes_per_row / 512 * 512;
+    if (rows < 512) return false;
+    if (rows > s.Bp) rows = s.Bp;
+    rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+    t.rows_per_launch = rows;
+    const size_t mtiles = (size_t)(rows / TC_BM);
+    const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
+    size_t a = mtiles * t.nkc * 2 * TC_A_IMG;                                     // Phi
+    const size_t a_t = (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;                   // Phi^T
+    const size_t a_gy = mtiles * t.noc * 2 * TC_A_IMG;                            // gy
+    if (a_t > a) a = a_t;
+    if (a_gy > a) a = a_gy;
+    size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);           // W
+    const size_t b_gyt = (size_t)t.nNT * bchunks * 2 * ((size_t)t.BN * TC_BK * 2);  // gy^T
+    const size_t b_wt = (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2);   // W^T
+    if (b_gyt > bb) bb = b_gyt;
+    if (b_wt > bb) bb = b_wt;
+    t.a_bytes = a;
+    t.b_bytes = bb;
+    t.enabled = true;
+    return true;
+}
+
+static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws, const TcPlan& t) {
+    p.a_tiles = (const unsigned char*)ws.tc_a;
+    p.b_tiles = (const unsigned char*)ws.tc_b;
+    p.sc = (const TcScalars*)ws.tc_scalars;
+    p.xl_t = ws.xl_t;
+    p.seg_t = ws.seg_t;
+    p.Bp = s.Bp;
+    p.n_basis = s.n;
+    p.I = s.I;
+    p.nb = s.nb;
+    p.Kin = t.Kin;
+    p.stride = s.stride;
+    p.transposed = 0;
+    p.length = s.length;
+    p.Sf = (float)s.S;
+    p.tab = s.tab;
+}
+
+static int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+template <int EPI, int N>
+static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_t st) {
+    const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
+    int nst = (HOL_SMEM_BUDGET - 1024) / stage;
+    if (nst > 6) nst = 6;
+    if (nst < 2) return HOL_EUNSUPPORTED;
+    const size_t smem = 1024 + (size_t)nst * stage;
+    p.nst = nst;
+    p.flush_chunks = p.BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
+    p.ntile_n = ntiles_n;
+    p.ntiles = mtiles * ntiles_n;
+    auto kern = pw_tc_gemm_kernel<EPI, N>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t sms = sm_count();
+    const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);  // persistent: one CTA per SM
+    kern<<<grid, 320, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+#define DISPATCH_N(n, CALL)                       \
+    switch (n) {                                  \
+        case 1: rc = CALL(1); break;              \
+        case 2: rc = CALL(2); break;              \
+        case 3: rc = CALL(3); break;              \
+        case 4: rc = CALL(4); break;              \
+        case 5: rc = CALL(5); break;              \
+        case 6: rc = CALL(6); break;              \
+        case 7: rc = CALL(7); break;              \
+        case 8: rc = CALL(8); break;              \
+        case 9: rc = CALL(9); break;              \
+        case 10: rc = CALL(10); break;            \
+        default: rc = HOL_EUNSUPPORTED;           \
+    }
+
+static int tc_absmax(const float* v, int64_t count, unsigned* out, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
+    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(v, count, out);
+    return (int)cudaGetLastError();
+}
+
+int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
+    if (rc != HOL_OK) return rc;
+    dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc);
+    pw_tc_pack_w_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.nkc, t.BN);
+    rc = (int)cudaGetLastError();
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+        dim3 egrid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
+#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab), (int)cudaGetLastError())
+        DISPATCH_N(s.n, EXPAND)
+#undef EXPAND
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.out = y;
+        p.row0 = row0;
+        p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
+        p.BN = t.BN;
+        p.n_valid = s.O;
+        p.ld = s.O;
+        p.nkc = t.nkc;
+        rc = launch_gemm<EPI_Y, 0>(p, rows / TC_BM, t.nNT, st);
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}
+
+int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
+                          cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
+        dim3 egrid((unsigned)t.nMTw, (unsigned)nbc);
+#define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
+        DISPATCH_N(s.n, EXPANDT)
+#undef EXPANDT
+        if (rc != HOL_OK) return rc;
+        dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
+        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BN);
+        rc = (int)cudaGetLastError();
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.out = dw;
+        p.row0 = row0;  // > 0: accumulate onto the previous batch chunk's result
+        p.rows_valid = 0;
+        p.BN = t.BN;
+        p.n_valid = s.O;
+        p.ld = 0;
+        p.nkc = nbc;
+        rc = launch_gemm<EPI_DW, 0>(p, t.nMTw, t.nNT, st);
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}
+
+int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
+                          float* dx, int transposed, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    int rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
+    if (rc != HOL_OK) return rc;
+    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
+    if (rc != HOL_OK) return rc;
+    dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc);
+    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc, t.BNx);
+    rc = (int)cudaGetLastError();
+    if (rc != HOL_OK) return rc;
+    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+        rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
+        dim3 ggrid((unsigned)(rows / TC_BM), (unsigned)t.noc);
+        pw_tc_pack_gy_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_a, sc, s.B, row0, s.O, t.noc);
+        rc = (int)cudaGetLastError();
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.out = dx;
+        p.row0 = row0;
+        p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
+        p.BN = t.BNx;
+        p.n_valid = 0;
+        p.ld = 0;
+        p.nkc = t.noc;
+        p.transposed = transposed;
+#define GEMM_DX(NN) launch_gemm<EPI_DX, NN>(p, rows / TC_BM, t.nNTx, st)
+        DISPATCH_N(s.n, GEMM_DX)
+#undef GEMM_DX
+        if (rc != HOL_OK) return rc;
+    }
+    return HOL_OK;
+}

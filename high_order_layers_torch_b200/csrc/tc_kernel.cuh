@@ -1,0 +1,297 @@
+#pragma once
+// Persistent split-fp16 tcgen05 GEMM with three epilogues (design notes: tc_gemm.cu).
+#include "tc_build.cuh"
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4, version=1 [46,48), layout NONE
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcGemmParams {
+    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
+    const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
+    float* out;                    // EPI_Y: y[rows][ld]; EPI_DW: dw[O][I][nb]; EPI_DX: dx[B][I] or dx_t[I][Bp]
+    const TcScalars* sc;
+    const float* xl_t;             // EPI_DX
+    const uint16_t* seg_t;         // EPI_DX
+    int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
+    int64_t ntiles;                // m-tiles * n-tiles (n fastest)
+    int ntile_n;
+    int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
+    int I, nb, Kin, stride, transposed;
+    float length, Sf;
+    BasisTab tab;
+};
+
+// Persistent: grid = min(#tiles, #SMs); every role walks the same tile sequence
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so CTAs running together share
+// A tiles in L2).  The smem ring (full/empty) and the two TMEM accumulators (tmem_full/tmem_empty)
+// run continuously across tiles, so the epilogue of tile t overlaps the main loop of tile t+1.
+// N is the basis size for the EPI_DX gather (0 otherwise).
+template <int EPI, int N>
+__global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int BN = p.BN;
+    const int B_IMG = BN * TC_BK * 2;
+    const int STAGE_BYTES = 2 * TC_A_IMG + 2 * B_IMG;
+    const int HALF = BN / 2;  // columns per epilogue thread
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [nst]
+    uint64_t* empty = full + 8;                              // [nst]
+    uint64_t* tmem_full = full + 16;                         // [2]
+    uint64_t* tmem_empty = full + 18;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
+    unsigned char* stages = smem_raw + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nst = p.nst;
+    const int FG = p.flush_chunks;
+    const int ngroups = (p.nkc + FG - 1) / FG;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;  // two accumulators; power of two >= 32
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int nt = (int)(tile % p.ntile_n);
+                const int64_t mt = tile / p.ntile_n;
+                const unsigned char* a_src = p.a_tiles + (mt * p.nkc) * (int64_t)(2 * TC_A_IMG);
+                const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
+                for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+                    const int st = it % nst;
+                    mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
+                    mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
+                    unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
+                    bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
+                    bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t LBO_A = TC_BM * 16, LBO_B = (uint32_t)BN * 16, SBO = 128;
+            int it = 0, g = 0;
+            for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+                    const int st = it % nst;
+                    const int acc = g & 1;
+                    const bool first = (kc % FG) == 0;
+                    if (first) {
+                        mbar_wait(&tmem_empty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));  // drained by the epilogue
+                        tc_fence_after();
+                    }
+                    mbar_wait(&full[st], (uint32_t)((it / nst) & 1));
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + (size_t)st * STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * TC_A_IMG;
+                    const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                        const uint64_t a_hi = umma_desc_kmajor_noswizzle(sa + kk * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t a_lo = umma_desc_kmajor_noswizzle(sa + TC_A_IMG + kk * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t b_hi = umma_desc_kmajor_noswizzle(sb + kk * 2 * LBO_B, LBO_B, SBO);
+                        const uint64_t b_lo = umma_desc_kmajor_noswizzle(sb + B_IMG + kk * 2 * LBO_B, LBO_B, SBO);
+                        umma_f16(td, a_hi, b_hi, idesc, (first && kk == 0) ? 0u : 1u);
+                        umma_f16(td, a_hi, b_lo, idesc, 1u);
+                        umma_f16(td, a_lo, b_hi, idesc, 1u);
+                    }
+                    umma_commit(&empty[st]);  // arrives when the MMAs above have finished reading this stage
+                    if ((kc % FG) == FG - 1 || kc == p.nkc - 1) {
+                        umma_commit(&tmem_full[acc]);
+                        ++g;
+                    }
+                }
+            }
+        }
+    } else {
+        // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        const int rl = q * 32 + lane;  // row inside the 128-row tile
+        int g = 0;
+        // scale factors (device scalars written before this launch)
+        float inv;
+        if (EPI == EPI_Y)
+            inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) * pow2_scale_for(__uint_as_float(p.sc->max_w)));
+        else if (EPI == EPI_DW)
+            inv = 1.0f / (phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis) * pow2_scale_for(__uint_as_float(p.sc->max_gy)));
+        else
+            inv = 1.0f / (pow2_scale_for(__uint_as_float(p.sc->max_gy)) * pow2_scale_for(__uint_as_float(p.sc->max_w)));
+
+        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int nt = (int)(tile % p.ntile_n);
+            const int64_t mt = tile / p.ntile_n;
+            float racc[TC_MAXHALF];
+#pragma unroll
+            for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
+            for (int gg = 0; gg < ngroups; ++gg, ++g) {
+                const int acc = g & 1;
+                mbar_wait(&tmem_full[acc], (uint32_t)((g >> 1) & 1));
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * HALF);
+#pragma unroll
+                for (int c0 = 0; c0 < TC_MAXHALF; c0 += 32) {
+                    if (c0 < HALF) {
+                        uint32_t v[32];
+                        tmem_ld32(t0 + (uint32_t)c0, v);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) racc[c0 + e] += __uint_as_float(v[e]);  // columns >= HALF: unused
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            const int64_t row = mt * TC_BM + rl;  // row inside this launch
+            const int colbase = nt * BN + h * HALF;
+
+            if (EPI == EPI_Y) {
+                if (row < p.rows_valid) {
+                    float* yrow = p.out + (p.row0 + row) * (int64_t)p.ld + colbase;
+                    const bool vec = (p.ld & 3) == 0 && (HALF & 3) == 0;
+#pragma unroll
+                    for (int e = 0; e < TC_MAXHALF; e += 4) {
+                        if (e < HALF) {
+                            const int col = colbase + e;
+                            const float4 o4 = make_float4(racc[e] * inv, racc[e + 1] * inv, racc[e + 2] * inv, racc[e + 3] * inv);
+                            if (vec && col + 3 < p.n_valid) {
+                                *reinterpret_cast<float4*>(yrow + e) = o4;
+                            } else {
+                                if (col + 0 < p.n_valid) yrow[e + 0] = o4.x;
+                                if (col + 1 < p.n_valid) yrow[e + 1] = o4.y;
+                                if (col + 2 < p.n_valid) yrow[e + 2] = o4.z;
+                                if (col + 3 < p.n_valid) yrow[e + 3] = o4.w;
+                            }
+                        }
+                    }
+                }
+            } else if (EPI == EPI_DW) {
+                // row = dense column k = i*Kin + v, columns = outputs; write the reference layout dw[o][i][v]
+                const int i = (int)(row / p.Kin), v = (int)(row % p.Kin);
+                if (i < p.I && v < p.nb) {
+                    const bool accumulate = p.row0 > 0;
+#pragma unroll
+                    for (int e = 0; e < TC_MAXHALF; ++e) {
+                        if (e < HALF) {
+                            const int o = colbase + e;
+                            if (o < p.n_valid) {
+                                float* dst = p.out + ((int64_t)o * p.I + i) * p.nb + v;
+                                *dst = accumulate ? *dst + racc[e] * inv : racc[e] * inv;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // EPI_DX: this thread holds T[b][k] for HALF/Kin whole inputs; pick the n active
+                // columns of each (segment-dependent, so a select chain over the static register index)
+                constexpr int NB = N > 0 ? N : 1;
+                const int64_t b = p.row0 + row;
+                int e_in = 0, i = colbase / p.Kin;
+                float dphi[NB];
+                float sum = 0.0f, chain = 0.0f;
+                int a0 = 0;
+                bool ok = false;
+                int64_t idx = 0;
+#pragma unroll
+                for (int e = 0; e < TC_MAXHALF; ++e) {
+                    if (e < HALF) {
+                        if (e_in == 0) {
+                            ok = i < p.I && b < p.Bp;
+                            sum = 0.0f;
+                            if (ok) {
+                                idx = (int64_t)i * p.Bp + b;
+                                const uint32_t sg = p.seg_t[idx];
+                                const int s = (int)(sg & HOL_SEG_MASK);
+                                a0 = s * p.stride;
+                                lagrange_basis_derivative<NB>(p.xl_t[idx], p.tab, dphi);
+                                const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
+                                const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
+                                chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
+                                if (sg & HOL_SEG_MIRROR) chain = -chain;
+                                if (sg & HOL_SEG_INVALID) chain = 0.0f;
+                            }
+                        }
+                        const int jj = e_in - a0;
+                        float d = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) d = (jj == j) ? dphi[j] : d;
+                        sum = fmaf(d, racc[e], sum);
+                        if (++e_in == p.Kin) {
+                            if (ok) {
+                                const float outv = sum * inv * chain;
+                                if (p.transposed)
+                                    p.out[idx] = outv;
+                                else if (row < p.rows_valid)
+                                    p.out[b * p.I + i] = outv;
+                            }
+                            e_in = 0;
+                            ++i;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
