@@ -238,51 +238,39 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
                     }
                 }
             } else {
-                // EPI_DX: this thread holds T[b][k] for HALF/Kin whole inputs; pick the n active
-                // columns of each (segment-dependent, so a select chain over the static register index)
+                // EPI_DX: this thread holds T[b][k] for HALF/Kin whole inputs.  The n active columns
+                // of an input depend on the sample's segment, so the finished sums are parked once per
+                // tile in a per-thread local array (L1/L2-backed, 512 B) and gathered with dynamic
+                // indices in a compact loop over the inputs.
                 constexpr int NB = N > 0 ? N : 1;
+                float T[TC_MAXHALF];
+#pragma unroll
+                for (int e = 0; e < TC_MAXHALF; ++e) T[e] = racc[e];
                 const int64_t b = p.row0 + row;
-                int e_in = 0, i = colbase / p.Kin;
-                float dphi[NB];
-                float sum = 0.0f, chain = 0.0f;
-                int a0 = 0;
-                bool ok = false;
-                int64_t idx = 0;
+                const int ninp = HALF / p.Kin;
+                if (b < p.Bp) {
+#pragma unroll 1
+                    for (int ii = 0; ii < ninp; ++ii) {
+                        const int i = colbase / p.Kin + ii;
+                        if (i >= p.I) break;
+                        const int64_t idx = (int64_t)i * p.Bp + b;
+                        const uint32_t sg = p.seg_t[idx];
+                        const int s = (int)(sg & HOL_SEG_MASK);
+                        float dphi[NB];
+                        lagrange_basis_derivative<NB>(p.xl_t[idx], p.tab, dphi);
+                        const float* Tr = T + ii * p.Kin + s * p.stride;
+                        float sum = 0.0f;
 #pragma unroll
-                for (int e = 0; e < TC_MAXHALF; ++e) {
-                    if (e < HALF) {
-                        if (e_in == 0) {
-                            ok = i < p.I && b < p.Bp;
-                            sum = 0.0f;
-                            if (ok) {
-                                idx = (int64_t)i * p.Bp + b;
-                                const uint32_t sg = p.seg_t[idx];
-                                const int s = (int)(sg & HOL_SEG_MASK);
-                                a0 = s * p.stride;
-                                lagrange_basis_derivative<NB>(p.xl_t[idx], p.tab, dphi);
-                                const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
-                                const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
-                                chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
-                                if (sg & HOL_SEG_MIRROR) chain = -chain;
-                                if (sg & HOL_SEG_INVALID) chain = 0.0f;
-                            }
-                        }
-                        const int jj = e_in - a0;
-                        float d = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) d = (jj == j) ? dphi[j] : d;
-                        sum = fmaf(d, racc[e], sum);
-                        if (++e_in == p.Kin) {
-                            if (ok) {
-                                const float outv = sum * inv * chain;
-                                if (p.transposed)
-                                    p.out[idx] = outv;
-                                else if (row < p.rows_valid)
-                                    p.out[b * p.I + i] = outv;
-                            }
-                            e_in = 0;
-                            ++i;
-                        }
+                        for (int j = 0; j < NB; ++j) sum = fmaf(dphi[j], Tr[j], sum);
+                        const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
+                        const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
+                        float chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
+                        if (sg & HOL_SEG_MIRROR) chain = -chain;
+                        const float outv = (sg & HOL_SEG_INVALID) ? 0.0f : sum * inv * chain;
+                        if (p.transposed)
+                            p.out[idx] = outv;
+                        else if (row < p.rows_valid)
+                            p.out[b * p.I + i] = outv;
                     }
                 }
             }

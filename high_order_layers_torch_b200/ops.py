@@ -88,11 +88,20 @@ def _(x, segments, length, periodicity):
 # ------------------------------------------------------------------------------------------
 # fully connected layer
 # ------------------------------------------------------------------------------------------
-@torch.library.custom_op("hol::pw_forward", mutates_args=(), device_types="cuda")
-def pw_forward(x: Tensor, w: Tensor, n: int, segments: int, length: float, discontinuous: bool,
-               periodicity: Optional[float]) -> Tuple[Tensor, Tensor]:
-    """-> (y[B, O], workspace).  The workspace keeps the prepared state (transposed local
-    coordinates, packed weights) for ``hol::pw_backward``."""
+def fc_workspace(x: Tensor, w: Tensor, n: int, segments: int, discontinuous: bool) -> Tensor:
+    """Scratch for one layer call (hol_pw_workspace_bytes), from torch's caching allocator."""
+    nbytes = _lib.load().hol_pw_workspace_bytes(x.shape[0], x.shape[1], w.shape[0], n, segments, int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2 if (n > _lib.HOL_MAX_N or segments > _lib.HOL_MAX_SEGMENTS) else -1, "hol_pw_workspace_bytes")
+    return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+
+
+@torch.library.custom_op("hol::pw_forward", mutates_args=("ws",), device_types="cuda")
+def pw_forward(x: Tensor, w: Tensor, ws: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+               periodicity: Optional[float]) -> Tensor:
+    """-> y[B, O].  `ws` (a mutated input, see fc_workspace) keeps the prepared state (transposed
+    local coordinates, packed weights) for ``hol::pw_backward``; it is an input rather than an
+    output so that autograd never materialises a multi-GB zero "gradient" for it."""
     _check_inputs(x, w, "pw_forward")
     if x.dim() != 2:
         raise ValueError(f"pw_forward: x must be [batch, in_features], got {tuple(x.shape)}")
@@ -103,23 +112,18 @@ def pw_forward(x: Tensor, w: Tensor, n: int, segments: int, length: float, disco
                          f"[out, {I}, {_nb(n, segments, discontinuous)}]")
     lib = _lib.load()
     xc, wc = x.contiguous(), w.contiguous()
-    nbytes = lib.hol_pw_workspace_bytes(B, I, O, n, segments, int(discontinuous))
-    if nbytes == 0:
-        _lib.check(-2 if (n > _lib.HOL_MAX_N or segments > _lib.HOL_MAX_SEGMENTS) else -1, "hol_pw_workspace_bytes")
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     y = torch.empty((B, O), dtype=torch.float32, device=x.device)
     nodes = lobatto_nodes(n, 2.0)  # FC layers always build LagrangePoly(n) with length 2 (PolynomialLayers.py:234)
     with torch.cuda.device(x.device):
         _lib.check(lib.hol_pw_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, I, O, n, segments, length,
-                                          int(discontinuous), _per(periodicity), _ptr(ws), nbytes, _stream(x)),
+                                          int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(), _stream(x)),
                    "hol_pw_forward_f32")
-    return y, ws
+    return y
 
 
 @pw_forward.register_fake
-def _(x, w, n, segments, length, discontinuous, periodicity):
-    return (torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device),
-            torch.empty((0,), dtype=torch.uint8, device=x.device))
+def _(x, w, ws, n, segments, length, discontinuous, periodicity):
+    return torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
 
 
 @torch.library.custom_op("hol::pw_backward", mutates_args=("ws",), device_types="cuda")
@@ -149,31 +153,42 @@ def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, ne
     return (torch.empty_like(x) if need_dx else e, torch.empty_like(w) if need_dw else e)
 
 
-def _pw_setup(ctx, inputs, output):
-    x, w, n, segments, length, discontinuous, periodicity = inputs
-    _, ws = output
-    ctx.save_for_backward(x, w, ws)
-    ctx.args = (n, segments, length, discontinuous, periodicity)
+class _PiecewiseFn(torch.autograd.Function):
+    """Autograd glue: forward = hol::pw_forward (fills the workspace), backward = hol::pw_backward
+    (reuses it).  The ops themselves are plain torch.library ops; the scratch buffer is a mutated
+    op argument, never an op output, so autograd does not materialise a zero gradient for it."""
 
+    @staticmethod
+    def forward(ctx, x, w, n, segments, length, discontinuous, periodicity):
+        ws = fc_workspace(x, w, n, segments, discontinuous)
+        y = pw_forward(x, w, ws, n, segments, length, discontinuous, periodicity)
+        ctx.save_for_backward(x, w)
+        ctx.ws = ws
+        ctx.args = (n, segments, length, discontinuous, periodicity)
+        return y
 
-def _pw_bwd(ctx, gy, _gws):
-    x, w, ws = ctx.saved_tensors
-    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-    dx = dw = None
-    if need_dx or need_dw:
-        rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True)
-        dx = rdx if need_dx else None
-        dw = rdw if need_dw else None
-    return dx, dw, None, None, None, None, None
-
-
-pw_forward.register_autograd(_pw_bwd, setup_context=_pw_setup)
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = dw = None
+        if need_dx or need_dw:
+            rdx, rdw = pw_backward(gy, x, w, ctx.ws, *ctx.args, need_dx, need_dw, True)
+            dx = rdx if need_dx else None
+            dw = rdw if need_dw else None
+        ctx.ws = None
+        return dx, dw, None, None, None, None, None
 
 
 def piecewise_polynomial(x: Tensor, w: Tensor, n: int, segments: int, length: float = 2.0,
                          discontinuous: bool = False, periodicity: Optional[float] = None) -> Tensor:
     """Functional form of the layer: y = Piecewise(n, segments)(x) with weights w[O, I, nb]."""
-    return pw_forward(x, w, n, segments, float(length), bool(discontinuous), periodicity)[0]
+    if x.is_meta:  # shape propagation only (register_fake)
+        return pw_forward(x, w, torch.empty((0,), dtype=torch.uint8, device=x.device), n, segments, float(length),
+                          bool(discontinuous), periodicity)
+    _check_inputs(x, w, "piecewise_polynomial")
+    return _PiecewiseFn.apply(x, w, n, segments, float(length), bool(discontinuous), periodicity)
 
 
 # ------------------------------------------------------------------------------------------
@@ -183,11 +198,21 @@ def conv_out_size(h: int, k: int, stride: int, padding: int, dilation: int) -> i
     return (h + 2 * padding - dilation * (k - 1) - 1) // stride + 1
 
 
-@torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=(), device_types="cuda")
-def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+def conv_workspace(x: Tensor, w_fc: Tensor, n: int, segments: int, discontinuous: bool, kernel_size: int,
+                   stride: int, padding: int, dilation: int) -> Tensor:
+    B, C, H, W = x.shape
+    nbytes = _lib.load().hol_pw_conv2d_workspace_bytes(B, C, H, W, w_fc.shape[0], kernel_size, stride, padding,
+                                                       dilation, n, segments, int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
+    return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+
+
+@torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=("ws",), device_types="cuda")
+def pw_conv2d_rows(x: Tensor, w_fc: Tensor, ws: Tensor, n: int, segments: int, length: float, discontinuous: bool,
                    periodicity: Optional[float], kernel_size: int, stride: int, padding: int,
-                   dilation: int) -> Tuple[Tensor, Tensor]:
-    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> (y_rows[B*Ho*Wo, O], workspace)."""
+                   dilation: int) -> Tensor:
+    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> y_rows[B*Ho*Wo, O]; `ws` from conv_workspace (mutated)."""
     _check_inputs(x, w_fc, "pw_conv2d_rows")
     if x.dim() != 4:
         raise ValueError(f"pw_conv2d_rows: x must be [B, C, H, W], got {tuple(x.shape)}")
@@ -201,11 +226,7 @@ def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float
         raise ValueError("pw_conv2d_rows: kernel does not fit the input")
     lib = _lib.load()
     xc, wc = x.contiguous(), w_fc.contiguous()
-    nbytes = lib.hol_pw_conv2d_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments,
-                                               int(discontinuous))
-    if nbytes == 0:
-        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    nbytes = ws.numel()
     y = torch.empty((B * Ho * Wo, O), dtype=torch.float32, device=x.device)
     nodes = lobatto_nodes(n, length)  # conv builds its basis with the layer's length (LagrangePolynomial.py:242-246)
     with torch.cuda.device(x.device):
@@ -213,16 +234,15 @@ def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float
                                                  padding, dilation, n, segments, length, int(discontinuous),
                                                  _per(periodicity), _ptr(ws), nbytes, _stream(x)),
                    "hol_pw_conv2d_forward_f32")
-    return y, ws
+    return y
 
 
 @pw_conv2d_rows.register_fake
-def _(x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
+def _(x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
     B, C, H, W = x.shape
     Ho = conv_out_size(H, kernel_size, stride, padding, dilation)
     Wo = conv_out_size(W, kernel_size, stride, padding, dilation)
-    return (torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device),
-            torch.empty((0,), dtype=torch.uint8, device=x.device))
+    return torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device)
 
 
 @torch.library.custom_op("hol::pw_conv2d_rows_backward", mutates_args=("ws",), device_types="cuda")
@@ -255,25 +275,29 @@ def _(gy, x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_s
     return (torch.empty_like(x) if need_dx else e, torch.empty_like(w_fc) if need_dw else e)
 
 
-def _conv_setup(ctx, inputs, output):
-    x, w_fc = inputs[0], inputs[1]
-    _, ws = output
-    ctx.save_for_backward(x, w_fc, ws)
-    ctx.args = tuple(inputs[2:])
+class _PiecewiseConvRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
+        ws = conv_workspace(x, w_fc, n, segments, discontinuous, kernel_size, stride, padding, dilation)
+        y = pw_conv2d_rows(x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding,
+                           dilation)
+        ctx.save_for_backward(x, w_fc)
+        ctx.ws = ws
+        ctx.args = (n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation)
+        return y
 
-
-def _conv_bwd(ctx, gy, _gws):
-    x, w_fc, ws = ctx.saved_tensors
-    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-    dx = dw = None
-    if need_dx or need_dw:
-        rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ws, *ctx.args, need_dx, need_dw, True)
-        dx = rdx if need_dx else None
-        dw = rdw if need_dw else None
-    return (dx, dw) + (None,) * 9
-
-
-pw_conv2d_rows.register_autograd(_conv_bwd, setup_context=_conv_setup)
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w_fc = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = dw = None
+        if need_dx or need_dw:
+            rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ctx.ws, *ctx.args, need_dx, need_dw, True)
+            dx = rdx if need_dx else None
+            dw = rdw if need_dw else None
+        ctx.ws = None
+        return (dx, dw) + (None,) * 9
 
 
 def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
@@ -286,8 +310,9 @@ def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int
     K = kernel_size
     nb = _nb(n, segments, discontinuous)
     w_fc = weight.view(O, C, nb, K, K).permute(0, 1, 3, 4, 2).reshape(O, C * K * K, nb)
-    y_rows, _ = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K, stride,
-                               padding, dilation)
+    _check_inputs(x, w_fc, "piecewise_polynomial_conv2d")
+    y_rows = _PiecewiseConvRowsFn.apply(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K,
+                                        stride, padding, dilation)
     Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
     y = y_rows.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
     if rescale != 1.0:

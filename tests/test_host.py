@@ -31,7 +31,12 @@ def test_abi_library_exports_every_declared_symbol():
 def test_workspace_queries_need_no_gpu():
     lib = _lib.load()
     c2 = lib.hol_pw_workspace_bytes(65536, 1024, 1024, 5, 8, 1)
-    assert 5e8 < c2 < 2e9
+    assert 5e8 < c2 < 2e10      # tensor-core path: + <= 8 GiB of operand tiles per launch chunk
+    os.environ["HOL_DISABLE_TC"] = "1"
+    try:
+        assert 5e8 < lib.hol_pw_workspace_bytes(65536, 1024, 1024, 5, 8, 1) < 2e9   # gather path only
+    finally:
+        del os.environ["HOL_DISABLE_TC"]
     assert lib.hol_pw_workspace_bytes(8, 4, 4, 11, 2, 0) == 0          # n above the compiled envelope
     assert lib.hol_pw_workspace_bytes(8, 4, 4, 3, 5000, 0) == 0        # too many segments
     assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 32, 32, 6, 5, 1, 0, 1, 3, 4, 0) > 0
@@ -103,7 +108,7 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="CUDA"):
         conv(torch.zeros(1, 1, 4, 4))
     with pytest.raises((RuntimeError, NotImplementedError)):
-        ops.pw_forward(torch.zeros(4, 2), layer.w, 3, 2, 2.0, False, None)
+        ops.piecewise_polynomial(torch.zeros(4, 2), layer.w, 3, 2, 2.0, False, None)
 
 
 def test_cpu_helpers_match_reference_segment_index():
@@ -126,9 +131,9 @@ def test_fake_tensor_shapes():
     # register_fake: shape/dtype propagation without a device
     x = torch.empty(7, 5, device="meta")
     w = torch.empty(3, 5, 9, device="meta")
-    y, ws = ops.pw_forward(x, w, 3, 4, 2.0, False, None)
+    y = ops.piecewise_polynomial(x, w, 3, 4, 2.0, False, None)
     assert y.shape == (7, 3) and y.dtype == torch.float32
     xi = torch.empty(2, 3, 8, 8, device="meta")
     wf = torch.empty(4, 27, 9, device="meta")
-    yr, _ = ops.pw_conv2d_rows(xi, wf, 3, 4, 2.0, False, None, 3, 1, 0, 1)
+    yr = ops.pw_conv2d_rows(xi, wf, torch.empty(0, dtype=torch.uint8, device="meta"), 3, 4, 2.0, False, None, 3, 1, 0, 1)
     assert yr.shape == (2 * 6 * 6, 4)
