@@ -127,6 +127,38 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def count_launches(layers, first_needs_dx=True, conv=False):
+    """Kernels of csrc/ launched per step for a stack of layers [(B, I, O, n, S, disc), ...]."""
+    from high_order_layers_torch_b200 import ops
+    total = 0
+    for k, (B, I, O, n, S, disc) in enumerate(layers):
+        want_dx = first_needs_dx or k > 0
+        total += ops.launch_count(0, B, I, O, n, S, disc)
+        total += ops.launch_count(1, B, I, O, n, S, disc, want_dx=want_dx, want_dw=True, prepared=True)
+        if conv and want_dx:
+            total += 1  # col2im
+    return total
+
+
+def tc_gemm_flops(kind, B, I, O, n, S, disc):
+    """Dense tensor-core flops EXECUTED by the split-fp16 GEMM of one pass (3 MMAs per k-step),
+    with the tile padding of csrc/tc_gemm.cu (tc_plan)."""
+    up = lambda a, b: (a + b - 1) // b * b
+    nb = nb_of(n, S, disc)
+    kin = up(nb, 8)
+    K = I * kin
+    bn = 256 if O > 128 else (128 if O > 64 else 64)
+    Bp = up(B, 512) if B > 256 else up(B, 32)
+    if kind == "forward":
+        M, N, Kc = up(Bp, 128), up(O, bn), up(K, 64)
+    elif kind == "dx":
+        bnx = (256 // (2 * kin)) * (2 * kin)
+        M, N, Kc = up(Bp, 128), up(K, bnx), up(O, 64)
+    else:
+        M, N, Kc = up(K, 128), up(O, bn), up(Bp, 64)
+    return 3 * 2 * M * N * Kc
+
+
 def make_inputs(torch, shape, gen, device):
     """x = 2*rand-1 with 1 % of the entries drawn from uniform(-1.25, 1.25)."""
     x = torch.rand(shape, generator=gen, device=device) * 2 - 1
@@ -177,7 +209,7 @@ def build_workload(torch, cfg, device, rank, args):
                   host=dict(x=x.detach().cpu().pin_memory(), gy=gy.cpu().pin_memory(),
                             loss=torch.zeros((), dtype=torch.float32).pin_memory()),
                   h2d=4 * B * I + 4 * B * O, d2h=4, bytes=by, flops=fl,
-                  launches=3 + 1 + 2,  # prep, pack, forward | dX | bucket sort, dW  (csrc kernels per step)
+                  launches=count_launches([(B, I, O, n, S, disc)]),
                   layers=[(B, I, O, n, S, disc)], x=x, gy=gy)
         return wl
 
@@ -226,7 +258,7 @@ def build_workload(torch, cfg, device, rank, args):
                   host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory(),
                             loss=torch.zeros((), dtype=torch.float32).pin_memory()),
                   h2d=x.numel() * 4 + target.numel() * target.element_size(), d2h=4, bytes=by, flops=fl,
-                  launches=3 * nl + (nl - 1) + 2 * nl,
+                  launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False),
                   layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x)
         return wl
 
@@ -283,7 +315,8 @@ def build_workload(torch, cfg, device, rank, args):
                   host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory(),
                             loss=torch.zeros((), dtype=torch.float32).pin_memory()),
                   h2d=x.numel() * 4 + target.numel() * 8, d2h=4, bytes=b1 + b2, flops=f1 + f2,
-                  launches=3 + 3 + (2 + 2) + (1 + 1 + 2),  # fwd x2; conv2 bwd: dX, col2im, sort, dW; conv1 bwd: sort, dW
+                  launches=count_launches([(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)],
+                                          first_needs_dx=False, conv=True),
                   layers=[(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)], x=x)
         return wl
     raise KeyError(cfg["kind"])
@@ -386,7 +419,8 @@ def run_ours(args):
             "step_algorithmic": {"bytes": wl["bytes"], "flops": wl["flops"],
                                  "hbm_frac_of_measured": wl["bytes"] / (ms_per_step / 1e3) / (peaks["hbm_gbs"] * 1e9),
                                  "fp32_frac_of_74.4TF": wl["flops"] / (ms_per_step / 1e3) / (FP32_PEAK_TFLOPS * 1e12),
-                                 "binding_roof": "fp32 (SIMT FMA issue / shared-memory bandwidth), not HBM"},
+                                 "binding_roof": "compute (tensor pipe on the tcgen05 path, fp32 FMA issue / shared "
+                                                 "memory on the gather path), not HBM"},
         }
         print(json.dumps(out))
     if world > 1:
@@ -423,6 +457,29 @@ def measure_roofline(torch, wl, ms_per_step):
     for _ in range(reps):
         for k, v in ops.profile_layer(x, w, gy, n, S, 2.0, disc, None).items():
             acc[k] = acc.get(k, 0.0) + v / reps
+    layer = {"B": B, "I": I, "O": O, "n": n, "segments": S, "discontinuous": disc}
+    hbm_note = ("this contraction is compute bound (arithmetic intensity >> ridge), so the HBM fraction of its "
+                "algorithmic bytes is small by construction")
+    if acc.get("gemm_fwd", 0.0) > 0.0:
+        # tensor-core path: the dominant kernel is the split-fp16 tcgen05 GEMM
+        names = {"forward": "gemm_fwd", "dx": "gemm_dx", "dw": "gemm_dw"}
+        dom = max(names, key=lambda k: acc[names[k]])
+        t = acc[names[dom]] / 1e3
+        executed = tc_gemm_flops(dom, B, I, O, n, S, disc)
+        by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        achieved = executed / t / 1e12
+        return {"bound": "tensor", "kernel": f"pw_tc_gemm_kernel ({dom} pass: split-fp16 hi*hi + hi*lo + lo*hi)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step); burst "
+                               f"{peaks['bf16_tflops']}",
+                "traffic": None, "executed_tensor_flops_per_launch_set": executed, "launch_ms": acc[names[dom]],
+                "useful": {"flops": fl, "tflops": fl / t / 1e12,
+                           "note": "2*B*I*O*n useful flops of this pass; the dense segment-expanded form executes "
+                                   "3*Kin/n times as many on the tensor pipe"},
+                "hbm": {"algorithmic_bytes": by, "achieved_gbs": by / t / 1e9, "frac": by / t / 1e9 / peaks["hbm_gbs"],
+                        "note": hbm_note},
+                "kernel_ms": acc, "layer": layer}
     dom = max(("forward", "dx", "dw"), key=lambda k: acc[k])
     by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
     t = acc[dom] / 1e3
@@ -433,9 +490,7 @@ def measure_roofline(torch, wl, ms_per_step):
             "algorithmic_bytes_per_launch": by, "launch_ms": acc[dom],
             "fp32": {"achieved_tflops": fl / t / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
                      "frac": fl / t / 1e12 / FP32_PEAK_TFLOPS, "flops_per_launch": fl},
-            "kernel_ms": acc, "layer": {"B": B, "I": I, "O": O, "n": n, "segments": S, "discontinuous": disc},
-            "note": "this contraction is bound by fp32 FMA issue / shared-memory bandwidth (arithmetic intensity "
-                    ">> ridge), so the HBM fraction is small by construction; see fp32.frac"}
+            "kernel_ms": acc, "layer": layer, "note": hbm_note + "; see fp32.frac"}
 
 
 # ------------------------------------------------------------------------------------------

@@ -286,6 +286,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
         if (cudaEventCreate(&ev[k]) != cudaSuccess) return (int)cudaGetLastError();
     int rc = HOL_OK;
     auto mark = [&](int k) { cudaEventRecord(ev[k], st); };
+    tc_prof_begin();
     mark(0);
     rc = launch_prep_fc(x, s, ws, st);
     mark(1);
@@ -312,16 +313,23 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
         ms_out_host[k] = ms;
     }
     for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
+    float g3[3];
+    tc_prof_end(g3);
+    ms_out_host[6] = g3[0];  // tensor-core GEMM inside "forward"
+    ms_out_host[7] = g3[2];  // ... inside "dx"
+    ms_out_host[8] = g3[1];  // ... inside "dw"
     return rc;
 }
 
-int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags) {
-    if (kind == 0) return 3;  // prep, pack, forward
-    int c = 0;
-    if (!(flags & HOL_WS_PREPARED)) c += 1 + ((want_dx && n > 1) ? 1 : 0);
-    if (want_dx && n > 1) c += 1;
-    if (want_dw) c += 2;  // bucket sort + dW (memsets are not kernels of ours; +1 reduce when dW is split)
-    (void)discontinuous;
+int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous,
+                        int32_t want_dx, int32_t want_dw, uint32_t flags) {
+    PwShape s;
+    if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
+    const bool prepared = (flags & HOL_WS_PREPARED) != 0;
+    if (kind == 0) return 1 + (s.tc.enabled ? tc_launch_count(s, s.tc, 0) : 2);  // prep + (pack, forward)
+    int c = prepared ? 0 : 1;  // prep
+    if (want_dx && n > 1) c += s.tc.enabled ? tc_launch_count(s, s.tc, 1) : (prepared ? 1 : 2);
+    if (want_dw) c += s.tc.enabled ? tc_launch_count(s, s.tc, 2) : (2 + (s.ksplit > 1 ? 1 : 0));
     return c;
 }
 

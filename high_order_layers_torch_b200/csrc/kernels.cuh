@@ -27,5 +27,9 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
 int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
                           float* dx, int transposed, cudaStream_t st);
 
+void tc_prof_begin();
+void tc_prof_end(float* ms3);
+int tc_launch_count(const PwShape& s, const TcPlan& t, int kind);
+
 // usable dynamic shared memory per CTA on sm_100 (227 KB) minus a safety margin
 #define HOL_SMEM_BUDGET (220 * 1024)

@@ -93,6 +93,31 @@ static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws
     p.tab = s.tab;
 }
 
+// diagnostic timing of the GEMM launches (only while hol_pw_profile_f32 runs on this thread)
+struct TcProf {
+    int active, count;
+    cudaEvent_t ev[48][2];
+    int kind[48];
+};
+static thread_local TcProf g_prof = {0, 0, {}, {}};
+
+void tc_prof_begin() {
+    g_prof.active = 1;
+    g_prof.count = 0;
+}
+// ms3[k] = summed duration of the GEMM launches with epilogue k (EPI_Y, EPI_DW, EPI_DX); call after a sync
+void tc_prof_end(float* ms3) {
+    ms3[0] = ms3[1] = ms3[2] = 0.0f;
+    for (int k = 0; k < g_prof.count; ++k) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[k][0], g_prof.ev[k][1]) == cudaSuccess) ms3[g_prof.kind[k]] += ms;
+        cudaEventDestroy(g_prof.ev[k][0]);
+        cudaEventDestroy(g_prof.ev[k][1]);
+    }
+    g_prof.active = 0;
+    g_prof.count = 0;
+}
+
 static int sm_count() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -115,8 +140,24 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     if (e != cudaSuccess) return (int)e;
     const int64_t sms = sm_count();
     const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);  // persistent: one CTA per SM
+    const bool prof = g_prof.active && g_prof.count < 48;
+    if (prof) {
+        cudaEventCreate(&g_prof.ev[g_prof.count][0]);
+        cudaEventCreate(&g_prof.ev[g_prof.count][1]);
+        g_prof.kind[g_prof.count] = EPI;
+        cudaEventRecord(g_prof.ev[g_prof.count][0], st);
+    }
     kern<<<grid, 320, smem, st>>>(p);
+    if (prof) cudaEventRecord(g_prof.ev[g_prof.count++][1], st);
     return (int)cudaGetLastError();
+}
+
+// kernels of ours per call (bench.py's gpu_launches): kind 0 forward, 1 dX, 2 dW (prep not included)
+int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
+    const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
+    if (kind == 0) return 2 + 1 + nl * 2;  // absmax x2, pack_w, (expand, gemm) per batch chunk
+    if (kind == 1) return 2 + 1 + nl * 2;  // absmax x2, pack_wt, (pack_gy, gemm)
+    return 2 + nl * 3;                     // absmax x2, (expand_t, pack_gyt, gemm)
 }
 
 #define DISPATCH_N(n, CALL)                       \

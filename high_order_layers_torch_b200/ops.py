@@ -320,29 +320,14 @@ def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int
     return y
 
 
-def launch_count(kind: int, n: int, discontinuous: bool, want_dx: bool, want_dw: bool, prepared: bool) -> int:
-    return _lib.load().hol_pw_launch_count(kind, n, int(discontinuous), int(want_dx), int(want_dw),
+def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, discontinuous: bool, want_dx: bool = True,
+                 want_dw: bool = True, prepared: bool = True) -> int:
+    """Kernels of this library launched by one forward (kind 0) / backward (kind 1) call of a layer."""
+    return _lib.load().hol_pw_launch_count(kind, B, I, O, n, segments, int(discontinuous), int(want_dx), int(want_dw),
                                            _lib.HOL_WS_PREPARED if prepared else 0)
 
 
-def profile_layer(x: Tensor, w: Tensor, gy: Tensor, n: int, segments: int, length: float = 2.0,
-                  discontinuous: bool = False, periodicity: Optional[float] = None) -> dict:
-    """Diagnostic: per-kernel CUDA-event durations (ms) of one forward+backward of a layer
-    (hol_pw_profile_f32; synchronises).  Keys: prep, pack, forward, dx, bucket_sort, dw."""
-    _check_inputs(x, w, "profile_layer")
-    B, I = x.shape
-    O = w.shape[0]
+def uses_tensor_cores(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> bool:
+    """True when the layer shape is planned onto the tcgen05 path (csrc/tc_gemm.cu: tc_plan)."""
     lib = _lib.load()
-    nbytes = lib.hol_pw_workspace_bytes(B, I, O, n, segments, int(discontinuous))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    y = torch.empty((B, O), dtype=torch.float32, device=x.device)
-    dx = torch.empty_like(x)
-    dw = torch.empty_like(w)
-    ms = (ctypes.c_float * 6)()
-    nodes = lobatto_nodes(n, 2.0)
-    with torch.cuda.device(x.device):
-        _lib.check(lib.hol_pw_profile_f32(_ptr(gy.contiguous()), _ptr(x.contiguous()), _ptr(w.contiguous()),
-                                          _ptr(nodes), _ptr(y), _ptr(dx), _ptr(dw), B, I, O, n, segments, length,
-                                          int(discontinuous), _per(periodicity), _ptr(ws), nbytes,
-                                          ctypes.cast(ms, ctypes.c_void_p), _stream(x)), "hol_pw_profile_f32")
-    return dict(zip(("prep", "pack", "forward", "dx", "bucket_sort", "dw"), (float(v) for v in ms)))
+    return lib.hol_pw_launch_count(0, B, I, O, n, segments, int(discontinuous), 1, 1, 0) > 3

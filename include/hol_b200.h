@@ -118,17 +118,19 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
 
 /* DIAGNOSTIC entry (the only one that synchronises): runs forward + backward once on `stream`
  * with CUDA events between the kernels and returns their durations in milliseconds in
- * ms_out_host[6] = {prep, pack, forward, dx, bucket_sort, dw}.  Used by bench.py for the
- * per-kernel roofline numbers; not part of the drop-in path. */
+ * ms_out_host[9] = {prep, pack, forward, dx, bucket_sort, dw, gemm_fwd, gemm_dx, gemm_dw}: the
+ * first six bracket the stages (for a tensor-core layer "forward"/"dx"/"dw" include the operand
+ * builders), the last three are the tcgen05 GEMM launches alone (0 on the gather path).  Used by
+ * bench.py for the per-kernel roofline numbers; not part of the drop-in path. */
 int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const float* nodes_host,
                        float* y, float* dx, float* dw, int64_t B, int32_t I, int32_t O, int32_t n,
                        int32_t S, float length, int32_t discontinuous, float periodicity, void* ws,
                        size_t ws_bytes, float* ms_out_host, void* stream);
 
-/* Number of kernel launches the last call of each kind issues for the given shape
- * (what bench.py reports as gpu_launches).  kind: 0 forward, 1 backward(dx+dw). */
-int hol_pw_launch_count(int kind, int32_t n, int32_t discontinuous, int32_t want_dx,
-                        int32_t want_dw, uint32_t flags);
+/* Number of kernels of this library one call launches for the given shape (what bench.py
+ * reports as gpu_launches).  kind: 0 forward, 1 backward (want_dx / want_dw select the parts). */
+int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
+                        int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags);
 
 #ifdef __cplusplus
 }
