@@ -331,3 +331,27 @@ def uses_tensor_cores(B: int, I: int, O: int, n: int, segments: int, discontinuo
     """True when the layer shape is planned onto the tcgen05 path (csrc/tc_gemm.cu: tc_plan)."""
     lib = _lib.load()
     return lib.hol_pw_launch_count(0, B, I, O, n, segments, int(discontinuous), 1, 1, 0) > 3
+
+
+def profile_layer(x: Tensor, w: Tensor, gy: Tensor, n: int, segments: int, length: float = 2.0,
+                  discontinuous: bool = False, periodicity: Optional[float] = None) -> dict:
+    """Diagnostic: CUDA-event durations (ms) of the stages of one forward+backward of a layer
+    (hol_pw_profile_f32; synchronises).  Keys: prep, pack, forward, dx, bucket_sort, dw and, for a
+    tensor-core layer, gemm_fwd / gemm_dx / gemm_dw (the tcgen05 GEMM launches alone)."""
+    _check_inputs(x, w, "profile_layer")
+    B, I = x.shape
+    O = w.shape[0]
+    lib = _lib.load()
+    ws = fc_workspace(x, w, n, segments, discontinuous)
+    y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    dw = torch.empty_like(w)
+    ms = (ctypes.c_float * 9)()
+    nodes = lobatto_nodes(n, 2.0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_profile_f32(_ptr(gy.contiguous()), _ptr(x.contiguous()), _ptr(w.contiguous()),
+                                          _ptr(nodes), _ptr(y), _ptr(dx), _ptr(dw), B, I, O, n, segments, length,
+                                          int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
+                                          ctypes.cast(ms, ctypes.c_void_p), _stream(x)), "hol_pw_profile_f32")
+    return dict(zip(("prep", "pack", "forward", "dx", "bucket_sort", "dw", "gemm_fwd", "gemm_dx", "gemm_dw"),
+                    (float(v) for v in ms)))
