@@ -393,7 +393,10 @@ def run_ours(args):
     roof = None
     cpu = None
     if rank == 0:
-        roof = measure_roofline(torch, wl, ms_per_step)
+        try:
+            roof = measure_roofline(torch, wl, ms_per_step)
+        except torch.OutOfMemoryError as e:  # the largest sweep points leave no room for a second workspace
+            roof = {"error": f"out of memory in the diagnostic pass: {str(e)[:80]}"}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(cfg, budget_s=args.cpu_budget)
     if world > 1:
@@ -447,12 +450,21 @@ def measure_roofline(torch, wl, ms_per_step):
     peaks = load_peaks()
     B, I, O, n, S, disc = max(wl["layers"], key=lambda t: t[0] * t[1] * t[2] * t[3])
     dev = wl["x"].device
-    gen = torch.Generator(device=dev).manual_seed(99)
-    x = make_inputs(torch, (B, I), gen, dev)
-    w = torch.rand(O, I, nb_of(n, S, disc), generator=gen, device=dev) * 2 - 1
-    gy = torch.randn(B, O, generator=gen, device=dev)
+    if wl["cfg"]["kind"] == "layer":
+        # reuse the workload's own tensors (the 4096x4096 sweep points do not fit twice) and drop its gradients
+        x, gy, w = wl["x"].detach(), wl["gy"], wl["model"].w.detach()
+        for prm in wl["flat"].params:
+            prm.grad = None
+        wl["flat"].flat = None
+        wl["x"].grad = None
+        torch.cuda.empty_cache()
+    else:
+        gen = torch.Generator(device=dev).manual_seed(99)
+        x = make_inputs(torch, (B, I), gen, dev)
+        w = torch.rand(O, I, nb_of(n, S, disc), generator=gen, device=dev) * 2 - 1
+        gy = torch.randn(B, O, generator=gen, device=dev)
     acc = {}
-    reps = 3
+    reps = 3 if B * I * O * n < 2e12 else 1
     ops.profile_layer(x, w, gy, n, S, 2.0, disc, None)  # warm
     for _ in range(reps):
         for k, v in ops.profile_layer(x, w, gy, n, S, 2.0, disc, None).items():
