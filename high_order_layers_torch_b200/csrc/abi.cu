@@ -122,7 +122,7 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
             const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
             cudaError_t e = cudaMemsetAsync(dx, 0, bytes, st);
             if (e != cudaSuccess) return (int)e;
-        } else if (s.tc.enabled) {
+        } else if (s.tc.dx) {
             HOL_TRY(launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, dx_transposed, st));
         } else {
             if (!packed) HOL_TRY(launch_pack(w, s, ws, st));
@@ -130,7 +130,7 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
         }
     }
     if (dw) {
-        if (s.tc.enabled) {
+        if (s.tc.dw) {
             HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, st));
         } else {
             HOL_TRY(launch_bucket_sort(s, ws, st));
@@ -183,7 +183,7 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_fc(x, s, ws, st));
-    if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w, y, st);
+    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w, y, st);
     HOL_TRY(launch_pack(w, s, ws, st));
     return launch_forward(s, ws, y, st);
 }
@@ -207,7 +207,7 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_fc(x, s, ws, st));
     }
-    return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0, st);
+    return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, st);
 }
 
 size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
@@ -237,7 +237,7 @@ int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* no
     if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
-    if (s.tc.enabled) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
+    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
     HOL_TRY(launch_pack(w_fc, s, ws, st));
     return launch_forward(s, ws, y_rows, st);
 }
@@ -266,7 +266,7 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     }
-    HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc, (flags & HOL_WS_PREPARED) != 0, st));
+    HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, st));
     if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     return HOL_OK;
 }
@@ -290,20 +290,20 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     mark(0);
     rc = launch_prep_fc(x, s, ws, st);
     mark(1);
-    if (rc == HOL_OK && !s.tc.enabled) rc = launch_pack(w, s, ws, st);
+    if (rc == HOL_OK && !(s.tc.fwd && (s.tc.dx || n == 1))) rc = launch_pack(w, s, ws, st);
     mark(2);
-    if (rc == HOL_OK) rc = s.tc.enabled ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
+    if (rc == HOL_OK) rc = s.tc.fwd ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
     mark(3);
     if (rc == HOL_OK) {
         if (n == 1)
             cudaMemsetAsync(dx, 0, (size_t)B * I * 4, st);
         else
-            rc = s.tc.enabled ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, st) : launch_backward_dx(s, ws, gy, dx, 0, st);
+            rc = s.tc.dx ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, st) : launch_backward_dx(s, ws, gy, dx, 0, st);
     }
     mark(4);
-    if (rc == HOL_OK && !s.tc.enabled) rc = launch_bucket_sort(s, ws, st);
+    if (rc == HOL_OK && !s.tc.dw) rc = launch_bucket_sort(s, ws, st);
     mark(5);
-    if (rc == HOL_OK) rc = s.tc.enabled ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st);
+    if (rc == HOL_OK) rc = s.tc.dw ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st);
     mark(6);
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == HOL_OK && e != cudaSuccess) rc = (int)e;
@@ -326,10 +326,10 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     PwShape s;
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
     const bool prepared = (flags & HOL_WS_PREPARED) != 0;
-    if (kind == 0) return 1 + (s.tc.enabled ? tc_launch_count(s, s.tc, 0) : 2);  // prep + (pack, forward)
+    if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0) : 2);  // prep + (pack, forward)
     int c = prepared ? 0 : 1;  // prep
-    if (want_dx && n > 1) c += s.tc.enabled ? tc_launch_count(s, s.tc, 1) : (prepared ? 1 : 2);
-    if (want_dw) c += s.tc.enabled ? tc_launch_count(s, s.tc, 2) : (2 + (s.ksplit > 1 ? 1 : 0));
+    if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1) : ((prepared && !s.tc.fwd) ? 1 : 2);
+    if (want_dw) c += s.tc.dw ? tc_launch_count(s, s.tc, 2) : (2 + (s.ksplit > 1 ? 1 : 0));
     return c;
 }
 

@@ -20,7 +20,8 @@ struct BasisTab {
 
 // Plan of the tensor-core (tcgen05) forward for layers with few segments (tc.cu).
 struct TcPlan {
-    bool enabled;
+    bool enabled;             // any pass on the tensor cores
+    bool fwd, dx, dw;         // per pass (thresholds fitted to the c5 sweep, see tc_plan)
     int Kin;                  // dense columns per input: weights per link padded to 8
     int BN, nNT;              // output tile width and count
     int nkc;                  // 64-wide K chunks

@@ -33,19 +33,25 @@
 static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : 64); }
 
 bool tc_plan(const PwShape& s, TcPlan& t) {
-    t.enabled = false;
+    t.enabled = t.fwd = t.dx = t.dw = false;
     const char* off = getenv("HOL_DISABLE_TC");
     if (off && off[0] == '1') return false;
     t.Kin = (s.nb + 7) / 8 * 8;
-    // the dense form costs 3*Kin tensor MACs per n useful fp32 FMAs
-    if (t.Kin > 20 * s.n || t.Kin > 128) return false;
     if (s.O < 32 || s.I * (int64_t)t.Kin < 256) return false;  // too narrow to be worth a tile
+    // The dense form costs 3*Kin tensor MACs per n useful fp32 FMAs, so its time grows with Kin (i.e.
+    // with the segment count) while the gather kernels' does not.  Cross-over points measured on
+    // B200 (c5 sweep, profiles/r1_sweep_c5.md): forward/dX gather run at ~7-16 TFLOP/s useful, the
+    // bucketed dW gather at ~25-40, the tensor path at ~1.3 PFLOP/s executed.
+    t.fwd = t.Kin <= 40 * s.n;
+    t.dx = t.fwd && t.Kin <= 128 && s.n > 1;  // the dX epilogue keeps whole inputs per thread (Kin <= 128)
+    t.dw = t.Kin <= 44 + 7 * s.n;
+    if (!t.fwd && !t.dw) return false;
     t.BN = tc_bn_for(s.O);
     t.nNT = (s.O + t.BN - 1) / t.BN;
     const int64_t K = (int64_t)s.I * t.Kin;
     t.nkc = (int)((K + TC_BK - 1) / TC_BK);
     // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kin (and of 16), <= 256
-    t.BNx = (256 / (2 * t.Kin)) * (2 * t.Kin);
+    t.BNx = t.Kin <= 128 ? (256 / (2 * t.Kin)) * (2 * t.Kin) : 256;
     t.nNTx = (int)((K + t.BNx - 1) / t.BNx);
     t.noc = (s.O + TC_BK - 1) / TC_BK;
     // dW: M tiles over the dense columns
@@ -66,7 +72,7 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     if (a_gy > a) a = a_gy;
     size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);           // W
     const size_t b_gyt = (size_t)t.nNT * bchunks * 2 * ((size_t)t.BN * TC_BK * 2);  // gy^T
-    const size_t b_wt = (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2);   // W^T
+    const size_t b_wt = t.dx ? (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2) : 0;  // W^T
     if (b_gyt > bb) bb = b_gyt;
     if (b_wt > bb) bb = b_wt;
     t.a_bytes = a;

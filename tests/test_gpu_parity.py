@@ -118,7 +118,9 @@ FC_ORACLE_CASES = [
     ("cont", 3, 2, 10, 10, 1024, None),      # config-1 hidden layer
     ("cont", 3, 2, 1, 10, 33, None),
     ("disc", 2, 64, 70, 130, 513, None),     # odd sizes, many segments, batch just over one tile
-    ("cont", 8, 32, 33, 65, 300, None),
+    ("cont", 8, 32, 33, 65, 300, None),      # mixed plan: tensor-core forward, gather dX and dW
+    ("cont", 4, 32, 33, 65, 300, None),      # mixed plan: tensor-core forward + dX, gather dW
+    ("disc", 3, 8, 200, 96, 700, None),      # all three passes on tensor cores, 2 batch tiles, ragged N tile
     ("disc", 10, 3, 7, 5, 2, None),
     ("cont", 1, 4, 9, 6, 40, None),
     ("disc", 1, 4, 9, 6, 40, None),
