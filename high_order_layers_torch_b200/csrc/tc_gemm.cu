@@ -140,7 +140,11 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     p.nst = nst;
     p.flush_chunks = p.BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
     p.ntile_n = ntiles_n;
+    p.ntile_m = mtiles;
     p.ntiles = mtiles * ntiles_n;
+    p.group_m = ntiles_n >= 12 ? 12 : (148 + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
+    if (p.group_m > mtiles) p.group_m = (int)mtiles;
+    if (p.group_m < 1) p.group_m = 1;
     auto kern = pw_tc_gemm_kernel<EPI, N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

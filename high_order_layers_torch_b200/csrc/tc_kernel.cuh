@@ -47,17 +47,30 @@ struct TcGemmParams {
     const float* xl_t;             // EPI_DX
     const uint16_t* seg_t;         // EPI_DX
     int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
-    int64_t ntiles;                // m-tiles * n-tiles (n fastest)
-    int ntile_n;
+    int64_t ntiles;                // m-tiles * n-tiles
+    int64_t ntile_m;
+    int ntile_n, group_m;          // rasterisation: groups of group_m m-tiles, m fastest inside a group
     int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
     int I, nb, Kin, stride, transposed;
     float length, Sf;
     BasisTab tab;
 };
 
+// tile index -> (m-tile, n-tile): m-tiles are taken in groups of group_m, inside a group the m-tile
+// varies fastest, so the ~148 CTAs running together cover a group_m x (148/group_m) block of tiles
+// and share both their A tiles and their B tiles in L2.
+__device__ __forceinline__ void tile_coords(const TcGemmParams& p, int64_t tile, int64_t& mt, int& nt) {
+    const int64_t per_group = (int64_t)p.group_m * p.ntile_n;
+    const int64_t group = tile / per_group;
+    const int64_t first_m = group * p.group_m;
+    const int64_t gsize = p.ntile_m - first_m < p.group_m ? p.ntile_m - first_m : p.group_m;
+    const int64_t local = tile - group * per_group;
+    mt = first_m + local % gsize;
+    nt = (int)(local / gsize);
+}
+
 // Persistent: grid = min(#tiles, #SMs); every role walks the same tile sequence
-// tile = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so CTAs running together share
-// A tiles in L2).  The smem ring (full/empty) and the two TMEM accumulators (tmem_full/tmem_empty)
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring (full/empty) and the two TMEM accumulators (tmem_full/tmem_empty)
 // run continuously across tiles, so the epilogue of tile t overlaps the main loop of tile t+1.
 // N is the basis size for the EPI_DX gather (0 otherwise).
 template <int EPI, int N>
@@ -107,8 +120,9 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
         if (lane == 0) {
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int nt = (int)(tile % p.ntile_n);
-                const int64_t mt = tile / p.ntile_n;
+                int nt;
+                int64_t mt;
+                tile_coords(p, tile, mt, nt);
                 const unsigned char* a_src = p.a_tiles + (mt * p.nkc) * (int64_t)(2 * TC_A_IMG);
                 const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
                 for (int kc = 0; kc < p.nkc; ++kc, ++it) {
@@ -175,8 +189,9 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
             inv = 1.0f / (pow2_scale_for(__uint_as_float(p.sc->max_gy)) * pow2_scale_for(__uint_as_float(p.sc->max_w)));
 
         for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const int nt = (int)(tile % p.ntile_n);
-            const int64_t mt = tile / p.ntile_n;
+            int nt;
+            int64_t mt;
+            tile_coords(p, tile, mt, nt);
             float racc[TC_MAXHALF];
 #pragma unroll
             for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
