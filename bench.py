@@ -359,6 +359,35 @@ def run_ours(args):
     for _ in range(warmup):
         step()
     barrier()
+    # Small-step workloads (MLP / conv nets: ~1 ms of GPU work in ~50 launches) are launch-latency
+    # bound in eager mode: capture the whole step (forward, backward, flat-gradient allreduce) in
+    # one CUDA graph and replay it.  The single-layer configs run for tens of ms and stay eager.
+    graphed = False
+    if args.graph == "on" or (args.graph == "auto" and cfg["kind"] in ("mlp", "conv")):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            eager_step = step
+            step = graph.replay
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            graphed = True
+        except Exception as e:  # capture is an optimisation, never a requirement
+            if rank == 0:
+                print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e)[:120]}); running eagerly",
+                      file=sys.stderr)
+            torch.cuda.synchronize()
+            step = wl["step"]
+    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -411,7 +440,8 @@ def run_ours(args):
             "config": {"workload": cfg["name"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world,
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)"
                        if wl["bytes"] > 3 * 126e6 else "working set fits L2; no flush between steps",
-                       "allreduce": "one flat fp32 NCCL sum-allreduce of dW per step" if world > 1 else "none"},
+                       "allreduce": "one flat fp32 NCCL sum-allreduce of dW per step" if world > 1 else "none",
+                       "cuda_graph": graphed},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": wl["h2d"],
                     "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps},
             "gpu_launches": wl["launches"] * steps,
@@ -689,6 +719,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture the step in a CUDA graph (auto: MLP / conv workloads only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

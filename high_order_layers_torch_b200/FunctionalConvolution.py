@@ -26,18 +26,21 @@ def _as_int(v, name: str) -> int:
     return int(v)
 
 
-class PiecewisePolynomialConvolution2d(nn.Module):
+class _PiecewiseConvolution2dBase(nn.Module):
+    _discontinuous = False
+
     def __init__(self, n: int, segments: int, in_channels: int, out_channels: int, kernel_size: int,
                  length: float = 2.0, rescale_output: bool = False, periodicity: Optional[float] = None,
                  weight_magnitude: float = 1.0, device: str = "cpu", *args, stride: int = 1, padding: int = 0,
                  dilation: int = 1, groups: int = 1, padding_mode: str = "zeros", **kwargs):
         super().__init__()
+        name = type(self).__name__
         if groups != 1:
-            raise ValueError("PiecewisePolynomialConvolution2d: groups != 1 is not supported by the CUDA path")
+            raise ValueError(f"{name}: groups != 1 is not supported by the CUDA path")
         if padding_mode != "zeros":
-            raise ValueError("PiecewisePolynomialConvolution2d: only padding_mode='zeros' is supported")
+            raise ValueError(f"{name}: only padding_mode='zeros' is supported")
         if isinstance(padding, str):
-            raise ValueError("PiecewisePolynomialConvolution2d: string padding modes are not supported")
+            raise ValueError(f"{name}: string padding modes are not supported")
         self._n = n
         self._segments = segments
         self._length = length
@@ -46,7 +49,7 @@ class PiecewisePolynomialConvolution2d(nn.Module):
         self._padding = _as_int(padding, "padding")
         self._dilation = _as_int(dilation, "dilation")
         self._in_channels = in_channels
-        self._nodes = (n - 1) * segments + 1
+        self._nodes = n * segments if self._discontinuous else (n - 1) * segments + 1
         self._channels = self._nodes * in_channels
         self._out_channels = out_channels
         self.periodicity = periodicity
@@ -76,10 +79,21 @@ class PiecewisePolynomialConvolution2d(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if not x.is_cuda:
             raise RuntimeError(
-                f"PiecewisePolynomialConvolution2d: input is on {x.device}; this build runs on CUDA (sm_100a) only "
+                f"{type(self).__name__}: input is on {x.device}; this build runs on CUDA (sm_100a) only "
                 "and has no CPU fallback")
         return ops.piecewise_polynomial_conv2d(x, self.conv.weight, self._n, self._segments, self._kernel_size,
-                                               length=float(self._length), discontinuous=False,
+                                               length=float(self._length), discontinuous=self._discontinuous,
                                                periodicity=self.periodicity, stride=self._stride,
                                                padding=self._padding, dilation=self._dilation,
                                                rescale=self._rescale)
+
+
+class PiecewisePolynomialConvolution2d(_PiecewiseConvolution2dBase):
+    """Continuous piecewise polynomial 2-d convolution (reference FunctionalConvolution.py:450-490)."""
+    _discontinuous = False
+
+
+class PiecewiseDiscontinuousPolynomialConvolution2d(_PiecewiseConvolution2dBase):
+    """Discontinuous variant: every segment owns its n nodes, C*n*segments expanded channels
+    (reference FunctionalConvolution.py:522-619; expansion Basis.py:220-296)."""
+    _discontinuous = True

@@ -122,3 +122,35 @@ class PiecewiseDiscontinuousPolynomial(PiecewiseDiscontinuous):
                  periodicity: Optional[float] = None, device: str = "cpu", **kwargs):
         super().__init__(n, in_features, out_features, segments, length, weight_magnitude, poly=LagrangePoly,
                          periodicity=periodicity, device=device)
+
+
+class Polynomial(nn.Module):
+    """One Lagrange polynomial per link on [-1, 1] (reference PolynomialLayers.py:26-76: Function with
+    LagrangePolyFlat): y[b,o] = sum_i sum_j phi_j(x[b,i]) w[o,i,j], no segment clamp.  It is the
+    single-segment case of the piecewise kernels; only the default length 2.0 maps onto
+    them (x_in == x), other lengths raise.  Keeps the reference's unused ``result`` parameter so
+    that state_dict keys match."""
+
+    def __init__(self, n: int, in_features: int, out_features: int, length: float = 2.0, weight_magnitude: float = 1.0,
+                 periodicity: Optional[float] = None, initialize: str = "constant_random", device: str = "cpu",
+                 **kwargs):
+        super().__init__()
+        if float(length) != 2.0:
+            raise ValueError("Polynomial: only length=2.0 is supported by the CUDA path")
+        self.poly = LagrangePoly(n, length=length)
+        self.n = n
+        self.in_features = in_features
+        self.out_features = out_features
+        self.periodicity = periodicity
+        self.w = nn.Parameter(torch.empty(out_features, in_features, n, device=device), requires_grad=True)
+        if initialize == "constant_random":
+            constant_random_initialization(self.w, out_features, in_features, weight_magnitude, device)
+        else:
+            self.w.data.uniform_(-weight_magnitude / in_features, weight_magnitude / in_features)
+        self.result = nn.Parameter(torch.empty(out_features), requires_grad=True)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(f"Polynomial: input is on {x.device}; this build runs on CUDA (sm_100a) only and has no "
+                               "CPU fallback")
+        return ops.piecewise_polynomial(x, self.w, self.n, 1, 2.0, True, self.periodicity)

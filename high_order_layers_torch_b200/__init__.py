@@ -13,8 +13,11 @@ from .layers import (  # noqa: F401
     high_order_convolution_layers,
     high_order_fc_layers,
 )
-from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial  # noqa: F401
-from .FunctionalConvolution import PiecewisePolynomialConvolution2d  # noqa: F401
+from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial  # noqa: F401
+from .FunctionalConvolution import (  # noqa: F401
+    PiecewiseDiscontinuousPolynomialConvolution2d,
+    PiecewisePolynomialConvolution2d,
+)
 from .networks import HighOrderMLP  # noqa: F401
 
 __version__ = "0.1.0"

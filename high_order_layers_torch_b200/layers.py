@@ -1,13 +1,14 @@
 """Layer registries and factories with the reference's names and error behaviour
 (reference layers.py:258-295, :357-372) restricted to the hot path: the keys ``continuous`` /
-``discontinuous`` (fully connected) and ``continuous2d`` (convolution).  Asking for any other key
+``discontinuous`` / ``polynomial`` (fully connected) and ``continuous2d`` / ``discontinuous2d``
+(convolution).  Asking for any other key
 raises the same ValueError the reference raises for an unknown layer type."""
 from __future__ import annotations
 
 import torch.nn as nn
 
-from .FunctionalConvolution import PiecewisePolynomialConvolution2d
-from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial
+from .FunctionalConvolution import PiecewiseDiscontinuousPolynomialConvolution2d, PiecewisePolynomialConvolution2d
+from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial
 from .utils import max_abs_normalization, max_abs_normalization_nd
 
 
@@ -52,10 +53,12 @@ normalization_layers = {"max_abs": MaxAbsNormalization}
 fc_layers = {
     "continuous": PiecewisePolynomial,
     "discontinuous": PiecewiseDiscontinuousPolynomial,
+    "polynomial": Polynomial,
 }
 
 convolutional_layers = {
     "continuous2d": PiecewisePolynomialConvolution2d,
+    "discontinuous2d": PiecewiseDiscontinuousPolynomialConvolution2d,
 }
 
 

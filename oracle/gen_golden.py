@@ -297,6 +297,55 @@ def main():
     mlp["cases"] = np.array(mlp_cases)
     np.savez_compressed(os.path.join(args.out, "mlp.npz"), **mlp)
 
+    # -------------------------------------------- SURVEY 8f-3 variants: discontinuous conv2d, Polynomial
+    var = {}
+    var_conv, var_poly = [], []
+    for (name, n, S, C, O, K, H, W, B, kw) in [("dconv_a", 3, 4, 2, 3, 3, 7, 7, 2, {}),
+                                               ("dconv_pad", 2, 5, 3, 2, 3, 6, 8, 2, dict(stride=2, padding=1)),
+                                               ("dconv_n1", 1, 3, 2, 2, 2, 5, 5, 1, {})]:
+        layer = R.fcv.PiecewiseDiscontinuousPolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O,
+                                                                   kernel_size=K, **kw)
+        with torch.no_grad():
+            layer.conv.weight.copy_(torch.from_numpy(
+                rng.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)))
+        x = rng.uniform(-1.2, 1.2, size=(B, C, H, W)).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        y = layer(xt)
+        gy = rng.standard_normal(size=tuple(y.shape)).astype(np.float32)
+        y.backward(torch.from_numpy(gy))
+        var[name + "_x"], var[name + "_w"], var[name + "_gy"] = x, layer.conv.weight.detach().numpy().copy(), gy
+        var[name + "_y"] = y.detach().numpy().copy()
+        var[name + "_dx"] = np.zeros_like(x) if xt.grad is None else xt.grad.numpy().copy()
+        var[name + "_dw"] = layer.conv.weight.grad.numpy().copy()
+        var[name + "_meta"] = np.array([n, S, C, O, K, H, W, B, kw.get("stride", 1), kw.get("padding", 0)], dtype=np.int64)
+        var_conv.append(name)
+    torch.manual_seed(1234)
+    dc = R.fcv.PiecewiseDiscontinuousPolynomialConvolution2d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3)
+    var["init_dconv_w"] = dc.conv.weight.detach().numpy().copy()
+    for (name, n, I, O, B, per) in [("poly_n3", 3, 5, 4, 9, None), ("poly_n5", 5, 7, 3, 11, None),
+                                    ("poly_n1", 1, 3, 2, 4, None), ("poly_n8_per", 8, 4, 6, 10, 2.0)]:
+        layer = R.pl.Polynomial(n=n, in_features=I, out_features=O, periodicity=per)
+        with torch.no_grad():
+            layer.w.copy_(torch.from_numpy(rng.uniform(-1, 1, size=tuple(layer.w.shape)).astype(np.float32)))
+        x = rng.uniform(-1, 1, size=(B, I)).astype(np.float32)
+        if per is not None:
+            x = rng.uniform(-5, 5, size=(B, I)).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        y = layer(xt)
+        gy = rng.standard_normal(size=tuple(y.shape)).astype(np.float32)
+        y.backward(torch.from_numpy(gy))
+        var[name + "_x"], var[name + "_w"], var[name + "_gy"] = x, layer.w.detach().numpy().copy(), gy
+        var[name + "_y"] = y.detach().numpy().copy()
+        var[name + "_dx"] = np.zeros_like(x) if xt.grad is None else xt.grad.numpy().copy()
+        var[name + "_dw"] = layer.w.grad.numpy().copy()
+        var[name + "_meta"] = np.array([n, I, O, B], dtype=np.int64)
+        var[name + "_fmeta"] = np.array([np.nan if per is None else per], dtype=np.float64)
+        var[name + "_keys"] = np.array(sorted(layer.state_dict().keys()))
+        var_poly.append(name)
+    var["conv_cases"] = np.array(var_conv)
+    var["poly_cases"] = np.array(var_poly)
+    np.savez_compressed(os.path.join(args.out, "variants.npz"), **var)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

@@ -295,3 +295,40 @@ def test_full_size_properties(kind, n, S, I, O, B):
     y64 = orc.pw_forward(xs[-64:].cpu().numpy(), w1.cpu().numpy(), n, S, 2.0, disc, None,
                          nodes=ops.lobatto_nodes(n).numpy())
     assert rel_err(y1[-64:].cpu().numpy(), y64) < TOL
+
+
+def test_variants_golden():
+    """discontinuous conv2d and Polynomial on the same kernels."""
+    g = load_golden("variants.npz")
+    for name in g["conv_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, stride, padding = (int(v) for v in g[name + "_meta"])
+        layer = hol.PiecewiseDiscontinuousPolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O,
+                                                                  kernel_size=K, device=DEV, stride=stride,
+                                                                  padding=padding)
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+        else:
+            assert not xt.grad.any()
+    for name in g["poly_cases"]:
+        name = str(name)
+        n, I, O, B = (int(v) for v in g[name + "_meta"])
+        per = float(g[name + "_fmeta"][0])
+        per = None if np.isnan(per) else per
+        layer = hol.Polynomial(n=n, in_features=I, out_features=O, periodicity=per, device=DEV)
+        with torch.no_grad():
+            layer.w.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.w.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name

@@ -138,3 +138,17 @@ def test_fake_tensor_shapes():
     wf = torch.empty(4, 27, 9, device="meta")
     yr = ops.pw_conv2d_rows(xi, wf, torch.empty(0, dtype=torch.uint8, device="meta"), 3, 4, 2.0, False, None, 3, 1, 0, 1)
     assert yr.shape == (2 * 6 * 6, 4)
+
+
+def test_variant_layers_host_side():
+    g = load_golden("variants.npz")
+    poly = hol.high_order_fc_layers("polynomial", n=3, in_features=5, out_features=4)
+    assert sorted(poly.state_dict().keys()) == [str(k) for k in g["poly_n3_keys"]]
+    assert poly.w.shape == (4, 5, 3)
+    with pytest.raises(ValueError):
+        hol.Polynomial(n=3, in_features=2, out_features=2, length=4.0)
+    torch.manual_seed(1234)
+    dc = hol.high_order_convolution_layers("discontinuous2d", n=3, segments=4, in_channels=2, out_channels=3,
+                                           kernel_size=3)
+    assert dc.conv.weight.shape == (3, 24, 3, 3)
+    assert np.array_equal(dc.conv.weight.detach().numpy(), g["init_dconv_w"])

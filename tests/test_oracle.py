@@ -169,3 +169,27 @@ def test_mlp_matches_reference():
         # HighOrderMLP registers first/last layer twice (checkpoint keys)
         keys = set(str(k) for k in g[name + "_keys"])
         assert {"input_layer.w", "output_layer.w", "model.0.w"} <= keys
+
+
+def test_variants_discontinuous_conv_and_polynomial():
+    """the discontinuous 2-d convolution and the single-segment Polynomial layer."""
+    g = load_golden("variants.npz")
+    nodes = load_golden("nodes.npz")
+    for name in g["conv_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, stride, padding = (int(v) for v in g[name + "_meta"])
+        y = orc.pw_conv2d_forward(g[name + "_x"], g[name + "_w"], n, S, 2.0, True, None, stride, padding, 1, 1.0,
+                                  nodes=nodes[f"X_{n}"])
+        assert rel_err(y, g[name + "_y"]) < TOL, name
+    for name in g["poly_cases"]:
+        name = str(name)
+        n, I, O, B = (int(v) for v in g[name + "_meta"])
+        per = float(g[name + "_fmeta"][0])
+        per = None if np.isnan(per) else per
+        x, w, gy = g[name + "_x"], g[name + "_w"], g[name + "_gy"]
+        y = orc.pw_forward(x, w, n, 1, 2.0, True, per, nodes=nodes[f"X_{n}"])
+        dx, dw = orc.pw_backward(gy, x, w, n, 1, 2.0, True, per, nodes=nodes[f"X_{n}"])
+        assert rel_err(y, g[name + "_y"]) < TOL, name
+        assert rel_err(dw, g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(dx, g[name + "_dx"]) < TOL, name
