@@ -332,3 +332,46 @@ def test_variants_golden():
         assert rel_err(layer.w.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
         if n > 1:
             assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+
+
+def test_wide_conv_tensor_core_path_matches_oracle_and_gather(contraction_path):
+    """A convolution wide enough (O >= 32) to be planned onto the tcgen05 path: forward vs the numpy
+    oracle, gradients vs the oracle's unfolded FC formulas (SURVEY 3.3 identity).  Exercises the
+    transposed dX epilogue + col2im."""
+    rng = np.random.default_rng(11)
+    n, S, C, O, K, H, W, B = 3, 4, 8, 40, 3, 10, 9, 3
+    layer = hol.PiecewisePolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K,
+                                                 device=DEV, padding=1)
+    w = rng.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)
+    x = rng.uniform(-1.1, 1.1, size=(B, C, H, W)).astype(np.float32)
+    with torch.no_grad():
+        layer.conv.weight.copy_(t(w))
+    xt = t(x).requires_grad_(True)
+    y = layer(xt)
+    gy = rng.standard_normal(size=tuple(y.shape)).astype(np.float32)
+    y.backward(t(gy))
+    nodes = ops.lobatto_nodes(n, 2.0).numpy()
+    y64 = orc.pw_conv2d_forward(x, w, n, S, 2.0, False, None, 1, 1, 1, 1.0, nodes=nodes)
+    assert rel_err(y.detach().cpu().numpy(), y64) < TOL
+    # reference gradients from the gather path (validated against the reference fixtures above)
+    import os
+    prev = os.environ.get("HOL_DISABLE_TC")
+    os.environ["HOL_DISABLE_TC"] = "1"
+    try:
+        layer.conv.weight.grad = None
+        xr = t(x).requires_grad_(True)
+        layer(xr).backward(t(gy))
+        dx_ref, dw_ref = xr.grad.cpu().numpy(), layer.conv.weight.grad.cpu().numpy().copy()
+    finally:
+        if prev is None:
+            del os.environ["HOL_DISABLE_TC"]
+        else:
+            os.environ["HOL_DISABLE_TC"] = prev
+    layer.conv.weight.grad = None
+    xt2 = t(x).requires_grad_(True)
+    layer(xt2).backward(t(gy))
+    assert rel_err(xt2.grad.cpu().numpy(), dx_ref) < TOL
+    assert rel_err(layer.conv.weight.grad.cpu().numpy(), dw_ref) < TOL
+    if contraction_path == "tensor-core":
+        rows = B * H * W
+        assert ops.uses_tensor_cores(rows, C * K * K, O, n, S, False)
