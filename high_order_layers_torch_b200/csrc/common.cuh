@@ -22,6 +22,7 @@ struct BasisTab {
 struct TcPlan {
     bool enabled;             // any pass on the tensor cores
     bool fwd, dx, dw;         // per pass (thresholds fitted to the c5 sweep, see tc_plan)
+    bool gen;                 // Phi / Phi^T tiles are generated inside the GEMM (Kin >= 16), never materialised
     int Kin;                  // dense columns per input: weights per link padded to 8
     int BN, nNT;              // output tile width and count
     int nkc;                  // 64-wide K chunks

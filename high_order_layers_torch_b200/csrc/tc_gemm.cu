@@ -56,18 +56,25 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     t.noc = (s.O + TC_BK - 1) / TC_BK;
     // dW: M tiles over the dense columns
     t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
-    // rows per launch: bound the Phi tiles to ~8 GiB
-    const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
-    int64_t rows = (int64_t)(8ll << 30) / bytes_per_row / 512 * 512;
-    if (rows < 512) return false;
-    if (rows > s.Bp) rows = s.Bp;
+    // The generator warps handle <= TC_GEN_PMAX (sample, input) pairs per thread and k-chunk, which
+    // holds for Kin >= 16; narrower links fall back to materialised Phi / Phi^T tiles.
+    t.gen = t.Kin >= 16;
+    // rows per launch: everything at once when the operand is generated in the kernel, else bound the
+    // Phi tiles to ~8 GiB
+    int64_t rows = s.Bp;
+    if (!t.gen) {
+        const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
+        rows = (int64_t)(8ll << 30) / bytes_per_row / 512 * 512;
+        if (rows < 512) return false;
+        if (rows > s.Bp) rows = s.Bp;
+    }
     rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
     t.rows_per_launch = rows;
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
-    size_t a = mtiles * t.nkc * 2 * TC_A_IMG;                                     // Phi
-    const size_t a_t = (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;                   // Phi^T
-    const size_t a_gy = mtiles * t.noc * 2 * TC_A_IMG;                            // gy
+    size_t a = t.gen ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                         // Phi
+    const size_t a_t = t.gen ? 0 : (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;       // Phi^T
+    const size_t a_gy = t.dx ? mtiles * t.noc * 2 * TC_A_IMG : 0;                 // gy
     if (a_t > a) a = a_t;
     if (a_gy > a) a = a_gy;
     size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);           // W
@@ -75,7 +82,7 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     const size_t b_wt = t.dx ? (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2) : 0;  // W^T
     if (b_gyt > bb) bb = b_gyt;
     if (b_wt > bb) bb = b_wt;
-    t.a_bytes = a;
+    t.a_bytes = a > 0 ? a : 256;
     t.b_bytes = bb;
     t.enabled = true;
     return true;
@@ -130,7 +137,7 @@ static int sm_count() {
     return n > 0 ? n : 148;
 }
 
-template <int EPI, int N>
+template <int EPI, int N, bool GEN>
 static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_t st) {
     const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
     int nst = (HOL_SMEM_BUDGET - 1024) / stage;
@@ -145,7 +152,7 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     p.group_m = ntiles_n >= 12 ? 12 : (148 + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
     if (p.group_m > mtiles) p.group_m = (int)mtiles;
     if (p.group_m < 1) p.group_m = 1;
-    auto kern = pw_tc_gemm_kernel<EPI, N>;
+    auto kern = pw_tc_gemm_kernel<EPI, N, GEN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t sms = sm_count();
@@ -157,7 +164,7 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
         g_prof.kind[g_prof.count] = EPI;
         cudaEventRecord(g_prof.ev[g_prof.count][0], st);
     }
-    kern<<<grid, 320, smem, st>>>(p);
+    kern<<<grid, GEN ? 384 : 320, smem, st>>>(p);
     if (prof) cudaEventRecord(g_prof.ev[g_prof.count++][1], st);
     return (int)cudaGetLastError();
 }
@@ -165,9 +172,10 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
 // kernels of ours per call (bench.py's gpu_launches): kind 0 forward, 1 dX, 2 dW (prep not included)
 int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
     const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
-    if (kind == 0) return 2 + 1 + nl * 2;  // absmax x2, pack_w, (expand, gemm) per batch chunk
-    if (kind == 1) return 2 + 1 + nl * 2;  // absmax x2, pack_wt, (pack_gy, gemm)
-    return 2 + nl * 3;                     // absmax x2, (expand_t, pack_gyt, gemm)
+    const int ex = t.gen ? 0 : 1;          // Phi / Phi^T expansion kernel (absent when generated in the GEMM)
+    if (kind == 0) return 2 + 1 + nl * (1 + ex);  // absmax x2, pack_w, ([expand,] gemm) per batch chunk
+    if (kind == 1) return 2 + 1 + nl * 2;         // absmax x2, pack_wt, (pack_gy, gemm)
+    return 2 + nl * (2 + ex);                     // absmax x2, ([expand_t,] pack_gyt, gemm)
 }
 
 #define DISPATCH_N(n, CALL)                       \
@@ -206,9 +214,12 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
         rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
         dim3 egrid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
+        rc = HOL_OK;
+        if (!t.gen) {
 #define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab), (int)cudaGetLastError())
-        DISPATCH_N(s.n, EXPAND)
+            DISPATCH_N(s.n, EXPAND)
 #undef EXPAND
+        }
         if (rc != HOL_OK) return rc;
         TcGemmParams p;
         fill_common(p, s, ws, t);
@@ -219,7 +230,8 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         p.n_valid = s.O;
         p.ld = s.O;
         p.nkc = t.nkc;
-        rc = launch_gemm<EPI_Y, 0>(p, rows / TC_BM, t.nNT, st);
+        rc = t.gen ? launch_gemm<EPI_Y, 0, true>(p, rows / TC_BM, t.nNT, st)
+                   : launch_gemm<EPI_Y, 0, false>(p, rows / TC_BM, t.nNT, st);
         if (rc != HOL_OK) return rc;
     }
     return HOL_OK;
@@ -236,9 +248,12 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
         const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
         dim3 egrid((unsigned)t.nMTw, (unsigned)nbc);
+        rc = HOL_OK;
+        if (!t.gen) {
 #define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
-        DISPATCH_N(s.n, EXPANDT)
+            DISPATCH_N(s.n, EXPANDT)
 #undef EXPANDT
+        }
         if (rc != HOL_OK) return rc;
         dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
         pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BN);
@@ -253,7 +268,7 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.n_valid = s.O;
         p.ld = 0;
         p.nkc = nbc;
-        rc = launch_gemm<EPI_DW, 0>(p, t.nMTw, t.nNT, st);
+        rc = t.gen ? launch_gemm<EPI_DW, 0, true>(p, t.nMTw, t.nNT, st) : launch_gemm<EPI_DW, 0, false>(p, t.nMTw, t.nNT, st);
         if (rc != HOL_OK) return rc;
     }
     return HOL_OK;
@@ -287,7 +302,7 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.ld = 0;
         p.nkc = t.noc;
         p.transposed = transposed;
-#define GEMM_DX(NN) launch_gemm<EPI_DX, NN>(p, rows / TC_BM, t.nNTx, st)
+#define GEMM_DX(NN) launch_gemm<EPI_DX, NN, false>(p, rows / TC_BM, t.nNTx, st)
         DISPATCH_N(s.n, GEMM_DX)
 #undef GEMM_DX
         if (rc != HOL_OK) return rc;

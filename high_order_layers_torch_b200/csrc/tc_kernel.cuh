@@ -1,5 +1,6 @@
 #pragma once
-// Persistent split-fp16 tcgen05 GEMM with three epilogues (design notes: tc_gemm.cu).
+// Persistent split-fp16 tcgen05 GEMM with three epilogues and in-kernel generation of the
+// segment-expanded operand (design notes: tc_gemm.cu).
 #include "tc_build.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -25,6 +26,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -39,13 +42,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+#define TC_GEN_THREADS 64  // two generator warps
+#define TC_GEN_PMAX 10     // (sample, input) pairs per generator thread and k-chunk (planner keeps it <= this)
+
 struct TcGemmParams {
-    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
+    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows (unused when the A operand is generated)
     const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
     float* out;                    // EPI_Y: y[rows][ld]; EPI_DW: dw[O][I][nb]; EPI_DX: dx[B][I] or dx_t[I][Bp]
     const TcScalars* sc;
-    const float* xl_t;             // EPI_DX
-    const uint16_t* seg_t;         // EPI_DX
+    const float* xl_t;             // EPI_DX epilogue and the generators
+    const uint16_t* seg_t;
     int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
     int64_t ntiles;                // m-tiles * n-tiles
     int64_t ntile_m;
@@ -69,12 +75,106 @@ __device__ __forceinline__ void tile_coords(const TcGemmParams& p, int64_t tile,
     nt = (int)(local / gsize);
 }
 
+// phi_j(t) for a run-time basis size n <= HOL_MAX_N (prefix/suffix products like lagrange_basis<N>;
+// fully unrolled to the maximum with guards, so everything stays in registers)
+__device__ __forceinline__ void lagrange_basis_rt(float t, const BasisTab& tab, int n, float (&phi)[HOL_MAX_N]) {
+    float d[HOL_MAX_N];
+#pragma unroll
+    for (int m = 0; m < HOL_MAX_N; ++m) d[m] = (m < n) ? t - tab.X[m] : 1.0f;
+    float run = 1.0f;
+#pragma unroll
+    for (int j = 0; j < HOL_MAX_N; ++j) {
+        phi[j] = run;
+        run *= d[j];
+    }
+    run = 1.0f;
+#pragma unroll
+    for (int j = HOL_MAX_N - 1; j >= 0; --j) {
+        phi[j] = (j < n) ? phi[j] * (run * tab.C[j]) : 0.0f;
+        run *= d[j];
+    }
+    if (n == 1) phi[0] = 1.0f;
+}
+
+// One generator thread's share of a stage: which (row/column, input) pairs it owns and their
+// coordinates, loaded one k-chunk ahead of use.
+struct GenPairs {
+    float xl[TC_GEN_PMAX];
+    uint32_t sg[TC_GEN_PMAX];
+};
+
+// EPI_Y  : A tile = Phi  [128 samples (rows)] x [64 dense columns k0..k0+63]; pair = (sample r, input i)
+// EPI_DW : A tile = Phi^T[128 dense columns R0..R0+127 (rows)] x [64 samples c0..c0+63]; pair = (sample e, input i)
+template <int EPI>
+__device__ __forceinline__ void gen_load(const TcGemmParams& p, int gt, int64_t mt, int kc, GenPairs& g) {
+    const int span = (EPI == EPI_Y) ? TC_BK : TC_BM;                 // dense columns covered by the tile
+    const int64_t d0 = (EPI == EPI_Y) ? (int64_t)kc * TC_BK : mt * TC_BM;
+    const int i_lo = (int)(d0 / p.Kin);
+    const int i_hi = (int)min((int64_t)p.I - 1, (d0 + span - 1) / p.Kin);
+    const int nsamp = (EPI == EPI_Y) ? TC_BM : TC_BK;
+    const int64_t b0 = (EPI == EPI_Y) ? p.row0 + mt * TC_BM : p.row0 + (int64_t)kc * TC_BK;
+    const int npairs = nsamp * (i_hi - i_lo + 1);
+#pragma unroll
+    for (int q = 0; q < TC_GEN_PMAX; ++q) {
+        const int pidx = gt + TC_GEN_THREADS * q;
+        g.sg[q] = HOL_SEG_INVALID;
+        g.xl[q] = 0.0f;
+        if (pidx < npairs) {
+            const int e = pidx % nsamp, i = i_lo + pidx / nsamp;
+            const int64_t b = b0 + e;
+            if (b < p.Bp) {
+                const int64_t idx = (int64_t)i * p.Bp + b;
+                g.sg[q] = p.seg_t[idx];
+                g.xl[q] = p.xl_t[idx];
+            }
+        }
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void gen_scatter(const TcGemmParams& p, int gt, int64_t mt, int kc, const GenPairs& g,
+                                            unsigned char* img_hi, float scale) {
+    const int span = (EPI == EPI_Y) ? TC_BK : TC_BM;
+    const int64_t d0 = (EPI == EPI_Y) ? (int64_t)kc * TC_BK : mt * TC_BM;
+    const int i_lo = (int)(d0 / p.Kin);
+    const int nsamp = (EPI == EPI_Y) ? TC_BM : TC_BK;
+    unsigned char* img_lo = img_hi + TC_A_IMG;
+#pragma unroll
+    for (int q = 0; q < TC_GEN_PMAX; ++q) {
+        const uint32_t sg = g.sg[q];
+        if (sg & HOL_SEG_INVALID) continue;
+        const int pidx = gt + TC_GEN_THREADS * q;
+        const int e = pidx % nsamp, i = i_lo + pidx / nsamp;
+        float phi[HOL_MAX_N];
+        lagrange_basis_rt(g.xl[q], p.tab, p.n_basis, phi);
+        const int64_t kbase = (int64_t)i * p.Kin + (int)(sg & HOL_SEG_MASK) * p.stride - d0;  // dense column - d0
+#pragma unroll
+        for (int j = 0; j < HOL_MAX_N; ++j) {
+            const int64_t dc = kbase + j;
+            if (j < p.n_basis && dc >= 0 && dc < span) {
+                const float a = phi[j] * scale;
+                const __half h = __float2half_rn(a);
+                const __half l = __float2half_rn(a - __half2float(h));
+                // image layout [k/8][row][8 x fp16]: EPI_Y row = sample, k = dense column; EPI_DW row = dense column, k = sample
+                const int row = (EPI == EPI_Y) ? e : (int)dc;
+                const int kk = (EPI == EPI_Y) ? (int)dc : e;
+                const int off = (kk >> 3) * (TC_BM * 16) + row * 16 + (kk & 7) * 2;
+                *reinterpret_cast<__half*>(img_hi + off) = h;
+                *reinterpret_cast<__half*>(img_lo + off) = l;
+            }
+        }
+    }
+}
+
 // Persistent: grid = min(#tiles, #SMs); every role walks the same tile sequence
-// tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring (full/empty) and the two TMEM accumulators (tmem_full/tmem_empty)
-// run continuously across tiles, so the epilogue of tile t overlaps the main loop of tile t+1.
-// N is the basis size for the EPI_DX gather (0 otherwise).
-template <int EPI, int N>
-__global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring (full/empty) and the two TMEM
+// accumulators (tmem_full/tmem_empty) run continuously across tiles, so the epilogue of tile t
+// overlaps the main loop of tile t+1.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue, (GEN) 10..11 = operand generators that
+// zero-fill the A half of a stage and scatter the n non-zero basis values of every (sample, input)
+// pair into it, so Phi / Phi^T never exist in global memory.  N = basis size for the EPI_DX gather.
+template <int EPI, int N, bool GEN>
+__global__ void __launch_bounds__(GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int BN = p.BN;
     const int B_IMG = BN * TC_BK * 2;
@@ -96,7 +196,7 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], GEN ? 2 : 1);  // TMA producer (+ the generators' elected thread)
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -128,9 +228,13 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
                 for (int kc = 0; kc < p.nkc; ++kc, ++it) {
                     const int st = it % nst;
                     mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
-                    mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
                     unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
-                    bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
+                    if (GEN) {
+                        mbar_expect_tx(&full[st], (uint32_t)(2 * B_IMG));
+                    } else {
+                        mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
+                        bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
+                    }
                     bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
                 }
             }
@@ -173,7 +277,52 @@ __global__ void __launch_bounds__(320, 1) pw_tc_gemm_kernel(const __grid_constan
                 }
             }
         }
-    } else {
+    } else if (GEN && warp >= 10) {
+        // operand generators: stay one k-chunk ahead with the coordinate loads
+        const int gt = threadIdx.x - 320;
+        const float scale = phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis);
+        int it = 0;
+        GenPairs cur, nxt;
+        int64_t tile = blockIdx.x;
+        int kc = 0;
+        int64_t mt = 0;
+        int nt = 0;
+        if (tile < p.ntiles) {
+            tile_coords(p, tile, mt, nt);
+            gen_load<EPI>(p, gt, mt, 0, cur);
+        }
+        while (tile < p.ntiles) {
+            // coordinates of the chunk after this one
+            int64_t ntile = tile, nmt = mt;
+            int nkc2 = kc + 1;
+            if (nkc2 == p.nkc) {
+                nkc2 = 0;
+                ntile = tile + gridDim.x;
+                if (ntile < p.ntiles) tile_coords(p, ntile, nmt, nt);
+            }
+            if (ntile < p.ntiles) gen_load<EPI>(p, gt, nmt, nkc2, nxt);
+
+            const int st = it % nst;
+            mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
+            unsigned char* img = stages + (size_t)st * STAGE_BYTES;
+            // zero both images (32 KB) cooperatively, then scatter the non-zeros
+            uint4* z = reinterpret_cast<uint4*>(img);
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 4
+            for (int e = gt; e < 2 * TC_A_IMG / 16; e += TC_GEN_THREADS) z[e] = zero;
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            gen_scatter<EPI>(p, gt, mt, kc, cur, img, scale);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            if (gt == 0) mbar_arrive(&full[st]);
+
+            cur = nxt;
+            tile = ntile;
+            mt = nmt;
+            kc = nkc2;
+            ++it;
+        }
+    } else if (warp >= 2 && warp < 10) {
         // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;

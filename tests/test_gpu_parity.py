@@ -121,6 +121,8 @@ FC_ORACLE_CASES = [
     ("cont", 8, 32, 33, 65, 300, None),      # mixed plan: tensor-core forward, gather dX and dW
     ("cont", 4, 32, 33, 65, 300, None),      # mixed plan: tensor-core forward + dX, gather dW
     ("disc", 3, 8, 200, 96, 700, None),      # all three passes on tensor cores, 2 batch tiles, ragged N tile
+    ("cont", 2, 4, 64, 48, 300, None),       # Kin = 8 < 16: tensor cores on materialised Phi / Phi^T tiles
+    ("disc", 1, 8, 40, 33, 200, None),       # n = 1 on the tensor-core path (dX == 0)
     ("disc", 10, 3, 7, 5, 2, None),
     ("cont", 1, 4, 9, 6, 40, None),
     ("disc", 1, 4, 9, 6, 40, None),
