@@ -56,9 +56,12 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     t.noc = (s.O + TC_BK - 1) / TC_BK;
     // dW: M tiles over the dense columns
     t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
-    // The generator warps handle <= TC_GEN_PMAX (sample, input) pairs per thread and k-chunk, which
-    // holds for Kin >= 16; narrower links fall back to materialised Phi / Phi^T tiles.
-    t.gen = t.Kin >= 16;
+    // In-kernel generation of the Phi / Phi^T tiles (two generator warps, <= TC_GEN_PMAX (sample, input)
+    // pairs per thread and k-chunk, Kin >= 16).  Measured on B200 at C2 it is generator-bound (forward
+    // GEMM 36.9 ms against 11.6 ms with materialised tiles, dW 31.7 against 11.8), so it is opt-in
+    // (HOL_TC_GEN=1) until the generator keeps up with the MMA warp; the default materialises the tiles.
+    const char* gen = getenv("HOL_TC_GEN");
+    t.gen = gen && gen[0] == '1' && t.Kin >= 16;
     // rows per launch: everything at once when the operand is generated in the kernel, else bound the
     // Phi tiles to ~8 GiB
     int64_t rows = s.Bp;

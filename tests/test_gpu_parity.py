@@ -16,11 +16,13 @@ from tests.conftest import load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tensor-core", "gather"], autouse=True)
+@pytest.fixture(params=["tensor-core", "gather", "tensor-core-gen"], autouse=True)
 def contraction_path(request, monkeypatch):
-    """Every parity test runs twice: with the tcgen05 segment-expanded path enabled (it is chosen
-    per shape, see tc_plan in csrc/tc.cu) and with it disabled (gather kernels everywhere)."""
-    monkeypatch.setenv("HOL_DISABLE_TC", "0" if request.param == "tensor-core" else "1")
+    """Every parity test runs three times: with the tcgen05 segment-expanded path enabled (it is
+    chosen per shape, see tc_plan in csrc/tc_gemm.cu), with it disabled (gather kernels everywhere),
+    and with the opt-in in-kernel generation of the Phi / Phi^T tiles (HOL_TC_GEN=1)."""
+    monkeypatch.setenv("HOL_DISABLE_TC", "1" if request.param == "gather" else "0")
+    monkeypatch.setenv("HOL_TC_GEN", "1" if request.param == "tensor-core-gen" else "0")
     return request.param
 
 
