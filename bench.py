@@ -135,6 +135,8 @@ def count_launches(layers, first_needs_dx=True, conv=False):
         want_dx = first_needs_dx or k > 0
         total += ops.launch_count(0, B, I, O, n, S, disc)
         total += ops.launch_count(1, B, I, O, n, S, disc, want_dx=want_dx, want_dw=True, prepared=True)
+        if conv:
+            total += 1  # the conv prep is two kernels (per-pixel prep, unfold)
         if conv and want_dx:
             total += 1  # col2im
     return total

@@ -45,8 +45,8 @@ int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, floa
     }
     // output tile: wide layers use 64 accumulators per thread; the packed rows of ONE input
     // (R x (OT+4) floats) must fit the shared-memory budget at least once
-    int OT = O >= 48 ? 64 : (O > 16 ? 32 : 16);
-    while (OT > 16 && (size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) OT >>= 1;
+    int OT = O >= 48 ? 64 : (O > 16 ? 32 : (O > 8 ? 16 : 8));
+    while (OT > 8 && (size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) OT >>= 1;
     if ((size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) return HOL_EUNSUPPORTED;
     s.OT = OT;
     s.OTP = OT + 4;
@@ -79,10 +79,12 @@ int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, floa
         }
     }
     tc_plan(s, s.tc);
+    dwd_plan(n, S, O, s.disc, B, I, s.dwd);
     return HOL_OK;
 }
 
-size_t carve(const PwShape& s, void* base, PwWorkspace& ws, bool conv) {
+size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels) {
+    const bool conv = conv_pixels >= 0;
     size_t off = 0;
     char* p = (char*)base;
     auto take = [&](size_t bytes) {
@@ -93,10 +95,15 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, bool conv) {
     ws.xl_t = (float*)take((size_t)s.I * s.Bp * sizeof(float));
     ws.seg_t = (uint16_t*)take((size_t)s.I * s.Bp * sizeof(uint16_t));
     ws.wk = (float*)take((size_t)s.nOT * s.I * s.R * s.OTP * sizeof(float));
-    ws.order = (uint32_t*)take((size_t)s.I * s.Bp * sizeof(uint32_t));
-    ws.offs = (uint32_t*)take((size_t)s.I * s.nchunks * (s.Seff + 1) * sizeof(uint32_t));
-    ws.dw_part = s.ksplit > 1 ? (float*)take((size_t)s.ksplit * s.O * s.I * s.nb * sizeof(float)) : nullptr;
+    // the bucket lists only exist for the bucketed dW kernel
+    const bool bucketed = !s.dwd.enabled;
+    ws.order = bucketed ? (uint32_t*)take((size_t)s.I * s.Bp * sizeof(uint32_t)) : nullptr;
+    ws.offs = bucketed ? (uint32_t*)take((size_t)s.I * s.nchunks * (s.Seff + 1) * sizeof(uint32_t)) : nullptr;
+    const int parts = bucketed ? s.ksplit : s.dwd.ksplit;
+    ws.dw_part = parts > 1 ? (float*)take((size_t)parts * s.O * s.I * s.nb * sizeof(float)) : nullptr;
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
+    ws.xl_img = conv ? (float*)take((size_t)conv_pixels * sizeof(float)) : nullptr;
+    ws.seg_img = conv ? (uint16_t*)take((size_t)conv_pixels * sizeof(uint16_t)) : nullptr;
     ws.tc_a = s.tc.enabled ? (void*)take(s.tc.a_bytes) : nullptr;
     ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
     ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
@@ -132,6 +139,8 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
     if (dw) {
         if (s.tc.dw) {
             HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, st));
+        } else if (s.dwd.enabled) {
+            HOL_TRY(launch_backward_dw_dense(s, ws, gy, dw, st));
         } else {
             HOL_TRY(launch_bucket_sort(s, ws, st));
             HOL_TRY(launch_backward_dw(s, ws, gy, dw, st));
@@ -161,7 +170,7 @@ size_t hol_pw_workspace_bytes(int64_t B, int32_t I, int32_t O, int32_t n, int32_
     PwShape s;
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
     PwWorkspace ws;
-    return carve(s, nullptr, ws, false);
+    return carve(s, nullptr, ws, -1);
 }
 
 int hol_pw_segment_index_i64(const float* x, int64_t* seg, int64_t count, int32_t S, float length, float periodicity,
@@ -180,7 +189,7 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
     if (B == 0) return HOL_OK;
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(launch_prep_fc(x, s, ws, st));
     if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w, y, st);
@@ -203,7 +212,7 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
         return HOL_OK;
     }
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_fc(x, s, ws, st));
     }
@@ -219,7 +228,7 @@ size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t
     PwShape s;
     if (make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
     PwWorkspace ws;
-    return carve(s, nullptr, ws, true);
+    return carve(s, nullptr, ws, Bimg * C * H * W);
 }
 
 int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
@@ -234,9 +243,9 @@ int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* no
     HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
     if (s.B == 0) return HOL_OK;
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+    HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
     HOL_TRY(launch_pack(w_fc, s, ws, st));
     return launch_forward(s, ws, y_rows, st);
@@ -262,9 +271,9 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
         return HOL_OK;
     }
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, true) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
-        HOL_TRY(launch_prep_conv(x, s, ws, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+        HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     }
     HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, st));
     if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
@@ -279,7 +288,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     PwShape s;
     HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, false) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev[7];
     for (int k = 0; k < 7; ++k)
@@ -301,9 +310,11 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
             rc = s.tc.dx ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, st) : launch_backward_dx(s, ws, gy, dx, 0, st);
     }
     mark(4);
-    if (rc == HOL_OK && !s.tc.dw) rc = launch_bucket_sort(s, ws, st);
+    if (rc == HOL_OK && !s.tc.dw && !s.dwd.enabled) rc = launch_bucket_sort(s, ws, st);
     mark(5);
-    if (rc == HOL_OK) rc = s.tc.dw ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st);
+    if (rc == HOL_OK)
+        rc = s.tc.dw ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st)
+                     : (s.dwd.enabled ? launch_backward_dw_dense(s, ws, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st));
     mark(6);
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == HOL_OK && e != cudaSuccess) rc = (int)e;
@@ -329,7 +340,9 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0) : 2);  // prep + (pack, forward)
     int c = prepared ? 0 : 1;  // prep
     if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1) : ((prepared && !s.tc.fwd) ? 1 : 2);
-    if (want_dw) c += s.tc.dw ? tc_launch_count(s, s.tc, 2) : (2 + (s.ksplit > 1 ? 1 : 0));
+    if (want_dw)
+        c += s.tc.dw ? tc_launch_count(s, s.tc, 2)
+                     : (s.dwd.enabled ? 1 + (s.dwd.ksplit > 1 ? 1 : 0) : 2 + (s.ksplit > 1 ? 1 : 0));
     return c;
 }
 

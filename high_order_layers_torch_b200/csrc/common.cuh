@@ -32,6 +32,13 @@ struct TcPlan {
     size_t a_bytes, b_bytes;  // Phi tile / W tile storage
 };
 
+// Plan of the dense-register dW kernel for narrow layers (dwd.cu).
+struct DwdPlan {
+    bool enabled;
+    int smax, oc, nog, ksplit;  // compiled segment bound, outputs per thread, output groups, sample ranges
+    int64_t rows_per_split;
+};
+
 // Problem description shared by host planning code and kernels.
 struct PwShape {
     int64_t B;    // rows (samples; im2col rows for conv)
@@ -53,6 +60,7 @@ struct PwShape {
     int periodic;
     BasisTab tab;
     TcPlan tc;
+    DwdPlan dwd;
 };
 
 struct PwWorkspace {
@@ -63,6 +71,8 @@ struct PwWorkspace {
     uint32_t* offs;   // [I][nchunks][Seff+1] bucket offsets into order
     float* dw_part;   // [ksplit][O][I][nb] partial weight gradients (ksplit > 1 only)
     float* dx_rows;   // conv only: [rows][I] unfolded input gradient
+    float* xl_img;    // conv only: [Bimg][C][H][W] local coordinate per pixel (before the unfold)
+    uint16_t* seg_img;  // conv only: segment + flags per pixel
     void* tc_a;       // tensor-core path: Phi tiles (fp16 hi/lo shared-memory images)
     void* tc_b;       // tensor-core path: W tiles
     void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|)

@@ -203,9 +203,11 @@ int launch_backward_dw(const PwShape& s, const PwWorkspace& ws, const float* gy,
         case 10: rc = launch_dw_n<10>(s, ws, gy, out, st); break;
     }
     if (rc != HOL_OK) return rc;
-    if (s.ksplit > 1) {
-        pw_dw_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(ws.dw_part, dw, count, s.ksplit);
-        return (int)cudaGetLastError();
-    }
+    if (s.ksplit > 1) return launch_dw_reduce(ws.dw_part, dw, count, s.ksplit, st);
     return HOL_OK;
+}
+
+int launch_dw_reduce(const float* part, float* dw, int64_t count, int ksplit, cudaStream_t st) {
+    pw_dw_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(part, dw, count, ksplit);
+    return (int)cudaGetLastError();
 }

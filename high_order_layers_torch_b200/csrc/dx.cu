@@ -72,12 +72,13 @@ __global__ void __launch_bounds__(256, 1) pw_dx_kernel(const __grid_constant__ D
     for (int c = 0; c < p.nOT; ++c) {
         mbar_wait(&bars[c % p.nst], (uint32_t)((c / p.nst) & 1));
         const float* slab = slab0 + (size_t)(c % p.nst) * p.stage_floats;
+        constexpr int QW = OT < 16 ? OT : 16;  // output columns per register block
 #pragma unroll 1
-        for (int qb = 0; qb < OT / 16; ++qb) {
-            float4 g[4];
+        for (int qb = 0; qb < OT / QW; ++qb) {
+            float4 g[QW / 4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int o = c * OT + qb * 16 + 4 * t;
+            for (int t = 0; t < QW / 4; ++t) {
+                const int o = c * OT + qb * QW + 4 * t;
                 g[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (rowok) {
                     if (vec && o + 3 < p.O) {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256, 1) pw_dx_kernel(const __grid_constant__ D
                     }
                 }
             }
-            const float* slabq = slab + qb * 16;
+            const float* slabq = slab + qb * QW;
 #pragma unroll
             for (int k = 0; k < IT; ++k) {
                 if (k >= ni) break;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256, 1) pw_dx_kernel(const __grid_constant__ D
                 for (int j = 0; j < N; ++j) {
                     const float4* wp = reinterpret_cast<const float4*>(slabq + rowoff[k] + p.jrow[j]);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
+                    for (int t = 0; t < QW / 4; ++t) {
                         const float4 w = wp[t];
                         acc[k][j] = ffma2v(make_float2(g[t].x, g[t].y), make_float2(w.x, w.y), acc[k][j]);
                         acc[k][j] = ffma2v(make_float2(g[t].z, g[t].w), make_float2(w.z, w.w), acc[k][j]);
@@ -194,6 +195,7 @@ static int launch_dx_n(const PwShape& s, const PwWorkspace& ws, const float* gy,
         case 64: return launch_dx_t<N, 64>(s, ws, gy, dx, transposed, st);
         case 32: return launch_dx_t<N, 32>(s, ws, gy, dx, transposed, st);
         case 16: return launch_dx_t<N, 16>(s, ws, gy, dx, transposed, st);
+        case 8: return launch_dx_t<N, 8>(s, ws, gy, dx, transposed, st);
     }
     return HOL_EUNSUPPORTED;
 }

@@ -191,6 +191,7 @@ static int launch_fwd_n(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
         case 64: return launch_fwd_t<N, 64>(s, ws, y, st);
         case 32: return launch_fwd_t<N, 32>(s, ws, y, st);
         case 16: return launch_fwd_t<N, 16>(s, ws, y, st);
+        case 8: return launch_fwd_t<N, 8>(s, ws, y, st);
     }
     return HOL_EUNSUPPORTED;
 }

@@ -5,8 +5,8 @@
 
 int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwShape& s, cudaStream_t st);
 int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st);
-int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int C, int H, int W, int K, int stride,
-                     int padding, int dilation, int Ho, int Wo, cudaStream_t st);
+int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, int C, int H, int W, int K,
+                     int stride, int padding, int dilation, int Ho, int Wo, cudaStream_t st);
 int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, int C, int H, int W, int K, int stride,
                   int padding, int dilation, int Ho, int Wo, cudaStream_t st);
 int launch_pack(const float* w, const PwShape& s, const PwWorkspace& ws, cudaStream_t st);
@@ -18,6 +18,11 @@ int launch_forward(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream
 int launch_backward_dx(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int dx_transposed,
                        cudaStream_t st);
 int launch_backward_dw(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dw, cudaStream_t st);
+int launch_dw_reduce(const float* part, float* dw, int64_t count, int ksplit, cudaStream_t st);
+
+// dense-register dW for narrow layers (dwd.cu)
+bool dwd_plan(int n, int S, int O, int disc, int64_t B, int I, DwdPlan& d);
+int launch_backward_dw_dense(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dw, cudaStream_t st);
 
 // tensor-core forward (tc.cu)
 bool tc_plan(const PwShape& s, TcPlan& t);

@@ -105,26 +105,53 @@ struct ConvGeom {
     int C, H, W, K, stride, padding, dilation, Ho, Wo;
 };
 
-__global__ void __launch_bounds__(256) pw_prep_conv_kernel(const float* __restrict__ x, float* __restrict__ xl_t,
-                                                           uint16_t* __restrict__ seg_t, int64_t rows, int64_t Bp,
-                                                           ConvGeom g, PrepConst c) {
+// Stage 1: the elementwise recipe once per pixel, image layout kept (NCHW).
+__global__ void __launch_bounds__(256) pw_prep_image_kernel(const float* __restrict__ x, float* __restrict__ xl_img,
+                                                            uint16_t* __restrict__ seg_img, int64_t count, PrepConst c) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    float xl;
+    uint32_t sg;
+    prep_elem(x[e], c, xl, sg);
+    xl_img[e] = xl;
+    seg_img[e] = (uint16_t)sg;
+}
+
+// Stage 2: unfold the prepared image into xl_t / seg_t [I][Bp].  One thread = one row (b, ho, wo),
+// decoded once; the loop over the taps writes one coalesced line per tap and re-reads the
+// window from L1.
+__global__ void __launch_bounds__(256) pw_unfold_kernel(const float* __restrict__ xl_img, const uint16_t* __restrict__ seg_img,
+                                                        float* __restrict__ xl_t, uint16_t* __restrict__ seg_t, int64_t rows,
+                                                        int64_t Bp, ConvGeom g) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
     if (row >= Bp) return;
-    float xl = 0.0f;
-    uint32_t sg = HOL_SEG_INVALID;
-    if (row < rows) {
-        const int kw = i % g.K, kh = (i / g.K) % g.K, ch = i / (g.K * g.K);
-        const int wo = (int)(row % g.Wo);
-        const int64_t t = row / g.Wo;
-        const int ho = (int)(t % g.Ho);
-        const int64_t b = t / g.Ho;
-        const int h = ho * g.stride - g.padding + kh * g.dilation;
-        const int w = wo * g.stride - g.padding + kw * g.dilation;
-        if (h >= 0 && h < g.H && w >= 0 && w < g.W) prep_elem(x[((b * g.C + ch) * g.H + h) * g.W + w], c, xl, sg);
+    const bool live = row < rows;
+    const int wo = (int)(row % g.Wo);
+    const int64_t t = row / g.Wo;
+    const int ho = (int)(t % g.Ho);
+    const int64_t b = t / g.Ho;
+    const int h0 = ho * g.stride - g.padding, w0 = wo * g.stride - g.padding;
+    int i = 0;
+    for (int ch = 0; ch < g.C; ++ch) {
+        const int64_t plane = (b * g.C + ch) * (int64_t)g.H * g.W;
+        for (int kh = 0; kh < g.K; ++kh) {
+            const int h = h0 + kh * g.dilation;
+            const bool hok = live && h >= 0 && h < g.H;
+#pragma unroll 5
+            for (int kw = 0; kw < g.K; ++kw, ++i) {
+                const int w = w0 + kw * g.dilation;
+                float xl = 0.0f;
+                uint16_t sg = (uint16_t)HOL_SEG_INVALID;
+                if (hok && w >= 0 && w < g.W) {
+                    const int64_t src = plane + (int64_t)h * g.W + w;
+                    xl = __ldg(xl_img + src);
+                    sg = __ldg(seg_img + src);
+                }
+                xl_t[(int64_t)i * Bp + row] = xl;
+                seg_t[(int64_t)i * Bp + row] = sg;
+            }
+        }
     }
-    xl_t[(int64_t)i * Bp + row] = xl;
-    seg_t[(int64_t)i * Bp + row] = (uint16_t)sg;
 }
 
 // dx[b,c,h,w] = sum over the (kh,kw) taps that read this pixel of dx_t[(c,kh,kw)][row].
@@ -277,11 +304,17 @@ int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cuda
     return (int)cudaGetLastError();
 }
 
-int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int C, int H, int W, int K, int stride,
-                     int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
+int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, int C, int H, int W, int K,
+                     int stride, int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
     ConvGeom g{C, H, W, K, stride, padding, dilation, Ho, Wo};
-    dim3 grid((unsigned)((s.Bp + 255) / 256), (unsigned)s.I);
-    pw_prep_conv_kernel<<<grid, 256, 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, g, make_prep_const(s));
+    const int64_t count = Bimg * C * H * W;
+    if (count > 0) {
+        pw_prep_image_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, ws.xl_img, ws.seg_img, count,
+                                                                              make_prep_const(s));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    pw_unfold_kernel<<<(unsigned)((s.Bp + 255) / 256), 256, 0, st>>>(ws.xl_img, ws.seg_img, ws.xl_t, ws.seg_t, s.B, s.Bp, g);
     return (int)cudaGetLastError();
 }
 

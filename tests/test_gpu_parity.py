@@ -22,6 +22,8 @@ def contraction_path(request, monkeypatch):
     chosen per shape, see tc_plan in csrc/tc_gemm.cu), with it disabled (gather kernels everywhere),
     and with the opt-in in-kernel generation of the Phi / Phi^T tiles (HOL_TC_GEN=1)."""
     monkeypatch.setenv("HOL_DISABLE_TC", "1" if request.param == "gather" else "0")
+    # "gather" also switches the dense-register dW of narrow layers off (bucketed dW everywhere)
+    monkeypatch.setenv("HOL_DISABLE_DWD", "1" if request.param == "gather" else "0")
     monkeypatch.setenv("HOL_TC_GEN", "1" if request.param == "tensor-core-gen" else "0")
     return request.param
 
@@ -129,6 +131,14 @@ FC_ORACLE_CASES = [
     ("cont", 1, 4, 9, 6, 40, None),
     ("disc", 1, 4, 9, 6, 40, None),
     ("cont", 2, 1, 3, 2, 1, None),
+    # narrow layers: dense-register dW (dwd.cu) with several sample ranges, every compiled segment bound
+    ("cont", 3, 4, 75, 6, 5000, None),       # config-4 conv1 as rows (OT = 8 tiles, float2 gy loads)
+    ("cont", 3, 4, 150, 16, 4100, None),     # config-4 conv2 as rows (two output groups)
+    ("disc", 5, 3, 9, 10, 6000, None),       # S = 3 under the compiled bound 4, 4 outputs per thread
+    ("cont", 5, 7, 6, 3, 4097, None),        # S = 7 under the compiled bound 8, odd O (scalar gy loads)
+    ("disc", 2, 8, 5, 31, 2100, 2.0),        # widest narrow layer, periodic fold
+    ("cont", 1, 8, 7, 12, 4096, None),
+    ("disc", 4, 1, 3, 1, 2500, None),
 ]
 
 

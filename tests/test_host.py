@@ -42,7 +42,12 @@ def test_workspace_queries_need_no_gpu():
     assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 32, 32, 6, 5, 1, 0, 1, 3, 4, 0) > 0
     assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 4, 4, 6, 5, 1, 0, 1, 3, 4, 0) == 0   # kernel larger than image
     assert lib.hol_pw_launch_count(0, 64, 8, 4, 3, 2, 0, 1, 1, 0) == 3       # prep, pack, forward (gather path)
-    assert lib.hol_pw_launch_count(1, 64, 8, 4, 3, 2, 0, 1, 1, 1) == 3       # dX, bucket sort, dW
+    assert lib.hol_pw_launch_count(1, 64, 8, 4, 3, 2, 0, 1, 1, 1) == 2       # dX, dense-register dW (narrow layer)
+    os.environ["HOL_DISABLE_DWD"] = "1"
+    try:
+        assert lib.hol_pw_launch_count(1, 64, 8, 4, 3, 2, 0, 1, 1, 1) == 3   # dX, bucket sort, bucketed dW
+    finally:
+        del os.environ["HOL_DISABLE_DWD"]
     assert lib.hol_pw_launch_count(0, 65536, 1024, 1024, 5, 8, 1, 1, 1, 0) > 3   # tensor-core path
 
 
