@@ -445,6 +445,7 @@ def run_ours(args):
 
     roof = None
     cpu = None
+    ref_cuda = None
     if rank == 0:
         try:
             roof = measure_roofline(torch, wl, ms_per_step)
@@ -452,6 +453,8 @@ def run_ours(args):
             roof = {"error": f"out of memory in the diagnostic pass: {str(e)[:80]}"}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(cfg, budget_s=args.cpu_budget)
+        if world == 1 and not args.no_ref_cuda:
+            ref_cuda = ref_torch_cuda(cfg, args.config)
     if world > 1:
         dist.barrier()
 
@@ -475,6 +478,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "ref_torch_cuda": ref_cuda,
             "step_algorithmic": {"bytes": wl["bytes"], "flops": wl["flops"],
                                  "hbm_frac_of_measured": wl["bytes"] / (ms_per_step / 1e3) / (peaks["hbm_gbs"] * 1e9),
                                  "fp32_frac_of_74.4TF": wl["flops"] / (ms_per_step / 1e3) / (FP32_PEAK_TFLOPS * 1e12),
@@ -586,14 +590,24 @@ def _reference_modules():
         return None
 
 
-def cpu_step_factory(cfg, chunk):
-    """One bounded CPU step (fwd+bwd on `chunk` samples) of the workload; returns (fn, kind, samples)."""
+def cpu_step_factory(cfg, chunk, device="cpu"):
+    """One bounded step (fwd+bwd on `chunk` samples) of the workload through the UNMODIFIED reference
+    modules (or the numpy oracle port when baseline/_ref is absent); returns (fn, kind, samples).
+    device="cuda" runs the reference's own torch-CUDA path: construction and calls happen under
+    `with torch.device("cuda")` (the reference builds its node tables on the default device)."""
     import numpy as np
     import torch
 
     torch.set_num_threads(os.cpu_count() or 1)
     R = _reference_modules()
     rng = np.random.default_rng(0)
+    if device != "cpu":
+        if R is None:
+            raise RuntimeError("the torch-CUDA reference arm needs baseline/_ref")
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        inner, _, _ = _on_device(cfg, chunk, device, R, rng)
+        return inner, "reference", chunk
     if cfg["kind"] == "layer":
         n, S, I, O = cfg["n"], cfg["S"], cfg["I"], cfg["O"]
         disc = cfg["layer"] == "discontinuous"
@@ -668,7 +682,128 @@ def cpu_step_factory(cfg, chunk):
     raise KeyError(cfg["kind"])
 
 
+def _on_device(cfg, chunk, device, R, rng):
+    """The reference modules of the workload on `device`; returns (step fn, module, tensors)."""
+    import numpy as np
+    import torch
+
+    dev = torch.device(device)
+    with dev:
+        if cfg["kind"] == "layer":
+            n, S, I, O = cfg["n"], cfg["S"], cfg["I"], cfg["O"]
+            layer = R.layers.high_order_fc_layers(cfg["layer"], n=n, in_features=I, out_features=O, segments=S)
+            with torch.no_grad():
+                layer.w.uniform_(-1, 1)
+            xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, I)).astype(np.float32)).to(dev).requires_grad_(True)
+            gt = torch.from_numpy(rng.standard_normal(size=(chunk, O)).astype(np.float32)).to(dev)
+
+            def fn():
+                with dev:
+                    layer.w.grad = None
+                    xt.grad = None
+                    y = layer(xt)
+                    y.backward(gt)
+                    return y
+            return fn, layer, dict(x=xt, gy=gt)
+        if cfg["kind"] == "mlp":
+            n, S, wd = cfg["n"], cfg["S"], cfg["widths"]
+            net = R.networks.HighOrderMLP(layer_type=cfg["layer"], n=n, in_width=wd[0], out_width=wd[-1],
+                                          hidden_layers=len(wd) - 3, hidden_width=wd[1], in_segments=S, out_segments=S,
+                                          hidden_segments=S, normalization=R.layers.MaxAbsNormalization).to(dev)
+            xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, wd[0])).astype(np.float32)).to(dev)
+            classify = wd[-1] > 1
+            tgt = torch.randint(0, wd[-1], (chunk,), device=dev) if classify else torch.randn(chunk, wd[-1], device=dev)
+            lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
+
+            def fn():
+                with dev:
+                    net.zero_grad(set_to_none=True)
+                    loss = lossf(net(xt), tgt)
+                    loss.backward()
+                    return loss
+            return fn, net, dict(x=xt, t=tgt)
+        if cfg["kind"] == "conv":
+            n, S = cfg["n"], cfg["S"]
+            nn = torch.nn
+            c1 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=3, out_channels=6,
+                                                        kernel_size=5)
+            c2 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=6,
+                                                        out_channels=16, kernel_size=5)
+            pool, fc = nn.MaxPool2d(2, 2), nn.Linear(400, 100)
+            mods = nn.ModuleList([c1, c2, fc]).to(dev)
+            xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, 3, 32, 32)).astype(np.float32)).to(dev)
+            tgt = torch.randint(0, 100, (chunk,), device=dev)
+
+            def fn():
+                with dev:
+                    mods.zero_grad(set_to_none=True)
+                    loss = torch.nn.functional.cross_entropy(fc(pool(c2(pool(c1(xt)))).flatten(1)), tgt)
+                    loss.backward()
+                    return loss
+            return fn, mods, dict(x=xt, t=tgt)
+    raise KeyError(cfg["kind"])
+
+
+def ref_torch_cuda(cfg, key, budget_s=8.0):
+    """The reference's own torch-CUDA path on this GPU (north_star: reported next to ours): the
+    unmodified modules under `with torch.device("cuda")`, fp32, TF32 off, micro-batched so that its
+    [B, I, O, n] gathered tensors fit, CUDA-event timed.  For single-layer workloads the same
+    micro-batch is also pushed through our layer with the reference's weights (parity in the run)."""
+    import numpy as np
+    import torch
+
+    R = _reference_modules()
+    if R is None:
+        return {"unavailable": "baseline/_ref not installed"}
+    chunk = GPU_REF_CHUNK[key]
+    rng = np.random.default_rng(0)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        fn, mod, tens = _on_device(cfg, chunk, "cuda", R, rng)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, t0 = 0, time.perf_counter()
+        ev0.record()
+        while True:
+            fn()
+            reps += 1
+            if reps % 4 == 0:
+                torch.cuda.synchronize()
+            if time.perf_counter() - t0 > budget_s or reps >= 200:
+                break
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        out = {"value": chunk * reps / (ms / 1e3), "unit": "samples/s", "micro_batch": chunk, "steps": reps,
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+               "sample": f"{reps} micro-batches of {chunk} samples (fwd+bwd, fp32, TF32 off) through the unmodified "
+                         f"reference modules under torch.device('cuda'), CUDA events, {ms / 1e3:.1f} s"}
+        if cfg["kind"] == "layer":
+            import high_order_layers_torch_b200 as hol
+            ours = hol.high_order_fc_layers(cfg["layer"], n=cfg["n"], in_features=cfg["I"], out_features=cfg["O"],
+                                            segments=cfg["S"], device="cuda")
+            with torch.no_grad():
+                ours.w.copy_(mod.w)
+            y_ref = fn()
+            x2 = tens["x"].detach().clone().requires_grad_(True)
+            y = ours(x2)
+            y.backward(tens["gy"])
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+            out["parity_rel_err"] = {"y": rel(y, y_ref), "dx": rel(x2.grad, tens["x"].grad),
+                                     "dw": rel(ours.w.grad, mod.w.grad)}
+        return out
+    except Exception as e:  # a reported baseline, never a reason to lose the bench line
+        torch.cuda.synchronize()
+        return {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    finally:
+        torch.cuda.empty_cache()
+
+
 CPU_CHUNK = {"c2": 64, "c5": 8, "c3": 256, "c1": 1024, "c4": 128}
+GPU_REF_CHUNK = {"c2": 256, "c5": 16, "c3": 2048, "c1": 1024, "c4": 1024}
 
 
 def cpu_baseline(cfg, budget_s=15.0, key=None):
@@ -745,6 +880,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's torch-CUDA leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the step in a CUDA graph (auto: MLP / conv workloads only)")
     args = ap.parse_args()

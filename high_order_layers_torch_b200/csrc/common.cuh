@@ -35,8 +35,11 @@ struct TcPlan {
 // Plan of the dense-register dW kernel for narrow layers (dwd.cu).
 struct DwdPlan {
     bool enabled;
-    int smax, oc, nog, ksplit;  // compiled segment bound, outputs per thread, output groups, sample ranges
-    int64_t rows_per_split;
+    int smax, oc, nog;   // compiled segment bound, outputs per thread, output groups
+    int R, P;            // samples per staged gy range and its shared-memory pitch (floats)
+    int G, nig;          // inputs per CTA, input groups
+    int nranges, nkg;    // sample ranges, range groups (= partial results)
+    int ksplit;          // == nkg: partials summed by pw_dw_reduce_kernel when > 1
 };
 
 // Problem description shared by host planning code and kernels.

@@ -7,10 +7,15 @@
 // into the nb coefficients with S predicated multiplies, and the block is updated with nb*OC/2
 // packed FMAs per (sample, input).  That spends nb/n times the useful flops -- on the FMA pipe,
 // which is idle in the bucketed kernel (dw.cu) for such layers: there a warp gathers one
-// 24-64 byte gy row per sample for n*4 FMAs.  One CTA = (input, output group, sample range);
-// the partial sums are combined in a fixed order (warp butterfly, 8 warps in order, then the
-// sample ranges in order by pw_dw_reduce_kernel), so the result is bit-reproducible and weights
-// no sample touched are exact zeros.
+// 24-64 byte gy row per sample for n*4 FMAs.
+//
+// One CTA = (output group, input group, sample-range group).  The gy columns of a sample range
+// are staged ONCE in shared memory and reused for every input of the group (the first version
+// re-read gy from L2 per input and was L2-bandwidth bound); per input the CTA then streams only
+// xl_t / seg_t (6 bytes per (sample, input)).  Partial sums are combined in a fixed order
+// (transposing lane butterfly, 8 warps in order, sample ranges in order: single writer per
+// partial, then pw_dw_reduce_kernel), so the result is bit-reproducible and weights no sample
+// touched are exact zeros.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -19,9 +24,9 @@ struct DwdParams {
     const float* xl_t;
     const uint16_t* seg_t;
     const float* gy;
-    float* out;  // dw, or the partial buffer [ksplit][O][I][nb]
-    int64_t B, Bp, rows_per_split, part_stride;
-    int I, O, nb, nog;
+    float* out;  // dw, or the partial buffer [nkg][O][I][nb]
+    int64_t B, Bp, part_stride;
+    int I, O, nb, nog, R, P, G, nranges, nkg;
     BasisTab tab;
 };
 
@@ -30,99 +35,112 @@ struct DwdShape {
     static constexpr int NB = DISC ? N * SMAX : (N - 1) * SMAX + 1;
 };
 
+// One step of the transposing butterfly: CNT values per lane -> CNT/2, lanes whose `off` bit is
+// set keep the upper half of the index range.
+template <int CNT>
+__device__ __forceinline__ void dwd_fold(float* v, int lane, int off) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < CNT / 2; ++k) {
+        const float send = up ? v[k] : v[k + CNT / 2];
+        const float keep = up ? v[k + CNT / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+}
+
 template <int N, int SMAX, int OC, bool DISC>
 __global__ void __launch_bounds__(256) pw_dw_dense_kernel(const __grid_constant__ DwdParams p) {
     constexpr int NB = DwdShape<N, SMAX, DISC>::NB;
     constexpr int ST = DISC ? N : N - 1;
-    __shared__ float red[8][NB * OC];
+    constexpr int NV = NB * OC, NVP = (NV + 31) / 32 * 32;
+    extern __shared__ __align__(16) float gys[];  // [R][P] staged gy columns of this output group
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i = blockIdx.x % p.I;
-    const int og = blockIdx.x / p.I;
-    const int ks = blockIdx.y;
+    const int og = blockIdx.x % p.nog, ig = blockIdx.x / p.nog;
+    const int kg = blockIdx.y;
     const int o0 = og * OC;
-    const int64_t r_lo = (int64_t)ks * p.rows_per_split;
-    const int64_t r_hi = min(p.B, r_lo + p.rows_per_split);
-    const float* xl = p.xl_t + (int64_t)i * p.Bp;
-    const uint16_t* sgp = p.seg_t + (int64_t)i * p.Bp;
-    const int vecw = (p.O % 4 == 0) ? 4 : ((p.O % 2 == 0) ? 2 : 1);  // o0 is a multiple of 4
+    const int i_lo = ig * p.G, i_hi = min(p.I, i_lo + p.G);
+    const int P = p.P;
+    float* out = p.out + (int64_t)kg * p.part_stride;
+    // after the butterfly this lane holds the sums of the NVP/32 consecutive entries starting here
+    const int base = ((lane & 16) ? NVP / 2 : 0) + ((lane & 8) ? NVP / 4 : 0) + ((lane & 4) ? NVP / 8 : 0) +
+                     ((lane & 2) ? NVP / 16 : 0) + ((lane & 1) ? NVP / 32 : 0);
+    bool first = true;
 
-    float2 acc[NB][OC / 2];
+    for (int range = kg; range < p.nranges; range += p.nkg) {
+        const int64_t r_lo = (int64_t)range * p.R;
+        const int nrows = (int)min((int64_t)p.R, p.B - r_lo);
+        __syncthreads();
+        for (int idx = tid; idx < nrows * OC; idx += 256) {
+            const int r = idx / OC, c = idx % OC;
+            gys[r * P + c] = (o0 + c < p.O) ? __ldg(p.gy + (r_lo + r) * p.O + o0 + c) : 0.0f;
+        }
+        __syncthreads();
+        // every warp owns whole inputs: its lanes sweep the staged range, no cross-warp reduction
+        for (int i = i_lo + warp; i < i_hi; i += 8) {
+            const float* xl = p.xl_t + (int64_t)i * p.Bp + r_lo;
+            const uint16_t* sgp = p.seg_t + (int64_t)i * p.Bp + r_lo;
+            float2 acc[NB][OC / 2];
 #pragma unroll
-    for (int v = 0; v < NB; ++v)
+            for (int v = 0; v < NB; ++v)
 #pragma unroll
-        for (int q = 0; q < OC / 2; ++q) acc[v][q] = make_float2(0.0f, 0.0f);
+                for (int q = 0; q < OC / 2; ++q) acc[v][q] = make_float2(0.0f, 0.0f);
 
-#pragma unroll 2
-    for (int64_t b = r_lo + tid; b < r_hi; b += 256) {
-        const float t = __ldg(xl + b);
-        const uint32_t sg = __ldg(sgp + b);
-        float g[OC];
-        const float* row = p.gy + b * p.O + o0;
-        if (vecw == 4) {
+#pragma unroll 4
+            for (int rr = lane; rr < nrows; rr += 32) {
+                const float t = __ldg(xl + rr);
+                const uint32_t sg = __ldg(sgp + rr);
+                float2 g[OC / 2];
 #pragma unroll
-            for (int q = 0; q < OC / 4; ++q) {
-                float4 v4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (o0 + 4 * q < p.O) v4 = __ldg(reinterpret_cast<const float4*>(row + 4 * q));
-                g[4 * q] = v4.x, g[4 * q + 1] = v4.y, g[4 * q + 2] = v4.z, g[4 * q + 3] = v4.w;
+                for (int q = 0; q < OC / 2; ++q) g[q] = *reinterpret_cast<const float2*>(gys + rr * P + 2 * q);
+                float phi[N];
+                lagrange_basis<N>(t, p.tab, phi);
+                const int s = (sg & HOL_SEG_INVALID) ? -1 : (int)(sg & HOL_SEG_MASK);
+                float coef[NB];
+#pragma unroll
+                for (int v = 0; v < NB; ++v) coef[v] = 0.0f;
+#pragma unroll
+                for (int ss = 0; ss < SMAX; ++ss) {
+                    // continuous n == 1 has one weight per link whatever the segment
+                    const float m = ((!DISC && N == 1) ? (s >= 0 && ss == 0) : (s == ss)) ? 1.0f : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const int v = (!DISC && N == 1) ? 0 : ss * ST + j;
+                        if (v < NB) coef[v] = fmaf(m, phi[j], coef[v]);  // shared end nodes: at most one term is non-zero
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < NB; ++v)
+#pragma unroll
+                    for (int q = 0; q < OC / 2; ++q) acc[v][q] = ffma2(coef[v], g[q], acc[v][q]);
             }
-        } else if (vecw == 2) {
-#pragma unroll
-            for (int q = 0; q < OC / 2; ++q) {
-                float2 v2 = make_float2(0.0f, 0.0f);
-                if (o0 + 2 * q < p.O) v2 = __ldg(reinterpret_cast<const float2*>(row + 2 * q));
-                g[2 * q] = v2.x, g[2 * q + 1] = v2.y;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < OC; ++q) g[q] = (o0 + q < p.O) ? __ldg(row + q) : 0.0f;
-        }
-        float phi[N];
-        lagrange_basis<N>(t, p.tab, phi);
-        const int s = (sg & HOL_SEG_INVALID) ? -1 : (int)(sg & HOL_SEG_MASK);
-        float coef[NB];
-#pragma unroll
-        for (int v = 0; v < NB; ++v) coef[v] = 0.0f;
-#pragma unroll
-        for (int ss = 0; ss < SMAX; ++ss) {
-            // continuous n == 1 has one weight per link whatever the segment
-            const float m = ((!DISC && N == 1) ? (s >= 0 && ss == 0) : (s == ss)) ? 1.0f : 0.0f;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const int v = (!DISC && N == 1) ? 0 : ss * ST + j;
-                if (v < NB) coef[v] = fmaf(m, phi[j], coef[v]);  // end nodes shared by two segments: at most one is non-zero
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < NB; ++v)
-#pragma unroll
-            for (int q = 0; q < OC / 2; ++q) acc[v][q] = ffma2(coef[v], make_float2(g[2 * q], g[2 * q + 1]), acc[v][q]);
-    }
 
-    // lanes (fixed butterfly) -> warps (in order) -> global
+            // lanes: transposing butterfly (NVP values per lane -> NVP/32), fixed order
+            float v[NVP];
 #pragma unroll
-    for (int v = 0; v < NB; ++v)
+            for (int k = 0; k < NVP; ++k) v[k] = 0.0f;
 #pragma unroll
-        for (int q = 0; q < OC / 2; ++q) {
-            float ax = acc[v][q].x, ay = acc[v][q].y;
+            for (int vv = 0; vv < NB; ++vv)
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                ax += __shfl_xor_sync(0xffffffffu, ax, m);
-                ay += __shfl_xor_sync(0xffffffffu, ay, m);
-            }
-            if (lane == 0) {
-                red[warp][v * OC + 2 * q] = ax;
-                red[warp][v * OC + 2 * q + 1] = ay;
+                for (int q = 0; q < OC / 2; ++q) {
+                    v[vv * OC + 2 * q] = acc[vv][q].x;
+                    v[vv * OC + 2 * q + 1] = acc[vv][q].y;
+                }
+            dwd_fold<NVP>(v, lane, 16);
+            dwd_fold<NVP / 2>(v, lane, 8);
+            dwd_fold<NVP / 4>(v, lane, 4);
+            dwd_fold<NVP / 8>(v, lane, 2);
+            dwd_fold<NVP / 16>(v, lane, 1);
+#pragma unroll
+            for (int k = 0; k < NVP / 32; ++k) {
+                const int e = base + k;
+                const int vv = e / OC, o = o0 + e % OC;
+                if (e < NV && vv < p.nb && o < p.O) {
+                    float* dst = out + ((int64_t)o * p.I + i) * p.nb + vv;
+                    *dst = first ? v[k] : *dst + v[k];  // single writer per partial entry, ranges in order
+                }
             }
         }
-    __syncthreads();
-    if (tid < NB * OC) {
-        const int v = tid / OC, o = o0 + tid % OC;
-        if (v < p.nb && o < p.O) {
-            float sum = 0.0f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) sum += red[w][tid];
-            p.out[(int64_t)ks * p.part_stride + ((int64_t)o * p.I + i) * p.nb + v] = sum;
-        }
+        first = false;
     }
 }
 
@@ -135,20 +153,40 @@ bool dwd_plan(int n, int S, int O, int disc, int64_t B, int I, DwdPlan& d) {
     if (n > 5 || S > 8 || O >= 32 || B < 1) return false;
     const int smax = S <= 2 ? 2 : (S <= 4 ? 4 : 8);
     const int nbmax = (!disc && n == 1) ? 1 : (disc ? n * smax : (n - 1) * smax + 1);
-    int oc = O <= 4 ? 4 : 8;
-    if (nbmax * oc > 128) oc = 4;
-    if (nbmax * oc > 128) return false;
+    // outputs per thread: 4, 6 or 8 -- the choice with the fewest padded columns that still fits
+    // 128 accumulators (O = 6 -> 6, O = 10 -> 2 x 6, O = 16 -> 2 x 8)
+    int oc = 0, best = 1 << 30;
+    for (int c : {8, 6, 4}) {
+        if (nbmax * c > 128) continue;
+        const int slots = (O + c - 1) / c * c;
+        if (slots < best) best = slots, oc = c;
+    }
+    if (!oc) return false;
     d.smax = smax;
     d.oc = oc;
     d.nog = (O + oc - 1) / oc;
-    // sample ranges: enough CTAs for ~4 per SM, at least 8 rows per thread
-    int64_t ks = (4 * 148 + (int64_t)I * d.nog - 1) / ((int64_t)I * d.nog);
-    const int64_t ks_max = B / (256 * 8) > 1 ? B / (256 * 8) : 1;
-    if (ks > ks_max) ks = ks_max;
-    if (ks > 64) ks = 64;
-    if (ks < 1) ks = 1;
-    d.rows_per_split = (B + ks - 1) / ks;
-    d.ksplit = (int)((B + d.rows_per_split - 1) / d.rows_per_split);
+    // staged gy pitch (floats): even, and P/2 odd so that the 64-bit reads of consecutive rows are
+    // conflict free; ~96 KB of gy per CTA (two CTAs per SM)
+    d.P = (oc / 2) % 2 ? oc : oc + 2;
+    int64_t R = (96 * 1024) / (d.P * 4) / 256 * 256;
+    if (R > (B + 255) / 256 * 256) R = (B + 255) / 256 * 256;
+    for (;;) {
+        d.R = (int)R;
+        d.nranges = (int)((B + R - 1) / R);
+        d.nkg = d.nranges < 64 ? d.nranges : 64;
+        // input groups: enough CTAs for ~4 per SM, at least one input per warp where possible; gy
+        // is staged once per group
+        int64_t nig = (4 * 148 + (int64_t)d.nkg * d.nog - 1) / ((int64_t)d.nkg * d.nog);
+        if (nig > (I + 7) / 8) nig = (I + 7) / 8;
+        if (nig < 1) nig = 1;
+        d.G = (int)((I + nig - 1) / nig);
+        d.G = (d.G + 7) / 8 * 8;
+        d.nig = (I + d.G - 1) / d.G;
+        // small problems: shorter sample ranges until every SM has ~2 CTAs
+        if ((int64_t)d.nkg * d.nog * d.nig >= 2 * 148 || R <= 1024 || d.nkg >= 64) break;
+        R /= 2;
+    }
+    d.ksplit = d.nkg;
     d.enabled = true;
     return true;
 }
@@ -165,23 +203,35 @@ static int launch_dwd_t(const PwShape& s, const PwWorkspace& ws, const float* gy
         p.out = out;
         p.B = s.B;
         p.Bp = s.Bp;
-        p.rows_per_split = s.dwd.rows_per_split;
         p.part_stride = (int64_t)s.O * s.I * s.nb;
         p.I = s.I;
         p.O = s.O;
         p.nb = s.nb;
         p.nog = s.dwd.nog;
+        p.R = s.dwd.R;
+        p.P = s.dwd.P;
+        p.G = s.dwd.G;
+        p.nranges = s.dwd.nranges;
+        p.nkg = s.dwd.nkg;
         p.tab = s.tab;
-        dim3 grid((unsigned)(s.I * s.dwd.nog), (unsigned)s.dwd.ksplit);
-        pw_dw_dense_kernel<N, SMAX, OC, DISC><<<grid, 256, 0, st>>>(p);
+        const size_t smem = (size_t)p.R * p.P * sizeof(float);
+        auto kern = pw_dw_dense_kernel<N, SMAX, OC, DISC>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        dim3 grid((unsigned)(s.dwd.nig * s.dwd.nog), (unsigned)s.dwd.nkg);
+        kern<<<grid, 256, smem, st>>>(p);
         return (int)cudaGetLastError();
     }
 }
 
 template <int N, int SMAX, bool DISC>
 static int launch_dwd_oc(const PwShape& s, const PwWorkspace& ws, const float* gy, float* out, cudaStream_t st) {
-    return s.dwd.oc == 8 ? launch_dwd_t<N, SMAX, 8, DISC>(s, ws, gy, out, st)
-                         : launch_dwd_t<N, SMAX, 4, DISC>(s, ws, gy, out, st);
+    switch (s.dwd.oc) {
+        case 8: return launch_dwd_t<N, SMAX, 8, DISC>(s, ws, gy, out, st);
+        case 6: return launch_dwd_t<N, SMAX, 6, DISC>(s, ws, gy, out, st);
+        case 4: return launch_dwd_t<N, SMAX, 4, DISC>(s, ws, gy, out, st);
+    }
+    return HOL_EUNSUPPORTED;
 }
 
 template <int N, bool DISC>
