@@ -251,7 +251,9 @@ def build_workload(torch, cfg, device, rank, args):
         wl.update(model=net, flat=flat, step=step, e2e_compute=e2e_compute, samples=B,
                   host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory()),
                   h2d=x.numel() * 4 + target.numel() * target.element_size(), d2h=4, bytes=by, flops=fl,
-                  launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False),
+                  # + one fused normalisation kernel each way between consecutive layers (csrc/norm.cu)
+                  launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False)
+                  + 2 * (len(dims) - 1),
                   layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x)
         return wl
 
@@ -691,7 +693,8 @@ def _on_device(cfg, chunk, device, R, rng):
     with dev:
         if cfg["kind"] == "layer":
             n, S, I, O = cfg["n"], cfg["S"], cfg["I"], cfg["O"]
-            layer = R.layers.high_order_fc_layers(cfg["layer"], n=n, in_features=I, out_features=O, segments=S)
+            layer = R.layers.high_order_fc_layers(cfg["layer"], n=n, in_features=I, out_features=O, segments=S,
+                                                  device=device).to(dev)
             with torch.no_grad():
                 layer.w.uniform_(-1, 1)
             xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, I)).astype(np.float32)).to(dev).requires_grad_(True)
@@ -709,7 +712,8 @@ def _on_device(cfg, chunk, device, R, rng):
             n, S, wd = cfg["n"], cfg["S"], cfg["widths"]
             net = R.networks.HighOrderMLP(layer_type=cfg["layer"], n=n, in_width=wd[0], out_width=wd[-1],
                                           hidden_layers=len(wd) - 3, hidden_width=wd[1], in_segments=S, out_segments=S,
-                                          hidden_segments=S, normalization=R.layers.MaxAbsNormalization).to(dev)
+                                          hidden_segments=S, normalization=R.layers.MaxAbsNormalization,
+                                          device=device).to(dev)
             xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, wd[0])).astype(np.float32)).to(dev)
             classify = wd[-1] > 1
             tgt = torch.randint(0, wd[-1], (chunk,), device=dev) if classify else torch.randn(chunk, wd[-1], device=dev)
@@ -726,9 +730,9 @@ def _on_device(cfg, chunk, device, R, rng):
             n, S = cfg["n"], cfg["S"]
             nn = torch.nn
             c1 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=3, out_channels=6,
-                                                        kernel_size=5)
+                                                        kernel_size=5, device=device)
             c2 = R.layers.high_order_convolution_layers("continuous2d", n=n, segments=S, in_channels=6,
-                                                        out_channels=16, kernel_size=5)
+                                                        out_channels=16, kernel_size=5, device=device)
             pool, fc = nn.MaxPool2d(2, 2), nn.Linear(400, 100)
             mods = nn.ModuleList([c1, c2, fc]).to(dev)
             xt = torch.from_numpy(rng.uniform(-1, 1, size=(chunk, 3, 32, 32)).astype(np.float32)).to(dev)

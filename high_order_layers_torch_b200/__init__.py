@@ -6,8 +6,15 @@ Drop-in for the hot path of jloveric/high-order-layers-torch: the same construct
 shapes; forward/backward run hand-written CUDA kernels through a C-ABI library
 (`csrc/libhol_b200.so`, `include/hol_b200.h`).  CUDA only -- there is no CPU fallback.
 """
+from . import layers  # noqa: F401
 from .layers import (  # noqa: F401
+    L2Normalization,
     MaxAbsNormalization,
+    MaxAbsNormalizationLast,
+    MaxAbsNormalizationND,
+    MaxCenterNormalization,
+    MaxCenterNormalizationND,
+    normalization_layers,
     convolutional_layers,
     fc_layers,
     high_order_convolution_layers,

@@ -39,6 +39,8 @@ SIGNATURES = {
                                                   _vp]),
     "hol_pw_profile_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
                                           _f32, _vp, _sz, _vp, _vp]),
+    "hol_row_norm_forward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "hol_row_norm_backward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "hol_pw_launch_count": (ctypes.c_int, [ctypes.c_int, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32]),
 }
 

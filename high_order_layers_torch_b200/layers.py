@@ -9,7 +9,8 @@ import torch.nn as nn
 
 from .FunctionalConvolution import PiecewiseDiscontinuousPolynomialConvolution2d, PiecewisePolynomialConvolution2d
 from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial
-from .utils import max_abs_normalization, max_abs_normalization_nd
+from .utils import (l2_normalization, max_abs_normalization, max_abs_normalization_last, max_abs_normalization_nd,
+                    max_center_normalization, max_center_normalization_nd)
 
 
 class MaxAbsNormalization(nn.Module):
@@ -25,13 +26,59 @@ class MaxAbsNormalization(nn.Module):
         return max_abs_normalization(x, eps=self._eps, dim=self._dim)
 
 
+class MaxAbsNormalizationLast(nn.Module):
+    """reference layers.py:44-53"""
+
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self._eps = eps
+
+    def forward(self, x):
+        return max_abs_normalization_last(x, eps=self._eps)
+
+
+class MaxCenterNormalization(nn.Module):
+    """(x - midrange) / (max - midrange + eps) per sample (reference layers.py:84-96)."""
+
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self._eps = eps
+
+    def forward(self, x):
+        return max_center_normalization(x, eps=self._eps)
+
+
+class MaxCenterNormalizationND(nn.Module):
+    """reference layers.py:99-112"""
+
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self._eps = eps
+
+    def forward(self, x):
+        return max_center_normalization_nd(x, eps=self._eps)
+
+
 class MaxAbsNormalizationND(nn.Module):
+    """reference layers.py:115-127"""
+
     def __init__(self, eps: float = 1e-6):
         super().__init__()
         self._eps = eps
 
     def forward(self, x):
         return max_abs_normalization_nd(x, eps=self._eps)
+
+
+class L2Normalization(nn.Module):
+    """x / (||x||_2 + eps) per sample (reference layers.py:130-141)."""
+
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self._eps = eps
+
+    def forward(self, x):
+        return l2_normalization(x, eps=self._eps)
 
 
 class SumLayer(nn.Module):
@@ -48,7 +95,7 @@ class SumLayer(nn.Module):
         return out
 
 
-normalization_layers = {"max_abs": MaxAbsNormalization}
+normalization_layers = {"max_abs": MaxAbsNormalization, "max_center": MaxCenterNormalization, "l2": L2Normalization}
 
 fc_layers = {
     "continuous": PiecewisePolynomial,

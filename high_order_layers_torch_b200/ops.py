@@ -320,6 +320,67 @@ def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int
     return y
 
 
+# ------------------------------------------------------------------------------------------
+# per-sample normalisations between layers: one fused kernel each way
+# ------------------------------------------------------------------------------------------
+NORM_KINDS = {"max_abs": 0, "max_center": 1, "l2": 2}
+
+
+@torch.library.custom_op("hol::row_norm", mutates_args=(), device_types="cuda")
+def row_norm(x: Tensor, kind: int, eps: float) -> Tuple[Tensor, Tensor]:
+    """x[B, W] -> (y[B, W], stats[B, 4]); kind 0 max_abs, 1 max_center, 2 l2 (reference utils.py:8-58)."""
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError(f"row_norm: float32 [batch, width] input required, got {x.dtype} {tuple(x.shape)}")
+    lib = _lib.load()
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    stats = torch.empty((xc.shape[0], 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_row_norm_forward_f32(kind, _ptr(xc), _ptr(y), _ptr(stats), xc.shape[0], xc.shape[1], eps,
+                                                _stream(x)), "hol_row_norm_forward_f32")
+    return y, stats
+
+
+@row_norm.register_fake
+def _(x, kind, eps):
+    return torch.empty_like(x), torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+
+
+@torch.library.custom_op("hol::row_norm_backward", mutates_args=(), device_types="cuda")
+def row_norm_backward(gy: Tensor, x: Tensor, stats: Tensor, kind: int) -> Tensor:
+    lib = _lib.load()
+    gyc, xc = gy.contiguous(), x.contiguous()
+    dx = torch.empty_like(xc)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_row_norm_backward_f32(kind, _ptr(gyc), _ptr(xc), _ptr(stats), _ptr(dx), xc.shape[0],
+                                                 xc.shape[1], _stream(x)), "hol_row_norm_backward_f32")
+    return dx
+
+
+@row_norm_backward.register_fake
+def _(gy, x, stats, kind):
+    return torch.empty_like(x)
+
+
+def _row_norm_setup(ctx, inputs, output):
+    x, kind, _ = inputs
+    ctx.save_for_backward(x, output[1])
+    ctx.kind = kind
+
+
+def _row_norm_bwd(ctx, gy, _gstats):
+    x, stats = ctx.saved_tensors
+    return row_norm_backward(gy, x, stats, ctx.kind), None, None
+
+
+row_norm.register_autograd(_row_norm_bwd, setup_context=_row_norm_setup)
+
+
+def normalize_rows(x: Tensor, kind: str, eps: float = 1e-6) -> Tensor:
+    """Fused per-sample normalisation over dim 1 of a CUDA fp32 [B, W] tensor."""
+    return row_norm(x, NORM_KINDS[kind], float(eps))[0]
+
+
 def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, discontinuous: bool, want_dx: bool = True,
                  want_dw: bool = True, prepared: bool = True) -> int:
     """Kernels of this library launched by one forward (kind 0) / backward (kind 1) call of a layer."""

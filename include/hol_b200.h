@@ -132,6 +132,20 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
 int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
                         int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags);
 
+/* ---- per-sample normalisations between layers ------------------------------
+ * One fused kernel each way for the reference's max_abs_normalization (utils.py:8-13, used by
+ * layers.py:70-81 MaxAbsNormalization), max_center_normalization (utils.py:20-28, layers.py:84-96)
+ * and l2_normalization (utils.py:57-58, layers.py:132-141) over dim 1 of x[B, W].
+ * kind: 0 max_abs, 1 max_center, 2 l2.  stats[B][4] (fp32) is written by the forward and read by
+ * the backward (denominator, centre / norm, arg-max / arg-min as int bits). */
+#define HOL_NORM_MAX_ABS 0
+#define HOL_NORM_MAX_CENTER 1
+#define HOL_NORM_L2 2
+int hol_row_norm_forward_f32(int32_t kind, const float* x, float* y, float* stats, int64_t B,
+                             int32_t W, float eps, void* stream);
+int hol_row_norm_backward_f32(int32_t kind, const float* gy, const float* x, const float* stats,
+                              float* dx, int64_t B, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,6 +346,28 @@ def main():
     var["poly_cases"] = np.array(var_poly)
     np.savez_compressed(os.path.join(args.out, "variants.npz"), **var)
 
+    # -------------------------------------------- per-sample normalisations (utils.py:8-58)
+    nr = {}
+    nr_cases = []
+    fns = {"max_abs": R.utils.max_abs_normalization, "max_center": R.utils.max_center_normalization,
+           "l2": R.utils.l2_normalization}
+    for kind, fn in fns.items():
+        for (B, W) in [(1, 1), (3, 10), (64, 128), (17, 1000), (5, 33)]:
+            x = rng.uniform(-2, 2, size=(B, W)).astype(np.float32)
+            if B >= 3:
+                x[1] = 0.0                       # an all-zero sample
+                x[2, : max(W // 2, 1)] = x[2, 0]  # ties for the maximum
+            xt = torch.from_numpy(x.copy()).requires_grad_(True)
+            y = fn(xt)
+            gy = rng.standard_normal(size=(B, W)).astype(np.float32)
+            y.backward(torch.from_numpy(gy))
+            name = f"{kind}_{B}x{W}"
+            nr[name + "_x"], nr[name + "_gy"] = x, gy
+            nr[name + "_y"], nr[name + "_dx"] = y.detach().numpy().copy(), xt.grad.numpy().copy()
+            nr_cases.append(name)
+    nr["cases"] = np.array(nr_cases)
+    np.savez_compressed(os.path.join(args.out, "row_norms.npz"), **nr)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

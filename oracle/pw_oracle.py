@@ -265,6 +265,53 @@ def max_abs_normalization_backward(g, x, eps: float = 1e-6, dtype=np.float64):
     return dx
 
 
+def max_center_normalization(x, eps: float = 1e-6, dtype=np.float64):
+    """utils.py:20-28: midrange = (max+min)/2, mag = max - midrange, (x - midrange)/(mag + eps)."""
+    x = np.asarray(x).astype(dtype)
+    mx, mn = np.max(x, axis=1, keepdims=True), np.min(x, axis=1, keepdims=True)
+    mid = dtype(0.5) * (mx + mn)
+    return (x - mid) / ((mx - mid) + dtype(eps))
+
+
+def max_center_normalization_backward(g, x, eps: float = 1e-6, dtype=np.float64):
+    """Gradient of the above; max / min route their gradients to the first arg-max / arg-min."""
+    x = np.asarray(x).astype(dtype)
+    g = np.asarray(g).astype(dtype)
+    rows = np.arange(x.shape[0])
+    ia, ib = np.argmax(x, axis=1), np.argmin(x, axis=1)
+    mx, mn = x[rows, ia][:, None], x[rows, ib][:, None]
+    mid = dtype(0.5) * (mx + mn)
+    d = (mx - mid) + dtype(eps)
+    dx = g / d
+    dmid = -np.sum(g, axis=1) / d[:, 0]
+    dd = -np.sum(g * (x - mid), axis=1) / d[:, 0] ** 2
+    np.add.at(dx, (rows, ia), dtype(0.5) * (dmid + dd))
+    np.add.at(dx, (rows, ib), dtype(0.5) * (dmid - dd))
+    return dx
+
+
+def l2_normalization(x, eps: float = 1e-6, dtype=np.float64):
+    """utils.py:57-58"""
+    x = np.asarray(x).astype(dtype)
+    return x / (np.sqrt(np.sum(x * x, axis=1, keepdims=True)) + dtype(eps))
+
+
+def l2_normalization_backward(g, x, eps: float = 1e-6, dtype=np.float64):
+    x = np.asarray(x).astype(dtype)
+    g = np.asarray(g).astype(dtype)
+    nrm = np.sqrt(np.sum(x * x, axis=1, keepdims=True))
+    d = nrm + dtype(eps)
+    k = np.where(nrm > 0, -np.sum(g * x, axis=1, keepdims=True) / (d * d * np.where(nrm > 0, nrm, 1)), 0)
+    return g / d + k * x
+
+
+ROW_NORMS = {
+    "max_abs": (max_abs_normalization, max_abs_normalization_backward),
+    "max_center": (max_center_normalization, max_center_normalization_backward),
+    "l2": (l2_normalization, l2_normalization_backward),
+}
+
+
 def mlp_forward_backward(x, weights, gy, n, segments, discontinuous=False, periodicity=None,
                          normalize=True, nodes=None, dtype=np.float64):
     """HighOrderMLP (networks.py:222-288) = layer, [max_abs, layer]*; returns (y, dx, [dW...])."""

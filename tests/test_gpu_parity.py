@@ -389,3 +389,52 @@ def test_wide_conv_tensor_core_path_matches_oracle_and_gather(contraction_path):
     if contraction_path == "tensor-core":
         rows = B * H * W
         assert ops.uses_tensor_cores(rows, C * K * K, O, n, S, False)
+
+
+def test_row_norms_vs_golden_and_oracle():
+    """fused normalisation kernels (csrc/norm.cu) against the reference's outputs and
+    autograd gradients; max_abs / max_center forward keep the reference's op order -> bit-exact."""
+    from high_order_layers_torch_b200 import utils as U
+    fns = {"max_abs": U.max_abs_normalization, "max_center": U.max_center_normalization, "l2": U.l2_normalization}
+    g = load_golden("row_norms.npz")
+    for name in g["cases"]:
+        name = str(name)
+        kind = name.rsplit("_", 1)[0]
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = fns[kind](xt)
+        y.backward(t(g[name + "_gy"]))
+        yn, dxn = y.detach().cpu().numpy(), xt.grad.cpu().numpy()
+        if kind != "l2":
+            assert np.array_equal(yn, g[name + "_y"]), name
+        assert rel_err(yn, g[name + "_y"]) < TOL, name
+        assert np.abs(dxn - g[name + "_dx"]).max() < TOL * max(np.abs(g[name + "_dx"]).max(), 1.0), name
+    # a wide, many-row case against the fp64 oracle
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-3, 3, size=(4099, 777)).astype(np.float32)
+    gy = rng.standard_normal(size=x.shape).astype(np.float32)
+    for kind, fn in fns.items():
+        xt = t(x).requires_grad_(True)
+        y = fn(xt)
+        y.backward(t(gy))
+        fwd, bwd = orc.ROW_NORMS[kind]
+        assert rel_err(y.detach().cpu().numpy(), fwd(x)) < TOL, kind
+        assert rel_err(xt.grad.cpu().numpy(), bwd(gy, x)) < TOL, kind
+
+
+def test_mlp_with_fused_normalizations_matches_torch_expression():
+    """HighOrderMLP with each normalisation class: fused kernels vs the reference's torch
+    expression evaluated on the same device."""
+    for norm, expr in ((hol.layers.MaxCenterNormalization,
+                        lambda v: (v - 0.5 * (v.max(1, keepdim=True)[0] + v.min(1, keepdim=True)[0])) /
+                        (v.max(1, keepdim=True)[0] - 0.5 * (v.max(1, keepdim=True)[0] + v.min(1, keepdim=True)[0]) + 1e-6)),
+                       (hol.layers.L2Normalization, lambda v: v / (v.norm(2, 1, keepdim=True) + 1e-6))):
+        torch.manual_seed(3)
+        net = hol.HighOrderMLP(layer_type="continuous", n=3, in_width=5, out_width=4, hidden_layers=1, hidden_width=12,
+                               in_segments=3, out_segments=3, hidden_segments=3, normalization=norm, device=DEV)
+        x = (torch.rand(37, 5, device=DEV) * 2 - 1).requires_grad_(True)
+        y = net(x)
+        y.sum().backward()
+        h = expr(net.input_layer(x.detach()))
+        h = expr(net.model[2](h))
+        y2 = net.output_layer(h)
+        assert rel_err(y.detach().cpu().numpy(), y2.detach().cpu().numpy()) < MLP_TOL

@@ -193,3 +193,16 @@ def test_variants_discontinuous_conv_and_polynomial():
         assert rel_err(dw, g[name + "_dw"]) < TOL, name
         if n > 1:
             assert rel_err(dx, g[name + "_dx"]) < TOL, name
+
+
+def test_row_norms_match_reference():
+    """the oracle's normalisations and their closed-form gradients against the
+    reference's utils.py:8-58 + autograd (fixture row_norms.npz, incl. all-zero rows and ties)."""
+    g = load_golden("row_norms.npz")
+    for name in g["cases"]:
+        name = str(name)
+        fwd, bwd = orc.ROW_NORMS[name.rsplit("_", 1)[0]]
+        x, gy = g[name + "_x"], g[name + "_gy"]
+        assert rel_err(fwd(x), g[name + "_y"]) < 1e-6, name
+        # width-1 rows: the gradient is a cancellation residue (~eps), compare absolutely
+        assert np.abs(bwd(gy, x) - g[name + "_dx"]).max() < 1e-6 * max(np.abs(g[name + "_dx"]).max(), 1.0), name
