@@ -104,6 +104,7 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
     ws.xl_img = conv ? (float*)take((size_t)conv_pixels * sizeof(float)) : nullptr;
     ws.seg_img = conv ? (uint16_t*)take((size_t)conv_pixels * sizeof(uint16_t)) : nullptr;
+    ws.tc_phi = (s.tc.enabled && s.tc.share_phi) ? (void*)take(s.tc.phi_bytes) : nullptr;
     ws.tc_a = s.tc.enabled ? (void*)take(s.tc.a_bytes) : nullptr;
     ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
     ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
@@ -122,8 +123,9 @@ int conv_out(int H, int K, int stride, int padding, int dilation) {
     } while (0)
 
 // `packed`: the gather-path weight packing (wk) in the workspace is valid
+// `prepared`: the workspace still holds the forward's state (Phi tiles on the shared-Phi path)
 int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, const float* w, float* dx,
-                    int dx_transposed, float* dw, bool packed, cudaStream_t st) {
+                    int dx_transposed, float* dw, bool packed, bool prepared, cudaStream_t st) {
     if (dx) {
         if (s.n == 1) {
             const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
@@ -138,7 +140,7 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
     }
     if (dw) {
         if (s.tc.dw) {
-            HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, st));
+            HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, prepared && s.tc.fwd, st));
         } else if (s.dwd.enabled) {
             HOL_TRY(launch_backward_dw_dense(s, ws, gy, dw, st));
         } else {
@@ -216,7 +218,8 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_fc(x, s, ws, st));
     }
-    return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, st);
+    return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd,
+                           (flags & HOL_WS_PREPARED) != 0, st);
 }
 
 size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
@@ -275,7 +278,8 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     }
-    HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, st));
+    HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc,
+                            (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, (flags & HOL_WS_PREPARED) != 0, st));
     if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     return HOL_OK;
 }
@@ -313,7 +317,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     if (rc == HOL_OK && !s.tc.dw && !s.dwd.enabled) rc = launch_bucket_sort(s, ws, st);
     mark(5);
     if (rc == HOL_OK)
-        rc = s.tc.dw ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, st)
+        rc = s.tc.dw ? launch_backward_dw_tc(s, ws, s.tc, gy, dw, s.tc.fwd, st)
                      : (s.dwd.enabled ? launch_backward_dw_dense(s, ws, gy, dw, st) : launch_backward_dw(s, ws, gy, dw, st));
     mark(6);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -341,7 +345,7 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     int c = prepared ? 0 : 1;  // prep
     if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1) : ((prepared && !s.tc.fwd) ? 1 : 2);
     if (want_dw)
-        c += s.tc.dw ? tc_launch_count(s, s.tc, 2)
+        c += s.tc.dw ? tc_launch_count(s, s.tc, 2) + ((s.tc.share_phi && !(prepared && s.tc.fwd)) ? 1 : 0)
                      : (s.dwd.enabled ? 1 + (s.dwd.ksplit > 1 ? 1 : 0) : 2 + (s.ksplit > 1 ? 1 : 0));
     return c;
 }

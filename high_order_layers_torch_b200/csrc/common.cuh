@@ -23,6 +23,10 @@ struct TcPlan {
     bool enabled;             // any pass on the tensor cores
     bool fwd, dx, dw;         // per pass (thresholds fitted to the c5 sweep, see tc_plan)
     bool gen;                 // Phi / Phi^T tiles are generated inside the GEMM (Kin >= 16), never materialised
+    bool share_phi;           // Phi tiles of the WHOLE batch are built once by the forward and read again by dW
+                              // (MN-major A operand), so Phi^T is never built
+    int nkc_pad;              // share_phi: k-chunks per batch tile in the Phi storage (nkc rounded up to even)
+    size_t phi_bytes;         // share_phi: Phi storage for the whole batch
     int Kin;                  // dense columns per input: weights per link padded to 8
     int BN, nNT;              // output tile width and count
     int nkc;                  // 64-wide K chunks
@@ -76,7 +80,8 @@ struct PwWorkspace {
     float* dx_rows;   // conv only: [rows][I] unfolded input gradient
     float* xl_img;    // conv only: [Bimg][C][H][W] local coordinate per pixel (before the unfold)
     uint16_t* seg_img;  // conv only: segment + flags per pixel
-    void* tc_a;       // tensor-core path: Phi tiles (fp16 hi/lo shared-memory images)
+    void* tc_phi;     // tensor-core path, share_phi: Phi tiles of the whole batch (forward -> dW)
+    void* tc_a;       // tensor-core path: Phi / Phi^T / gy tiles (fp16 hi/lo shared-memory images)
     void* tc_b;       // tensor-core path: W tiles
     void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|)
     size_t total;

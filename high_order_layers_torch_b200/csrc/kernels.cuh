@@ -27,8 +27,9 @@ int launch_backward_dw_dense(const PwShape& s, const PwWorkspace& ws, const floa
 // tensor-core forward (tc.cu)
 bool tc_plan(const PwShape& s, TcPlan& t);
 int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st);
+// phi_valid: ws.tc_phi still holds the forward's Phi tiles (shared-Phi path)
 int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
-                          cudaStream_t st);
+                          bool phi_valid, cudaStream_t st);
 int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
                           float* dx, int transposed, cudaStream_t st);
 

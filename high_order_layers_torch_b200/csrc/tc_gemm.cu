@@ -71,12 +71,27 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
         if (rows < 512) return false;
         if (rows > s.Bp) rows = s.Bp;
     }
+    // Shared Phi: when forward and dW both run on the tensor cores, the forward materialises the Phi
+    // tiles of the WHOLE batch once and dW reads the same tiles as its MN-major A operand -- no Phi^T
+    // builder, no batch chunking.  Bounded to 40 GiB of tiles; larger layers keep the chunked scheme.
+    t.share_phi = false;
+    t.nkc_pad = (t.nkc + 1) & ~1;
+    t.phi_bytes = 0;
+    {
+        const char* off2 = getenv("HOL_TC_SHARE_PHI");
+        const size_t all = (size_t)((s.Bp + TC_BM - 1) / TC_BM) * t.nkc_pad * 2 * TC_A_IMG;
+        if (!(off2 && off2[0] == '0') && t.fwd && t.dw && !t.gen && all <= ((size_t)40 << 30)) {
+            t.share_phi = true;
+            t.phi_bytes = all;
+            rows = s.Bp;
+        }
+    }
     rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
     t.rows_per_launch = rows;
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
-    size_t a = t.gen ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                         // Phi
-    const size_t a_t = t.gen ? 0 : (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;       // Phi^T
+    size_t a = (t.gen || t.share_phi) ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
+    const size_t a_t = (t.gen || t.share_phi) ? 0 : (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;  // Phi^T
     const size_t a_gy = t.dx ? mtiles * t.noc * 2 * TC_A_IMG : 0;                 // gy
     if (a_t > a) a = a_t;
     if (a_gy > a) a = a_gy;
@@ -107,6 +122,7 @@ static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws
     p.length = s.length;
     p.Sf = (float)s.S;
     p.tab = s.tab;
+    p.a_nkc = 0;  // set by the launchers
 }
 
 // diagnostic timing of the GEMM launches (only while hol_pw_profile_f32 runs on this thread)
@@ -140,8 +156,10 @@ static int sm_count() {
     return n > 0 ? n : 148;
 }
 
-template <int EPI, int N, bool GEN>
+template <int EPI, int N, int AMODE>
 static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_t st) {
+    constexpr bool GEN = AMODE == A_GEN;
+    if (p.a_nkc == 0) p.a_nkc = p.nkc;
     const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
     int nst = (HOL_SMEM_BUDGET - 1024) / stage;
     if (nst > 6) nst = 6;
@@ -155,7 +173,7 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     p.group_m = ntiles_n >= 12 ? 12 : (148 + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
     if (p.group_m > mtiles) p.group_m = (int)mtiles;
     if (p.group_m < 1) p.group_m = 1;
-    auto kern = pw_tc_gemm_kernel<EPI, N, GEN>;
+    auto kern = pw_tc_gemm_kernel<EPI, N, AMODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t sms = sm_count();
@@ -178,6 +196,7 @@ int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
     const int ex = t.gen ? 0 : 1;          // Phi / Phi^T expansion kernel (absent when generated in the GEMM)
     if (kind == 0) return 2 + 1 + nl * (1 + ex);  // absmax x2, pack_w, ([expand,] gemm) per batch chunk
     if (kind == 1) return 2 + 1 + nl * 2;         // absmax x2, pack_wt, (pack_gy, gemm)
+    if (t.share_phi) return 2 + 2;                // absmax x2, pack_gyt, gemm (the Phi tiles come from the forward)
     return 2 + nl * (2 + ex);                     // absmax x2, ([expand_t,] pack_gyt, gemm)
 }
 
@@ -216,10 +235,13 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
     for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
         int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
         rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
-        dim3 egrid((unsigned)(rows / TC_BM), (unsigned)t.nkc);
+        // shared Phi: one launch builds the tiles of the whole batch (k-chunks padded to even with zero tiles)
+        const int ekc = t.share_phi ? t.nkc_pad : t.nkc;
+        unsigned char* phi = (unsigned char*)(t.share_phi ? ws.tc_phi : ws.tc_a);
+        dim3 egrid((unsigned)(rows / TC_BM), (unsigned)ekc);
         rc = HOL_OK;
         if (!t.gen) {
-#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, t.nkc, s.stride, s.tab), (int)cudaGetLastError())
+#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, phi, sc, s.Bp, row0, s.I, t.Kin, ekc, s.stride, s.tab), (int)cudaGetLastError())
             DISPATCH_N(s.n, EXPAND)
 #undef EXPAND
         }
@@ -233,20 +255,49 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         p.n_valid = s.O;
         p.ld = s.O;
         p.nkc = t.nkc;
-        rc = t.gen ? launch_gemm<EPI_Y, 0, true>(p, rows / TC_BM, t.nNT, st)
-                   : launch_gemm<EPI_Y, 0, false>(p, rows / TC_BM, t.nNT, st);
+        p.a_nkc = ekc;
+        p.a_tiles = phi;
+        rc = t.gen ? launch_gemm<EPI_Y, 0, A_GEN>(p, rows / TC_BM, t.nNT, st)
+                   : launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, st);
         if (rc != HOL_OK) return rc;
     }
     return HOL_OK;
 }
 
 int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
-                          cudaStream_t st) {
+                          bool phi_valid, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
     int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
     if (rc != HOL_OK) return rc;
     rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
     if (rc != HOL_OK) return rc;
+    if (t.share_phi) {
+        const int64_t mtiles = (s.Bp + TC_BM - 1) / TC_BM;
+        if (!phi_valid) {  // backward without the forward's workspace: build the Phi tiles first
+            dim3 egrid((unsigned)mtiles, (unsigned)t.nkc_pad);
+#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_phi, sc, s.Bp, (int64_t)0, s.I, t.Kin, t.nkc_pad, s.stride, s.tab), (int)cudaGetLastError())
+            DISPATCH_N(s.n, EXPAND)
+#undef EXPAND
+            if (rc != HOL_OK) return rc;
+        }
+        const int nbc = (int)((s.Bp + TC_BK - 1) / TC_BK);
+        dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
+        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, (int64_t)0, s.O, nbc, t.BN);
+        rc = (int)cudaGetLastError();
+        if (rc != HOL_OK) return rc;
+        TcGemmParams p;
+        fill_common(p, s, ws, t);
+        p.a_tiles = (const unsigned char*)ws.tc_phi;
+        p.a_nkc = t.nkc_pad;
+        p.out = dw;
+        p.row0 = 0;
+        p.rows_valid = 0;
+        p.BN = t.BN;
+        p.n_valid = s.O;
+        p.ld = 0;
+        p.nkc = nbc;  // 64-sample stages: stage sc = samples 64*(sc & 1).. of batch tile sc >> 1
+        return launch_gemm<EPI_DW, 0, A_PHI_MN>(p, t.nkc_pad / 2, t.nNT, st);
+    }
     for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
         int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
         const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
@@ -271,7 +322,7 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.n_valid = s.O;
         p.ld = 0;
         p.nkc = nbc;
-        rc = t.gen ? launch_gemm<EPI_DW, 0, true>(p, t.nMTw, t.nNT, st) : launch_gemm<EPI_DW, 0, false>(p, t.nMTw, t.nNT, st);
+        rc = t.gen ? launch_gemm<EPI_DW, 0, A_GEN>(p, t.nMTw, t.nNT, st) : launch_gemm<EPI_DW, 0, A_TILES>(p, t.nMTw, t.nNT, st);
         if (rc != HOL_OK) return rc;
     }
     return HOL_OK;
@@ -305,7 +356,7 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.ld = 0;
         p.nkc = t.noc;
         p.transposed = transposed;
-#define GEMM_DX(NN) launch_gemm<EPI_DX, NN, false>(p, rows / TC_BM, t.nNTx, st)
+#define GEMM_DX(NN) launch_gemm<EPI_DX, NN, A_TILES>(p, rows / TC_BM, t.nNTx, st)
         DISPATCH_N(s.n, GEMM_DX)
 #undef GEMM_DX
         if (rc != HOL_OK) return rc;

@@ -57,6 +57,7 @@ struct TcGemmParams {
     int64_t ntile_m;
     int ntile_n, group_m;          // rasterisation: groups of group_m m-tiles, m fastest inside a group
     int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
+    int a_nkc;                     // k-chunks per m-tile in the A tile storage (>= nkc: shared Phi pads to even)
     int I, nb, Kin, stride, transposed;
     float length, Sf;
     BasisTab tab;
@@ -173,8 +174,19 @@ __device__ __forceinline__ void gen_scatter(const TcGemmParams& p, int gt, int64
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue, (GEN) 10..11 = operand generators that
 // zero-fill the A half of a stage and scatter the n non-zero basis values of every (sample, input)
 // pair into it, so Phi / Phi^T never exist in global memory.  N = basis size for the EPI_DX gather.
-template <int EPI, int N, bool GEN>
-__global__ void __launch_bounds__(GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+// AMODE: where the A operand of a stage comes from
+//   A_TILES  one bulk copy of a ready-made K-major tile image (Phi, Phi^T or gy tiles)
+//   A_GEN    generated in the kernel by two extra warps (opt-in, see tc_plan)
+//   A_PHI_MN EPI_DW only: the FORWARD's Phi tiles [128 samples][64 dense columns] read as the
+//            MN-major operand Phi^T: a stage = 128 dense columns (two forward k-chunks) x 64
+//            samples (half a batch tile), gathered as 32 pieces of 1 KB (one per lane of the
+//            producer warp) into the canonical MN-major no-swizzle layout
+//            [image][column group of 8][64 samples][8 x fp16]  (SBO = 1024 B, LBO = 128 B)
+enum { A_TILES = 0, A_GEN = 1, A_PHI_MN = 2 };
+
+template <int EPI, int N, int AMODE>
+__global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    constexpr bool GEN = AMODE == A_GEN;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int BN = p.BN;
     const int B_IMG = BN * TC_BK * 2;
@@ -216,14 +228,40 @@ __global__ void __launch_bounds__(GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 && AMODE == A_PHI_MN) {
+        // every lane copies one 1 KB piece per stage: lane = (image, forward k-chunk parity, column group)
+        const int img = lane >> 4, c2 = (lane >> 3) & 1, kg = lane & 7;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            int nt;
+            int64_t mt;
+            tile_coords(p, tile, mt, nt);
+            const int64_t kcf = 2 * mt + c2;  // forward k-chunk holding these 64 dense columns
+            const unsigned char* a_lane = p.a_tiles + (kcf * 2 + img) * (int64_t)TC_A_IMG + kg * (TC_BM * 16);
+            const int64_t a_bt = (int64_t)p.a_nkc * (2 * TC_A_IMG);  // bytes per batch tile
+            const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
+            const uint32_t dst_off = (uint32_t)(img * TC_A_IMG + (c2 * 8 + kg) * 1024);
+            for (int sc = 0; sc < p.nkc; ++sc, ++it) {
+                const int st = it % nst;
+                mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
+                unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
+                if (lane == 0) {
+                    mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
+                    bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)sc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
+                }
+                __syncwarp();
+                // samples 64*(sc & 1) .. +63 of batch tile sc >> 1: rows of 16 bytes, 1 KB contiguous
+                bulk_g2s(dst + dst_off, a_lane + (int64_t)(sc >> 1) * a_bt + (sc & 1) * 1024, 1024u, &full[st]);
+            }
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 int nt;
                 int64_t mt;
                 tile_coords(p, tile, mt, nt);
-                const unsigned char* a_src = p.a_tiles + (mt * p.nkc) * (int64_t)(2 * TC_A_IMG);
+                const unsigned char* a_src = p.a_tiles + (mt * p.a_nkc) * (int64_t)(2 * TC_A_IMG);
                 const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
                 for (int kc = 0; kc < p.nkc; ++kc, ++it) {
                     const int st = it % nst;
@@ -242,8 +280,12 @@ __global__ void __launch_bounds__(GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __
     } else if (warp == 1) {
         if (lane == 0) {
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t LBO_A = TC_BM * 16, LBO_B = (uint32_t)BN * 16, SBO = 128;
+            // (A_PHI_MN: a_major bit 15 = MN-major)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24) |
+                                   (AMODE == A_PHI_MN ? (1u << 15) : 0u);
+            // LBO = byte stride between core matrices along K, SBO = along M / N
+            const uint32_t LBO_A = AMODE == A_PHI_MN ? 128u : TC_BM * 16, SBO_A = AMODE == A_PHI_MN ? 1024u : 128u;
+            const uint32_t LBO_B = (uint32_t)BN * 16, SBO = 128;
             int it = 0, g = 0;
             for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 for (int kc = 0; kc < p.nkc; ++kc, ++it) {
@@ -261,8 +303,8 @@ __global__ void __launch_bounds__(GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __
                     const uint32_t td = tmem_base + (uint32_t)(acc * BN);
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 16; ++kk) {
-                        const uint64_t a_hi = umma_desc_kmajor_noswizzle(sa + kk * 2 * LBO_A, LBO_A, SBO);
-                        const uint64_t a_lo = umma_desc_kmajor_noswizzle(sa + TC_A_IMG + kk * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t a_hi = umma_desc_kmajor_noswizzle(sa + kk * 2 * LBO_A, LBO_A, SBO_A);
+                        const uint64_t a_lo = umma_desc_kmajor_noswizzle(sa + TC_A_IMG + kk * 2 * LBO_A, LBO_A, SBO_A);
                         const uint64_t b_hi = umma_desc_kmajor_noswizzle(sb + kk * 2 * LBO_B, LBO_B, SBO);
                         const uint64_t b_lo = umma_desc_kmajor_noswizzle(sb + B_IMG + kk * 2 * LBO_B, LBO_B, SBO);
                         umma_f16(td, a_hi, b_hi, idesc, (first && kk == 0) ? 0u : 1u);

@@ -16,15 +16,19 @@ from tests.conftest import load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tensor-core", "gather", "tensor-core-gen"], autouse=True)
+@pytest.fixture(params=["tensor-core", "gather", "tensor-core-gen", "tensor-core-chunked"], autouse=True)
 def contraction_path(request, monkeypatch):
-    """Every parity test runs three times: with the tcgen05 segment-expanded path enabled (it is
+    """Every parity test runs four times: with the tcgen05 segment-expanded path enabled (it is
     chosen per shape, see tc_plan in csrc/tc_gemm.cu), with it disabled (gather kernels everywhere),
-    and with the opt-in in-kernel generation of the Phi / Phi^T tiles (HOL_TC_GEN=1)."""
+    with the opt-in in-kernel generation of the Phi / Phi^T tiles (HOL_TC_GEN=1) and with the
+    chunked Phi / Phi^T scheme (HOL_TC_SHARE_PHI=0)."""
     monkeypatch.setenv("HOL_DISABLE_TC", "1" if request.param == "gather" else "0")
     # "gather" also switches the dense-register dW of narrow layers off (bucketed dW everywhere)
     monkeypatch.setenv("HOL_DISABLE_DWD", "1" if request.param == "gather" else "0")
     monkeypatch.setenv("HOL_TC_GEN", "1" if request.param == "tensor-core-gen" else "0")
+    # default: the forward's Phi tiles are shared with dW (MN-major operand); "chunked" = the older
+    # scheme with batch chunks and a separate Phi^T builder, still used above 40 GiB of tiles
+    monkeypatch.setenv("HOL_TC_SHARE_PHI", "0" if request.param == "tensor-core-chunked" else "1")
     return request.param
 
 
