@@ -23,6 +23,8 @@
 // UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
 // pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 =
 // MMA issuer (one elected lane), warps 2-9 = epilogue (tcgen05.ld -> fp32 register sums -> global).
+#include <string.h>
+
 #include "tc_build.cuh"
 
 #include "tc_kernel.cuh"

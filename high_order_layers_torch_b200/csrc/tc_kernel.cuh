@@ -179,8 +179,8 @@ __device__ __forceinline__ void gen_scatter(const TcGemmParams& p, int gt, int64
 //   A_GEN    generated in the kernel by two extra warps (opt-in, see tc_plan)
 //   A_PHI_MN EPI_DW only: the FORWARD's Phi tiles [128 samples][64 dense columns] read as the
 //            MN-major operand Phi^T: a stage = 128 dense columns (two forward k-chunks) x 64
-//            samples (half a batch tile), gathered as 32 pieces of 1 KB (one per lane of the
-//            producer warp) into the canonical MN-major no-swizzle layout
+//            samples (half a batch tile), gathered by the producer warp with 16-byte cp.async copies
+//            into the canonical MN-major no-swizzle layout
 //            [image][column group of 8][64 samples][8 x fp16]  (SBO = 1024 B, LBO = 128 B)
 enum { A_TILES = 0, A_GEN = 1, A_PHI_MN = 2 };
 
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) {
-            mbar_init(&full[s], GEN ? 2 : 1);  // TMA producer (+ the generators' elected thread)
+            mbar_init(&full[s], (GEN || AMODE == A_PHI_MN) ? 2 : 1);  // TMA producer (+ generators / cp.async gather)
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -229,29 +229,43 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && AMODE == A_PHI_MN) {
-        // every lane copies one 1 KB piece per stage: lane = (image, forward k-chunk parity, column group)
-        const int img = lane >> 4, c2 = (lane >> 3) & 1, kg = lane & 7;
+        // The whole producer warp gathers the A half of a stage with 16-byte cp.async copies (2048
+        // per stage, 64 per lane, 512 contiguous bytes per warp instruction): the pieces that are
+        // contiguous in the forward's tile storage are only 1 KB long, and 32 bulk copies of 1 KB
+        // (14.6 ms at C2) or four tiled TMA boxes with 16-byte rows (17.2 ms) cost more than the
+        // MMAs of the stage (11.8 ms with one 32 KB bulk copy of a K-major tile).
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             int nt;
             int64_t mt;
             tile_coords(p, tile, mt, nt);
-            const int64_t kcf = 2 * mt + c2;  // forward k-chunk holding these 64 dense columns
-            const unsigned char* a_lane = p.a_tiles + (kcf * 2 + img) * (int64_t)TC_A_IMG + kg * (TC_BM * 16);
+            const unsigned char* a_mt = p.a_tiles + (2 * mt) * (int64_t)(2 * TC_A_IMG) + lane * 16;
             const int64_t a_bt = (int64_t)p.a_nkc * (2 * TC_A_IMG);  // bytes per batch tile
             const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
-            const uint32_t dst_off = (uint32_t)(img * TC_A_IMG + (c2 * 8 + kg) * 1024);
             for (int sc = 0; sc < p.nkc; ++sc, ++it) {
                 const int st = it % nst;
                 mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
                 unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
                 if (lane == 0) {
-                    mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
+                    mbar_expect_tx(&full[st], (uint32_t)(2 * B_IMG));
                     bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)sc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
                 }
+                // samples 64*(sc & 1) .. +63 of batch tile sc >> 1
+                const unsigned char* src = a_mt + (int64_t)(sc >> 1) * a_bt + (sc & 1) * 1024;
+                const uint32_t d0 = smem_u32(dst) + lane * 16;
+#pragma unroll
+                for (int q = 0; q < 64; ++q) {
+                    // unit = (image, column group g = 8*c2 + kg, 32-row half)
+                    const int img = q >> 5, g = (q & 31) >> 1, c2 = g >> 3, kg = g & 7, rr = (q & 1) * 32;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + img * TC_A_IMG + g * 1024 + rr * 16),
+                                 "l"(src + (c2 * 2 + img) * TC_A_IMG + kg * (TC_BM * 16) + rr * 16)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fence_proxy_async_smem();
                 __syncwarp();
-                // samples 64*(sc & 1) .. +63 of batch tile sc >> 1: rows of 16 bytes, 1 KB contiguous
-                bulk_g2s(dst + dst_off, a_lane + (int64_t)(sc >> 1) * a_bt + (sc & 1) * 1024, 1024u, &full[st]);
+                if (lane == 0) mbar_arrive(&full[st]);
             }
         }
     } else if (warp == 0) {
