@@ -49,7 +49,10 @@ int make_shape(PwShape& s, int64_t B, int I, int O, int n, int S, int disc, floa
     while (OT > 8 && (size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) OT >>= 1;
     if ((size_t)s.R * (OT + 4) * 4 + 128 > HOL_SMEM_BUDGET) return HOL_EUNSUPPORTED;
     s.OT = OT;
-    s.OTP = OT + 4;
+    // up to 8 segments the +4 pitch keeps the segment rows in distinct banks; beyond that the pitch
+    // is the tile itself (a multiple of 128 bytes) and the lanes rotate their column order (fwd.cu)
+    s.rot = (S > 8 && OT >= 32) ? 1 : 0;
+    s.OTP = s.rot ? OT : OT + 4;
     s.nOT = (O + OT - 1) / OT;
     s.srow = single ? 0 : s.OTP;
     for (int j = 0; j < HOL_MAX_N; ++j) s.jrow[j] = 0;

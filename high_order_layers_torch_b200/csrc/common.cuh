@@ -60,6 +60,7 @@ struct PwShape {
     int ksplit;   // dW: number of chunk groups reduced separately (deterministic two-stage sum)
     int dw_lo;    // dW: lanes per sample (power of two; 4 outputs per lane)
     int OT, OTP;  // output tile and its padded pitch (floats) in the packed layout
+    int rot;      // S > 8, OT >= 32: pitch == OT and the gather kernels read the column chunks lane-rotated
     int nOT;      // number of output tiles
     int srow;     // packed floats per segment step (0 for continuous n == 1)
     int jrow[HOL_MAX_N];  // packed float offset of basis j inside an input block

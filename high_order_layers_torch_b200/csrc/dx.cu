@@ -22,12 +22,17 @@ struct DxParams {
     BasisTab tab;
 };
 
-template <int N, int OT, int IT>
+// ROT (S > 8, OT >= 32): the packed rows have a pitch of OT floats and lane l walks the 16-byte
+// column chunks of a tile in the rotated order ((qb + (l%8)/4) % (OT/16), (t + l%8) % 4), so the 8
+// lanes of a quarter warp always read 8 different bank groups whatever their segments are (see
+// fwd.cu); the matching gy chunk is loaded in the same order.
+template <int N, int OT, int IT, bool ROT>
 __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __grid_constant__ DxParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
-    constexpr int OTP = OT + 4;
+    constexpr int OTP = ROT ? OT : OT + 4;
+    const int rot = threadIdx.x & 7;
     const int tid = threadIdx.x;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
     const int in_floats = p.R * OTP;
@@ -84,11 +89,12 @@ __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __
         const float* slab = slab0 + (size_t)(c % p.nst) * p.stage_floats;
         constexpr int QW = OT < 16 ? OT : 16;  // output columns per register block
 #pragma unroll 1
-        for (int qb = 0; qb < OT / QW; ++qb) {
+        for (int qb0 = 0; qb0 < OT / QW; ++qb0) {
+            const int qb = ROT ? ((qb0 + (rot >> 2)) & (OT / QW - 1)) : qb0;
             float4 g[QW / 4];
 #pragma unroll
             for (int t = 0; t < QW / 4; ++t) {
-                const int o = ot * OT + qb * QW + 4 * t;
+                const int o = ot * OT + qb * QW + 4 * (ROT ? ((t + rot) & 3) : t);
                 g[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (rowok) {
                     if (vec && o + 3 < p.O) {
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __
                     const float4* wp = reinterpret_cast<const float4*>(slabq + rowoff[k] + p.jrow[j]);
 #pragma unroll
                     for (int t = 0; t < QW / 4; ++t) {
-                        const float4 w = wp[t];
+                        const float4 w = wp[ROT ? ((t + rot) & 3) : t];
                         acc[k][j] = ffma2v(make_float2(g[t].x, g[t].y), make_float2(w.x, w.y), acc[k][j]);
                         acc[k][j] = ffma2v(make_float2(g[t].z, g[t].w), make_float2(w.z, w.w), acc[k][j]);
                     }
@@ -152,10 +158,11 @@ struct DxTile {
     static constexpr int IT = N <= 2 ? 16 : (N <= 5 ? 8 : 4);
 };
 
-template <int N, int OT>
+template <int N, int OT, bool ROT>
 static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int transposed,
                        cudaStream_t st) {
-    constexpr int OTP = OT + 4;
+    constexpr int OTP = ROT ? OT : OT + 4;
+    if (s.OTP != OTP) return HOL_EINVAL;
     constexpr int IT = DxTile<N>::IT;
     const size_t in_bytes = (size_t)s.R * OTP * 4;
     int it_eff = IT, nst = 2;
@@ -191,7 +198,7 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
         BT = 256;
         if ((s.Bp / BT) * ((s.I + it_eff - 1) / it_eff) < 2 * 148) BT = 128;
     }
-    auto kern = pw_dx_kernel<N, OT, IT>;
+    auto kern = pw_dx_kernel<N, OT, IT, ROT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     // input groups are walked by the CTA; grid.y only has to fill the machine (~4 CTAs per SM)
@@ -207,11 +214,18 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
 template <int N>
 static int launch_dx_n(const PwShape& s, const PwWorkspace& ws, const float* gy, float* dx, int transposed,
                        cudaStream_t st) {
+    if (s.rot) {
+        switch (s.OT) {
+            case 64: return launch_dx_t<N, 64, true>(s, ws, gy, dx, transposed, st);
+            case 32: return launch_dx_t<N, 32, true>(s, ws, gy, dx, transposed, st);
+        }
+        return HOL_EUNSUPPORTED;
+    }
     switch (s.OT) {
-        case 64: return launch_dx_t<N, 64>(s, ws, gy, dx, transposed, st);
-        case 32: return launch_dx_t<N, 32>(s, ws, gy, dx, transposed, st);
-        case 16: return launch_dx_t<N, 16>(s, ws, gy, dx, transposed, st);
-        case 8: return launch_dx_t<N, 8>(s, ws, gy, dx, transposed, st);
+        case 64: return launch_dx_t<N, 64, false>(s, ws, gy, dx, transposed, st);
+        case 32: return launch_dx_t<N, 32, false>(s, ws, gy, dx, transposed, st);
+        case 16: return launch_dx_t<N, 16, false>(s, ws, gy, dx, transposed, st);
+        case 8: return launch_dx_t<N, 8, false>(s, ws, gy, dx, transposed, st);
     }
     return HOL_EUNSUPPORTED;
 }

@@ -7,6 +7,14 @@
 // segments: rows of neighbouring segments are adjacent with a pitch of OT+4 floats, so the (up
 // to 8) distinct 16-byte chunks a warp touches per LDS.128 sit in distinct banks and samples
 // that share a segment are served by the shared-memory broadcast.
+//
+// More than 8 segments cannot be separated by the pitch: rows 8 segments apart share their
+// banks and a warp with random segments pays ~2.5 wavefronts too many per LDS.128 (measured:
+// the forward ran at 6 TFLOP/s at S = 64 against 16 at S = 8).  For S > 8 (ROT) the row pitch is a
+// multiple of 128 bytes and lane l reads the column chunks in the rotated order (q + l%8) mod
+// (OT/4): the 8 lanes of every quarter warp then hit 8 different 16-byte bank groups whatever
+// their segments are -- always the 4-wavefront minimum -- and the rotation is undone for free when
+// the outputs are stored (slot q of lane l is output chunk (q + l%8) mod (OT/4)).
 #include "kernels.cuh"
 
 struct FwdParams {
@@ -20,9 +28,9 @@ struct FwdParams {
     BasisTab tab;
 };
 
-template <int N, int OT>
+template <int N, int OT, bool ROT>
 __device__ __forceinline__ void fwd_one(float xl, uint32_t sg, const float* slab_i, float2 (&acc)[OT / 2],
-                                        const FwdParams& p) {
+                                        const FwdParams& p, int rot) {
     float phi[N];
     lagrange_basis<N>(xl, p.tab, phi);
     const float keep = (sg & HOL_SEG_INVALID) ? 0.0f : 1.0f;
@@ -33,19 +41,20 @@ __device__ __forceinline__ void fwd_one(float xl, uint32_t sg, const float* slab
         const float4* rj = reinterpret_cast<const float4*>(r0 + p.jrow[j]);
 #pragma unroll
         for (int q = 0; q < OT / 4; ++q) {
-            const float4 w = rj[q];
+            const float4 w = rj[ROT ? ((q + rot) & (OT / 4 - 1)) : q];
             acc[2 * q] = ffma2(ph, make_float2(w.x, w.y), acc[2 * q]);
             acc[2 * q + 1] = ffma2(ph, make_float2(w.z, w.w), acc[2 * q + 1]);
         }
     }
 }
 
-template <int N, int OT>
+template <int N, int OT, bool ROT>
 __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
-    constexpr int OTP = OT + 4;
+    constexpr int OTP = ROT ? OT : OT + 4;
+    const int rot = threadIdx.x & 7;
     constexpr int G = 4;
     const int tid = threadIdx.x;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
             const int nbase = (g0 + G < ni) ? i0 + g0 + G : i0 + ni;
 #pragma unroll
             for (int k = 0; k < G; ++k) {
-                if (g0 + k < ni) fwd_one<N, OT>(xr[k], sr[k], slab + (size_t)(g0 + k) * in_floats, acc, p);
+                if (g0 + k < ni) fwd_one<N, OT, ROT>(xr[k], sr[k], slab + (size_t)(g0 + k) * in_floats, acc, p, rot);
                 const int ii = nbase + k;
                 xr[k] = 0.0f;
                 sr[k] = HOL_SEG_INVALID;
@@ -124,23 +133,25 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
         const bool vec = (p.O & 3) == 0;
 #pragma unroll
         for (int q = 0; q < OT / 4; ++q) {
-            const int o = o0 + 4 * q;
+            const int qc = ROT ? ((q + rot) & (OT / 4 - 1)) : q;  // output chunk held in slot q
+            const int o = o0 + 4 * qc;
             if (vec && o + 3 < p.O) {
-                *reinterpret_cast<float4*>(yrow + 4 * q) =
+                *reinterpret_cast<float4*>(yrow + 4 * qc) =
                     make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
             } else {
-                if (o + 0 < p.O) yrow[4 * q + 0] = acc[2 * q].x;
-                if (o + 1 < p.O) yrow[4 * q + 1] = acc[2 * q].y;
-                if (o + 2 < p.O) yrow[4 * q + 2] = acc[2 * q + 1].x;
-                if (o + 3 < p.O) yrow[4 * q + 3] = acc[2 * q + 1].y;
+                if (o + 0 < p.O) yrow[4 * qc + 0] = acc[2 * q].x;
+                if (o + 1 < p.O) yrow[4 * qc + 1] = acc[2 * q].y;
+                if (o + 2 < p.O) yrow[4 * qc + 2] = acc[2 * q + 1].x;
+                if (o + 3 < p.O) yrow[4 * qc + 3] = acc[2 * q + 1].y;
             }
         }
     }
 }
 
-template <int N, int OT>
+template <int N, int OT, bool ROT>
 static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream_t st) {
-    constexpr int OTP = OT + 4;
+    constexpr int OTP = ROT ? OT : OT + 4;
+    if (s.OTP != OTP) return HOL_EINVAL;
     FwdParams p;
     p.xl_t = ws.xl_t;
     p.seg_t = ws.seg_t;
@@ -177,7 +188,7 @@ static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
         BT = 512;
         while (BT > 128 && (s.Bp / BT) * s.nOT < 2 * 148) BT >>= 1;
     }
-    auto kern = pw_fwd_kernel<N, OT>;
+    auto kern = pw_fwd_kernel<N, OT, ROT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)(s.Bp / BT), (unsigned)s.nOT);
@@ -187,11 +198,18 @@ static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
 
 template <int N>
 static int launch_fwd_n(const PwShape& s, const PwWorkspace& ws, float* y, cudaStream_t st) {
+    if (s.rot) {  // more than 8 segments: lane-rotated column order (OT >= 32 only, see make_shape)
+        switch (s.OT) {
+            case 64: return launch_fwd_t<N, 64, true>(s, ws, y, st);
+            case 32: return launch_fwd_t<N, 32, true>(s, ws, y, st);
+        }
+        return HOL_EUNSUPPORTED;
+    }
     switch (s.OT) {
-        case 64: return launch_fwd_t<N, 64>(s, ws, y, st);
-        case 32: return launch_fwd_t<N, 32>(s, ws, y, st);
-        case 16: return launch_fwd_t<N, 16>(s, ws, y, st);
-        case 8: return launch_fwd_t<N, 8>(s, ws, y, st);
+        case 64: return launch_fwd_t<N, 64, false>(s, ws, y, st);
+        case 32: return launch_fwd_t<N, 32, false>(s, ws, y, st);
+        case 16: return launch_fwd_t<N, 16, false>(s, ws, y, st);
+        case 8: return launch_fwd_t<N, 8, false>(s, ws, y, st);
     }
     return HOL_EUNSUPPORTED;
 }

@@ -400,6 +400,25 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
             float racc[TC_MAXHALF];
 #pragma unroll
             for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
+            // EPI_DX: fetch the coordinates of the first inputs of this thread's columns now, so the
+            // gather after the last drain does not wait on global memory while the MMA warp needs
+            // the next drains
+            constexpr int PF = 4;
+            uint32_t pf_sg[PF];
+            float pf_xl[PF];
+            if (EPI == EPI_DX) {
+                const int64_t b = p.row0 + mt * TC_BM + rl;
+                const int i0 = (nt * BN + h * HALF) / p.Kin;
+#pragma unroll
+                for (int ii = 0; ii < PF; ++ii) {
+                    pf_sg[ii] = HOL_SEG_INVALID;
+                    pf_xl[ii] = 0.0f;
+                    if (b < p.Bp && i0 + ii < p.I) {
+                        pf_sg[ii] = p.seg_t[(int64_t)(i0 + ii) * p.Bp + b];
+                        pf_xl[ii] = p.xl_t[(int64_t)(i0 + ii) * p.Bp + b];
+                    }
+                }
+            }
             for (int gg = 0; gg < ngroups; ++gg, ++g) {
                 const int acc = g & 1;
                 mbar_wait(&tmem_full[acc], (uint32_t)((g >> 1) & 1));
@@ -474,10 +493,20 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                         const int i = colbase / p.Kin + ii;
                         if (i >= p.I) break;
                         const int64_t idx = (int64_t)i * p.Bp + b;
-                        const uint32_t sg = p.seg_t[idx];
+                        uint32_t sg;
+                        float xlv;
+                        if (ii < PF) {
+                            sg = pf_sg[0], xlv = pf_xl[0];
+#pragma unroll
+                            for (int q = 1; q < PF; ++q)
+                                if (ii == q) sg = pf_sg[q], xlv = pf_xl[q];
+                        } else {
+                            sg = p.seg_t[idx];
+                            xlv = p.xl_t[idx];
+                        }
                         const int s = (int)(sg & HOL_SEG_MASK);
                         float dphi[NB];
-                        lagrange_basis_derivative<NB>(p.xl_t[idx], p.tab, dphi);
+                        lagrange_basis_derivative<NB>(xlv, p.tab, dphi);
                         const float* Tr = T + ii * p.Kin + s * p.stride;
                         float sum = 0.0f;
 #pragma unroll

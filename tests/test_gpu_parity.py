@@ -135,6 +135,8 @@ FC_ORACLE_CASES = [
     ("cont", 1, 4, 9, 6, 40, None),
     ("disc", 1, 4, 9, 6, 40, None),
     ("cont", 2, 1, 3, 2, 1, None),
+    ("cont", 3, 16, 20, 40, 300, None),      # S > 8 with 32-wide tiles: lane-rotated column order (gather path)
+    ("disc", 4, 12, 37, 100, 1100, None),    # S > 8, 64-wide tiles, two output tiles, several sample blocks
     # narrow layers: dense-register dW (dwd.cu) with several sample ranges, every compiled segment bound
     ("cont", 3, 4, 75, 6, 5000, None),       # config-4 conv1 as rows (OT = 8 tiles, float2 gy loads)
     ("cont", 3, 4, 150, 16, 4100, None),     # config-4 conv2 as rows (two output groups)
