@@ -102,10 +102,28 @@ class Piecewise(_PiecewiseBase):
     """Continuous piecewise polynomial: neighbouring segments share their end node."""
     _discontinuous = False
 
+    def interpolate(self, layer_out: "Piecewise") -> None:
+        """p-refinement into `layer_out` (reference :346-350)."""
+        from .refinement import interpolate_polynomial_layer
+        interpolate_polynomial_layer(self, layer_out)
+
+    def refine(self, layer_out: "Piecewise") -> None:
+        """h-refinement into `layer_out` (reference :352-356)."""
+        from .refinement import refine_polynomial_layer
+        refine_polynomial_layer(layer_in=self, layer_out=layer_out)
+
 
 class PiecewiseDiscontinuous(_PiecewiseBase):
     """Discontinuous piecewise polynomial: every segment owns its n nodes."""
     _discontinuous = True
+
+    def interpolate(self, layer_out: "PiecewiseDiscontinuous") -> None:
+        from .refinement import interpolate_polynomial_layer
+        interpolate_polynomial_layer(layer_in=self, layer_out=layer_out)
+
+    def refine(self, layer_out: "PiecewiseDiscontinuous") -> None:
+        from .refinement import refine_discontinuous_polynomial_layer
+        refine_discontinuous_polynomial_layer(layer_in=self, layer_out=layer_out)
 
 
 class PiecewisePolynomial(Piecewise):

@@ -26,5 +26,16 @@ from .FunctionalConvolution import (  # noqa: F401
     PiecewisePolynomialConvolution2d,
 )
 from .networks import HighOrderMLP  # noqa: F401
+from .refinement import (  # noqa: F401
+    hp_refine_high_order_mlp,
+    initialize_network_polynomial_layers,
+    initialize_polynomial_layer,
+    interpolate_high_order_mlp,
+    interpolate_polynomial_layer,
+    refine_discontinuous_polynomial_layer,
+    refine_polynomial_layer,
+    smooth_discontinuous_layer,
+    smooth_discontinuous_network,
+)
 
 __version__ = "0.1.0"

@@ -368,6 +368,48 @@ def main():
     nr["cases"] = np.array(nr_cases)
     np.savez_compressed(os.path.join(args.out, "row_norms.npz"), **nr)
 
+    # -------------------------------------------- p / h refinement, linear init, smoothing
+    import random as pyrandom
+    rfn = {}
+    interp_cases, refine_cases, init_cases = [], [], []
+    kinds = {"cont": R.pl.PiecewisePolynomial, "disc": R.pl.PiecewiseDiscontinuousPolynomial}
+    for kind, cls in kinds.items():
+        for (n_in, n_out, I, O, S) in [(1, 4, 3, 2, 5), (3, 5, 3, 2, 5), (5, 5, 2, 3, 2), (7, 5, 3, 2, 5), (4, 1, 2, 2, 3)]:
+            li = cls(n=n_in, in_features=I, out_features=O, segments=S)
+            lo = cls(n=n_out, in_features=I, out_features=O, segments=S)
+            with torch.no_grad():
+                li.w.copy_(torch.from_numpy(rng.uniform(-1, 1, size=tuple(li.w.shape)).astype(np.float32)))
+            R.pl.interpolate_polynomial_layer(layer_in=li, layer_out=lo)
+            name = f"interp_{kind}_{n_in}_{n_out}_S{S}"
+            rfn[name + "_w_in"], rfn[name + "_w_out"] = li.w.detach().numpy().copy(), lo.w.detach().numpy().copy()
+            rfn[name + "_meta"] = np.array([n_in, n_out, I, O, S, int(kind == "disc")], dtype=np.int64)
+            interp_cases.append(name)
+    for (n_in, n_out, S_in, S_out) in [(3, 3, 3, 9), (5, 5, 5, 5), (2, 2, 2, 12), (3, 4, 2, 6), (4, 2, 5, 3), (2, 1, 3, 4)]:
+        li = R.pl.PiecewisePolynomial(n=n_in, in_features=3, out_features=2, segments=S_in)
+        lo = R.pl.PiecewisePolynomial(n=n_out, in_features=3, out_features=2, segments=S_out)
+        with torch.no_grad():
+            li.w.copy_(torch.from_numpy(rng.uniform(-1, 1, size=tuple(li.w.shape)).astype(np.float32)))
+        R.pl.refine_polynomial_layer(layer_in=li, layer_out=lo)
+        name = f"refine_{n_in}_{n_out}_S{S_in}_{S_out}"
+        rfn[name + "_w_in"], rfn[name + "_w_out"] = li.w.detach().numpy().copy(), lo.w.detach().numpy().copy()
+        rfn[name + "_meta"] = np.array([n_in, n_out, S_in, S_out], dtype=np.int64)
+        refine_cases.append(name)
+    for kind, cls in kinds.items():
+        layer = cls(n=4, in_features=3, out_features=2, segments=5)
+        pyrandom.seed(7)
+        R.pl.initialize_polynomial_layer(layer, max_slope=1.5, max_offset=0.3)
+        rfn[f"init_{kind}_w"] = layer.w.detach().numpy().copy()
+        init_cases.append(f"init_{kind}")
+    sm = R.pl.PiecewiseDiscontinuousPolynomial(n=3, in_features=3, out_features=2, segments=5)
+    with torch.no_grad():
+        sm.w.copy_(torch.from_numpy(rng.uniform(-1, 1, size=tuple(sm.w.shape)).astype(np.float32)))
+    rfn["smooth_w_in"] = sm.w.detach().numpy().copy()
+    R.pl.smooth_discontinuous_layer(sm, 0.5)
+    rfn["smooth_w_out"] = sm.w.detach().numpy().copy()
+    rfn["interp_cases"], rfn["refine_cases"], rfn["init_cases"] = (np.array(interp_cases), np.array(refine_cases),
+                                                                  np.array(init_cases))
+    np.savez_compressed(os.path.join(args.out, "refinement.npz"), **rfn)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

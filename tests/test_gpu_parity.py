@@ -444,3 +444,37 @@ def test_mlp_with_fused_normalizations_matches_torch_expression():
         h = expr(net.model[2](h))
         y2 = net.output_layer(h)
         assert rel_err(y.detach().cpu().numpy(), y2.detach().cpu().numpy()) < MLP_TOL
+
+
+@pytest.mark.parametrize("n_in,n_out,I,O,S", [(1, 4, 3, 2, 5), (3, 5, 3, 2, 5), (5, 5, 2, 3, 2), (2, 8, 64, 48, 4)])
+@pytest.mark.parametrize("disc", [False, True])
+def test_p_refinement_invariance_on_device(n_in, n_out, I, O, S, disc):
+    """reference tests/test_refinement.py:21-44 with the CUDA layers: a layer p-refined to a higher
+    order reproduces the original function (rtol 1e-5), weights interpolated on the device."""
+    cls = hol.PiecewiseDiscontinuousPolynomial if disc else hol.PiecewisePolynomial
+    torch.manual_seed(11)
+    li = cls(n=n_in, in_features=I, out_features=O, segments=S, device=DEV)
+    lo = cls(n=n_out, in_features=I, out_features=O, segments=S, device=DEV)
+    hol.interpolate_polynomial_layer(layer_in=li, layer_out=lo)
+    x = torch.rand(64, I, device=DEV)
+    a, b = li(x).detach().cpu().numpy(), lo(x).detach().cpu().numpy()
+    assert rel_err(b, a) < TOL
+
+
+def test_h_refinement_and_mlp_refinement_on_device():
+    """reference tests/test_refinement.py:100-123 (segments 3 -> 9 keeps the function, rtol 1e-3)
+    and :55-92 (MLP-level p-refinement, rtol 1e-4)."""
+    torch.manual_seed(5)
+    li = hol.PiecewisePolynomial(n=3, in_features=4, out_features=3, segments=3, device=DEV)
+    lo = hol.PiecewisePolynomial(n=3, in_features=4, out_features=3, segments=9, device=DEV)
+    with torch.no_grad():
+        li.w.uniform_(-1, 1)
+    hol.refine_polynomial_layer(li, lo)
+    x = torch.rand(50, 4, device=DEV) * 2 - 1
+    assert rel_err(lo(x).detach().cpu().numpy(), li(x).detach().cpu().numpy()) < 1e-3
+    kw = dict(layer_type="continuous", in_width=5, out_width=3, hidden_layers=2, hidden_width=5, in_segments=2,
+              out_segments=2, hidden_segments=2, device=DEV)
+    net_in, net_out = hol.HighOrderMLP(n=2, **kw), hol.HighOrderMLP(n=3, **kw)
+    hol.interpolate_high_order_mlp(net_in, net_out)
+    x = torch.rand(20, 5, device=DEV) * 2 - 1
+    assert rel_err(net_out(x).detach().cpu().numpy(), net_in(x).detach().cpu().numpy()) < MLP_TOL

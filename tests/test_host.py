@@ -157,3 +157,51 @@ def test_variant_layers_host_side():
                                            kernel_size=3)
     assert dc.conv.weight.shape == (3, 24, 3, 3)
     assert np.array_equal(dc.conv.weight.detach().numpy(), g["init_dconv_w"])
+
+
+def test_refinement_utilities_match_reference_fixtures():
+    """the batched p / h refinement, linear initialisation and smoothing reproduce the
+    reference's loop implementations (fixture refinement.npz, PolynomialLayers.py:757-1023)."""
+    import random
+
+    import numpy as np
+    import torch
+
+    import high_order_layers_torch_b200 as hol
+    from tests.conftest import load_golden
+
+    g = load_golden("refinement.npz")
+    for name in g["interp_cases"]:
+        name = str(name)
+        n_in, n_out, I, O, S, disc = (int(v) for v in g[name + "_meta"])
+        cls = hol.PiecewiseDiscontinuousPolynomial if disc else hol.PiecewisePolynomial
+        li, lo = cls(n=n_in, in_features=I, out_features=O, segments=S), cls(n=n_out, in_features=I, out_features=O, segments=S)
+        with torch.no_grad():
+            li.w.copy_(torch.from_numpy(g[name + "_w_in"]))
+        li.interpolate(lo)
+        assert np.abs(lo.w.detach().numpy() - g[name + "_w_out"]).max() < 1e-6, name
+    for name in g["refine_cases"]:
+        name = str(name)
+        n_in, n_out, S_in, S_out = (int(v) for v in g[name + "_meta"])
+        li = hol.PiecewisePolynomial(n=n_in, in_features=3, out_features=2, segments=S_in)
+        lo = hol.PiecewisePolynomial(n=n_out, in_features=3, out_features=2, segments=S_out)
+        with torch.no_grad():
+            li.w.copy_(torch.from_numpy(g[name + "_w_in"]))
+        li.refine(lo)
+        assert np.abs(lo.w.detach().numpy() - g[name + "_w_out"]).max() < 1e-6, name
+    for kind, cls in (("cont", hol.PiecewisePolynomial), ("disc", hol.PiecewiseDiscontinuousPolynomial)):
+        layer = cls(n=4, in_features=3, out_features=2, segments=5)
+        random.seed(7)
+        hol.initialize_polynomial_layer(layer, max_slope=1.5, max_offset=0.3)
+        assert np.abs(layer.w.detach().numpy() - g[f"init_{kind}_w"]).max() < 1e-6, kind
+    sm = hol.PiecewiseDiscontinuousPolynomial(n=3, in_features=3, out_features=2, segments=5)
+    with torch.no_grad():
+        sm.w.copy_(torch.from_numpy(g["smooth_w_in"]))
+    hol.smooth_discontinuous_layer(sm, 0.5)
+    assert np.abs(sm.w.detach().numpy() - g["smooth_w_out"]).max() < 1e-6
+    import pytest
+    with pytest.raises(ValueError):
+        sm.refine(sm)
+    with pytest.raises(ValueError):
+        hol.interpolate_polynomial_layer(hol.PiecewisePolynomial(n=2, in_features=1, out_features=1, segments=2),
+                                         hol.PiecewisePolynomial(n=2, in_features=1, out_features=1, segments=3))
