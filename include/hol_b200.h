@@ -146,6 +146,13 @@ int hol_row_norm_forward_f32(int32_t kind, const float* x, float* y, float* stat
 int hol_row_norm_backward_f32(int32_t kind, const float* gy, const float* x, const float* stats,
                               float* dx, int64_t B, int32_t W, void* stream);
 
+/* ---- SparseLion step (reference sparse_optimizers/sparse_lion.py:13-92) --------
+ * One fused elementwise kernel: where grad != 0, update = sign(beta1*exp_avg + (1-beta1)*grad),
+ * p -= lr*update, exp_avg = beta2*exp_avg + (1-beta2)*grad.  `wd` is accepted and, exactly like
+ * the reference (whose decay line acts on a copy), has no effect.  In place on p and exp_avg. */
+int hol_sparse_lion_step_f32(float* p, const float* grad, float* exp_avg, int64_t count, float lr,
+                             float wd, float beta1, float beta2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -410,6 +410,23 @@ def main():
                                                                   np.array(init_cases))
     np.savez_compressed(os.path.join(args.out, "refinement.npz"), **rfn)
 
+    # -------------------------------------------- SparseLion (sparse_optimizers/sparse_lion.py)
+    from high_order_layers_torch.sparse_optimizers import SparseLion as RefSparseLion
+    sl = {}
+    p0 = rng.standard_normal(size=(4, 5, 12)).astype(np.float32)
+    par = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = RefSparseLion([par], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.1)
+    grads = []
+    for k in range(4):
+        g = (rng.standard_normal(size=p0.shape) * (rng.uniform(size=p0.shape) < 0.3)).astype(np.float32)
+        grads.append(g)
+        par.grad = torch.from_numpy(g.copy())
+        opt.step()
+    sl["p0"], sl["grads"] = p0, np.stack(grads)
+    sl["p_final"], sl["exp_avg_final"] = par.detach().numpy().copy(), opt.state[par]["exp_avg"].numpy().copy()
+    sl["hyper"] = np.array([1e-2, 0.9, 0.99, 0.1])
+    np.savez_compressed(os.path.join(args.out, "sparse_lion.npz"), **sl)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

@@ -478,3 +478,22 @@ def test_h_refinement_and_mlp_refinement_on_device():
     hol.interpolate_high_order_mlp(net_in, net_out)
     x = torch.rand(20, 5, device=DEV) * 2 - 1
     assert rel_err(net_out(x).detach().cpu().numpy(), net_in(x).detach().cpu().numpy()) < MLP_TOL
+
+
+def test_sparse_lion_fused_kernel():
+    """the fused SparseLion kernel against the reference fixture, then the reference's
+    own test (tests/test_sparse_optimizer.py:24-58): only the touched weights move."""
+    from high_order_layers_torch_b200.sparse_optimizers import SparseLion
+    from tests.test_host import _run_sparse_lion
+    _run_sparse_lion(DEV)
+    layer = hol.PiecewiseDiscontinuousPolynomial(n=2, in_features=1, out_features=1, segments=10, device=DEV)
+    optim = SparseLion(params=layer.parameters(), lr=1e-4)
+    x = torch.ones(1, 1, device=DEV) * 0.5
+    out = layer(x)
+    torch.nn.functional.mse_loss(out, torch.ones(1, 1, device=DEV) * 0.2).backward()
+    assert layer.w.grad[layer.w.grad != 0.0].shape == torch.Size([2])
+    before = layer.w.detach().clone()
+    optim.step()
+    moved = (layer.w.detach() != before)
+    assert int(moved.sum()) == 2 and torch.equal(moved, layer.w.grad != 0.0)
+    assert torch.any(torch.abs(layer(x) - out) > 0)

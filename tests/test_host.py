@@ -205,3 +205,29 @@ def test_refinement_utilities_match_reference_fixtures():
     with pytest.raises(ValueError):
         hol.interpolate_polynomial_layer(hol.PiecewisePolynomial(n=2, in_features=1, out_features=1, segments=2),
                                          hol.PiecewisePolynomial(n=2, in_features=1, out_features=1, segments=3))
+
+
+def _run_sparse_lion(device):
+    import numpy as np
+    import torch
+
+    from high_order_layers_torch_b200.sparse_optimizers import SparseLion
+    from tests.conftest import load_golden
+
+    g = load_golden("sparse_lion.npz")
+    lr, b1, b2, wd = (float(v) for v in g["hyper"])
+    par = torch.nn.Parameter(torch.from_numpy(g["p0"].copy()).to(device))
+    opt = SparseLion([par], lr=lr, betas=(b1, b2), weight_decay=wd)
+    for grad in g["grads"]:
+        par.grad = torch.from_numpy(grad.copy()).to(device)
+        opt.step()
+    assert np.abs(par.detach().cpu().numpy() - g["p_final"]).max() < 1e-6
+    assert np.abs(opt.state[par]["exp_avg"].cpu().numpy() - g["exp_avg_final"]).max() < 1e-6
+    untouched = np.all(g["grads"] == 0, axis=0)
+    assert np.array_equal(par.detach().cpu().numpy()[untouched], g["p0"][untouched])   # never decayed, never moved
+
+
+def test_sparse_lion_matches_reference_fixture_cpu():
+    """four steps of SparseLion against the reference's (sparse_lion.py:13-92),
+    including its no-op weight decay."""
+    _run_sparse_lion("cpu")
