@@ -18,6 +18,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (cute::elect_one_sync).  ptxas knows that a branch on elect.sync has
+// exactly one active thread and issues the warp-uniform instructions inside it (UTCHMMA, UBLKCP,
+// UTCBAR) directly; behind a plain `lane == 0` test it wraps EVERY one of them in an
+// ELECT / BRA.U.ANY loop, which made the MMA-issuing thread the bottleneck of all three GEMMs
+// (ncu: 81 % of its samples in those wrappers, ~2100 cycles of issue per 1440-cycle k-chunk).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
             }
         }
     } else if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 int nt;
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             // (A_PHI_MN: a_major bit 15 = MN-major)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24) |
