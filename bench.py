@@ -337,6 +337,7 @@ def run_ours(args):
     if args.batch:
         cfg["B"] = args.batch
     wl = build_workload(torch, cfg, device, rank, args)
+    wl["key"] = args.config if not (args.n or args.segments or args.batch) else None
     step = wl["step"]
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
@@ -492,6 +493,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` capture of the same command (profiles/r1c_tc_ncu_full_summary.md); keyed by
+# (config, dominant pass).  None where no capture exists.
+NCU_TRAFFIC = {
+    ("c2", "forward"): 22.096271e9 + 0.278053e9,
+    ("c2", "dx"): 7.899103e9 + 0.397953e9,
+    ("c2", "dw"): 13.179519e9 + 0.167509e9,
+}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -547,18 +558,24 @@ def measure_roofline(torch, wl, ms_per_step):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step); burst "
                                f"{peaks['bf16_tflops']}",
-                "traffic": None, "executed_tensor_flops_per_launch_set": executed, "launch_ms": acc[names[dom]],
+                "traffic": NCU_TRAFFIC.get((wl.get("key"), dom)),
+                "traffic_source": "profiles/r1c_tc_ncu_full_summary.md (ncu --set full, same command)"
+                if (wl.get("key"), dom) in NCU_TRAFFIC else None,
+                "executed_tensor_flops_per_launch_set": executed, "launch_ms": acc[names[dom]],
                 "useful": {"flops": fl, "tflops": fl / t / 1e12,
                            "note": "2*B*I*O*n useful flops of this pass; the dense segment-expanded form executes "
                                    "3*Kin/n times as many on the tensor pipe"},
                 "hbm": {"algorithmic_bytes": by, "achieved_gbs": by / t / 1e9, "frac": by / t / 1e9 / peaks["hbm_gbs"],
                         "note": hbm_note},
-                "kernel_ms": acc, "layer": layer}
+                "kernel_ms": acc, "layer": layer, "plan": ops.plan_flags(B, I, O, n, S, disc)}
     dom = max(("forward", "dx", "dw"), key=lambda k: acc[k])
     by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
     t = acc[dom] / 1e3
     achieved = by / t / 1e9
-    return {"bound": "hbm", "kernel": {"forward": "pw_fwd_kernel", "dx": "pw_dx_kernel", "dw": "pw_dw_kernel"}[dom],
+    plan = ops.plan_flags(B, I, O, n, S, disc)
+    return {"bound": "hbm", "kernel": {"forward": "pw_fwd_kernel", "dx": "pw_dx_kernel",
+                                       "dw": "pw_dw_dense_kernel" if plan["dense_dw"] else "pw_dw_kernel"}[dom],
+            "plan": plan,
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "peak_source": peaks["source"], "traffic": None,
             "algorithmic_bytes_per_launch": by, "launch_ms": acc[dom],

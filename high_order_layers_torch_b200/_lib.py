@@ -42,6 +42,7 @@ SIGNATURES = {
     "hol_row_norm_forward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "hol_row_norm_backward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "hol_sparse_lion_step_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
+    "hol_pw_plan_flags": (ctypes.c_int, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "hol_pw_launch_count": (ctypes.c_int, [ctypes.c_int, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32]),
 }
 

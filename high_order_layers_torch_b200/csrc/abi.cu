@@ -339,6 +339,13 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     return rc;
 }
 
+int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous) {
+    PwShape s;
+    if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
+    return (s.tc.fwd ? 1 : 0) | (s.tc.dx ? 2 : 0) | (s.tc.dw ? 4 : 0) | (s.dwd.enabled ? 8 : 0) |
+           ((s.tc.enabled && s.tc.share_phi) ? 16 : 0) | (s.rot ? 32 : 0);
+}
+
 int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous,
                         int32_t want_dx, int32_t want_dw, uint32_t flags) {
     PwShape s;

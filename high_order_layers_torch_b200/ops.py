@@ -388,6 +388,15 @@ def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, disco
                                            _lib.HOL_WS_PREPARED if prepared else 0)
 
 
+def plan_flags(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> dict:
+    """Which kernels the planner picks for a layer shape (hol_pw_plan_flags)."""
+    f = _lib.load().hol_pw_plan_flags(B, I, O, n, segments, int(discontinuous))
+    if f < 0:
+        raise ValueError("plan_flags: shape outside the envelope")
+    return {"tc_forward": bool(f & 1), "tc_dx": bool(f & 2), "tc_dw": bool(f & 4), "dense_dw": bool(f & 8),
+            "shared_phi": bool(f & 16), "rotated_gather": bool(f & 32)}
+
+
 def uses_tensor_cores(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> bool:
     """True when the layer shape is planned onto the tcgen05 path (csrc/tc_gemm.cu: tc_plan)."""
     lib = _lib.load()

@@ -132,6 +132,11 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
 int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
                         int32_t discontinuous, int32_t want_dx, int32_t want_dw, uint32_t flags);
 
+/* Which kernels the planner picks for a layer shape (diagnostic, used by bench.py): bit 0 / 1 / 2 =
+ * forward / dX / dW on the tcgen05 path, bit 3 = dense-register dW (narrow layers), bit 4 = the
+ * forward's Phi tiles are shared with dW, bit 5 = lane-rotated gather kernels (S > 8); -1 = bad shape. */
+int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous);
+
 /* ---- per-sample normalisations between layers ------------------------------
  * One fused kernel each way for the reference's max_abs_normalization (utils.py:8-13, used by
  * layers.py:70-81 MaxAbsNormalization), max_center_normalization (utils.py:20-28, layers.py:84-96)
