@@ -111,6 +111,7 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     ws.tc_a = s.tc.enabled ? (void*)take(s.tc.a_bytes) : nullptr;
     ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
     ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
+    ws.tc_wmean = (s.tc.enabled && s.tc.dx) ? (float*)take((size_t)s.O * s.I * sizeof(float)) : nullptr;
     ws.total = off;
     return off;
 }

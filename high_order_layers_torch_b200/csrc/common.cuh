@@ -85,6 +85,7 @@ struct PwWorkspace {
     void* tc_a;       // tensor-core path: Phi / Phi^T / gy tiles (fp16 hi/lo shared-memory images)
     void* tc_b;       // tensor-core path: W tiles
     void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|)
+    float* tc_wmean;  // tensor-core dX: mean weight of every link [O][I] (the W^T tiles hold w - mean)
     size_t total;
 };
 

@@ -128,8 +128,24 @@ __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restri
     }
 }
 
-// dX B: W^T tiles [n-tile (BN rows k = i*Kin+v)][o-chunk (64 outputs)]
-__global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restrict__ w, unsigned char* __restrict__ tiles,
+// Mean weight of every link (o, i) over its nb nodes: one warp per link.  dX only needs the weights
+// up to a constant per link -- sum_j phi'_j = 0 inside every segment -- and centred weights remove the
+// cancellation that otherwise amplifies the rounding of T = gy W^T (same-sign weights: 1e-5 -> 1e-6).
+__global__ void __launch_bounds__(256) pw_tc_link_mean_kernel(const float* __restrict__ w, float* __restrict__ wmean,
+                                                              int64_t links, int nb) {
+    const int64_t link = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (link >= links) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for (int v = lane; v < nb; v += 32) s += w[link * nb + v];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) wmean[link] = s / (float)nb;
+}
+
+// dX B: (W - link mean)^T tiles [n-tile (BN rows k = i*Kin+v)][o-chunk (64 outputs)]
+__global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restrict__ w, const float* __restrict__ wmean,
+                                                            unsigned char* __restrict__ tiles,
                                                             const TcScalars* sc, int I, int O, int nb, int Kin, int noc,
                                                             int BN) {
     const int nt = blockIdx.x, oc = blockIdx.y;
@@ -144,7 +160,9 @@ __global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restr
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-            v[e] = (o0 + e < O && i < I && col < nb) ? w[((int64_t)(o0 + e) * I + i) * nb + col] : 0.0f;
+            v[e] = (o0 + e < O && i < I && col < nb)
+                       ? w[((int64_t)(o0 + e) * I + i) * nb + col] - wmean[(int64_t)(o0 + e) * I + i]
+                       : 0.0f;
         uint4* hi = reinterpret_cast<uint4*>(base + ogl * (BN * 16) + row * 16);
         uint4* lo = reinterpret_cast<uint4*>(base + img + ogl * (BN * 16) + row * 16);
         split_store8(v, scale, hi, lo);

@@ -15,7 +15,7 @@
 // hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (dropped lo*lo term ~2^-22 relative).
 // The tensor core accumulates with round-toward-zero: every chained MMA instruction loses on
 // average half an ulp of the running sum, a bias that grows linearly with K (measured 3e-5 at
-// K = 3136).  So a TMEM accumulator only ever holds <= 36 chained instructions (bias <= 2e-6); the
+// K = 3136).  So a TMEM accumulator only ever holds <= 48 chained instructions (bias <= 2.3e-6); the
 // epilogue warps drain it into round-to-nearest fp32 register sums while the MMA warp fills the
 // other of the two TMEM accumulators.
 //
@@ -168,7 +168,16 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     if (nst < 2) return HOL_EUNSUPPORTED;
     const size_t smem = 1024 + (size_t)nst * stage;
     p.nst = nst;
-    p.flush_chunks = p.BN >= 128 ? 2 : 3;  // <= 36 chained MMA instructions per TMEM accumulator
+    // k-chunks accumulated in TMEM between drains: 4 chunks = 48 chained MMA instructions.  The tensor
+    // core accumulates with round-toward-zero (bias ~ chain length); measured against the fp64 oracle
+    // with same-sign operands (the worst case, tools/check_flush_error.py): y / dX / dW relative error
+    // 1.4e-6 / 1.7e-6 / 5e-7 at 2 chunks, 1.3e-6 / 2.3e-6 / 9e-7 at 4, while draining half as often
+    // takes the dX GEMM of C2 from 15.7 to 13.6 ms.
+    p.flush_chunks = 4;
+    if (const char* fc = getenv("HOL_TC_FLUSH")) {  // experiment knob: k-chunks per accumulator drain
+        const int v = atoi(fc);
+        if (v >= 1 && v <= 8) p.flush_chunks = v;
+    }
     p.ntile_n = ntiles_n;
     p.ntile_m = mtiles;
     p.ntiles = mtiles * ntiles_n;
@@ -197,7 +206,7 @@ int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
     const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
     const int ex = t.gen ? 0 : 1;          // Phi / Phi^T expansion kernel (absent when generated in the GEMM)
     if (kind == 0) return 2 + 1 + nl * (1 + ex);  // absmax x2, pack_w, ([expand,] gemm) per batch chunk
-    if (kind == 1) return 2 + 1 + nl * 2;         // absmax x2, pack_wt, (pack_gy, gemm)
+    if (kind == 1) return 2 + 2 + nl * 2;         // absmax x2, link mean, pack_wt, (pack_gy, gemm)
     if (t.share_phi) return 2 + 2;                // absmax x2, pack_gyt, gemm (the Phi tiles come from the forward)
     return 2 + nl * (2 + ex);                     // absmax x2, ([expand_t,] pack_gyt, gemm)
 }
@@ -337,8 +346,13 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
     if (rc != HOL_OK) return rc;
     rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
     if (rc != HOL_OK) return rc;
+    const int64_t links = (int64_t)s.O * s.I;
+    pw_tc_link_mean_kernel<<<(unsigned)((links + 7) / 8), 256, 0, st>>>(w, ws.tc_wmean, links, s.nb);
+    rc = (int)cudaGetLastError();
+    if (rc != HOL_OK) return rc;
     dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc);
-    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc, t.BNx);
+    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, ws.tc_wmean, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc,
+                                                t.BNx);
     rc = (int)cudaGetLastError();
     if (rc != HOL_OK) return rc;
     for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
