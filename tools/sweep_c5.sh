@@ -2,7 +2,7 @@
 # BASELINE config 5: I=O=4096, B=32768, n in {2,4,8} x segments in {2,8,32,64}; one JSON line per point.
 out=gpurun_out/sweep_c5.jsonl; : > $out
 for n in 2 4 8; do for S in 2 8 32 64; do
-  timeout 600 python bench.py --config c5 --n $n --segments $S --steps 2 --warmup 3 --no-cpu-baseline 2>gpurun_out/sweep_err_${n}_${S}.log | tail -1 >> $out || echo "{\"n\": $n, \"segments\": $S, \"error\": \"failed\"}" >> $out
+  timeout 600 python bench.py --config c5 --n $n --segments $S --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda 2>gpurun_out/sweep_err_${n}_${S}.log | tail -1 >> $out || echo "{\"n\": $n, \"segments\": $S, \"error\": \"failed\"}" >> $out
 done; done
 python - <<'PY'
 import json
