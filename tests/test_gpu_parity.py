@@ -497,3 +497,25 @@ def test_sparse_lion_fused_kernel():
     moved = (layer.w.detach() != before)
     assert int(moved.sum()) == 2 and torch.equal(moved, layer.w.grad != 0.0)
     assert torch.any(torch.abs(layer(x) - out) > 0)
+
+
+@pytest.mark.parametrize("kind,n,S,I,O,B", [("disc", 3, 8, 200, 96, 300), ("cont", 4, 4, 50, 10, 64),
+                                            ("cont", 4, 32, 33, 65, 300)])
+def test_backward_without_the_forward_workspace(kind, n, S, I, O, B):
+    """hol_pw_backward_f32 with flags = 0 (no HOL_WS_PREPARED): the backward prepares its own state
+    (prep, and on the shared-Phi tensor-core path the Phi tiles) in a fresh workspace."""
+    rng = np.random.default_rng(n + S + I)
+    disc = kind == "disc"
+    x = rng.uniform(-1.2, 1.2, size=(B, I)).astype(np.float32)
+    w = rng.uniform(-1, 1, size=(O, I, orc.weights_per_link(n, S, disc))).astype(np.float32)
+    gy = rng.standard_normal(size=(B, O)).astype(np.float32)
+    xt, wt, gt = t(x), t(w), t(gy)
+    ws = ops.fc_workspace(xt, wt, n, S, disc)
+    ws.fill_(0xAB)  # nothing of a forward in it
+    dx, dw = ops.pw_backward(gt, xt, wt, ws, n, S, 2.0, disc, None, True, True, False)
+    torch.cuda.synchronize()
+    nodes = ops.lobatto_nodes(n, 2.0).numpy()
+    dx64, dw64 = orc.pw_backward(gy, x, w, n, S, 2.0, disc, None, nodes=nodes)
+    assert rel_err(dx.cpu().numpy(), dx64) < TOL
+    assert rel_err(dw.cpu().numpy(), dw64) < TOL
+    check_zero_pattern(dw.cpu().numpy(), dw64)
