@@ -97,3 +97,60 @@ class PiecewiseDiscontinuousPolynomialConvolution2d(_PiecewiseConvolution2dBase)
     """Discontinuous variant: every segment owns its n nodes, C*n*segments expanded channels
     (reference FunctionalConvolution.py:522-619; expansion Basis.py:220-296)."""
     _discontinuous = True
+
+
+class _PiecewiseConvolution1dBase(nn.Module):
+    """1-d variants (reference FunctionalConvolution.py:493-519, :622-650): Expansion1d + nn.Conv1d in
+    the reference, here the fully connected kernels on unfolded rows.  Parameter ``conv.weight
+    [O, C*V, K]`` initialised by the reference's conv_wrapper recipe (uniform in +-wm/(C*V*K*K); the
+    reference's 1-d classes do not apply the constant-per-link initialisation of the 2-d ones)."""
+    _discontinuous = False
+
+    def __init__(self, n: int, segments: int, in_channels: int, kernel_size: int, length: float = 2.0,
+                 rescale_output: bool = False, periodicity: Optional[float] = None, *args, out_channels: int,
+                 stride: int = 1, padding: int = 0, dilation: int = 1, groups: int = 1,
+                 padding_mode: str = "zeros", weight_magnitude: float = 1.0, device: str = "cpu", **kwargs):
+        super().__init__()
+        name = type(self).__name__
+        if groups != 1 or padding_mode != "zeros" or isinstance(padding, str):
+            raise ValueError(f"{name}: groups != 1 / non-zero padding modes are not supported by the CUDA path")
+        if _as_int(padding, "padding") != 0:
+            raise ValueError(f"{name}: padding != 0 is not supported yet")
+        if float(length) != 2.0:
+            raise ValueError(f"{name}: only length=2.0 is supported")
+        self._n, self._segments, self._length = n, segments, length
+        self._kernel_size = _as_int(kernel_size, "kernel_size")
+        self._stride, self._dilation = _as_int(stride, "stride"), _as_int(dilation, "dilation")
+        self._nodes = n * segments if self._discontinuous else (n - 1) * segments + 1
+        self._channels = self._nodes * in_channels
+        self._out_channels = out_channels
+        self.periodicity = periodicity
+        k = self._kernel_size
+        self.conv = nn.Conv1d(in_channels=self._channels, out_channels=out_channels, kernel_size=k,
+                              stride=self._stride, padding=0, dilation=self._dilation, groups=1, bias=False)
+        in_features = self._channels * k * k          # the reference's conv_wrapper uses k*k for every rank
+        if rescale_output is False:
+            self.conv.weight.data.uniform_(-weight_magnitude / in_features, weight_magnitude / in_features)
+        elif rescale_output is True:
+            self.conv.weight.data.uniform_(-weight_magnitude, weight_magnitude)
+        self._total_in = in_channels * k * k
+        self._rescale = 1.0 / self._total_in if rescale_output is True else 1.0
+        if str(device) != "cpu":
+            self.conv.to(device)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: input is on {x.device}; this build runs on CUDA (sm_100a) "
+                               "only and has no CPU fallback")
+        return ops.piecewise_polynomial_conv1d(x, self.conv.weight, self._n, self._segments, self._kernel_size,
+                                               length=float(self._length), discontinuous=self._discontinuous,
+                                               periodicity=self.periodicity, stride=self._stride, padding=0,
+                                               dilation=self._dilation, rescale=self._rescale)
+
+
+class PiecewisePolynomialConvolution1d(_PiecewiseConvolution1dBase):
+    _discontinuous = False
+
+
+class PiecewiseDiscontinuousPolynomialConvolution1d(_PiecewiseConvolution1dBase):
+    _discontinuous = True

@@ -22,7 +22,9 @@ from .layers import (  # noqa: F401
 )
 from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial  # noqa: F401
 from .FunctionalConvolution import (  # noqa: F401
+    PiecewiseDiscontinuousPolynomialConvolution1d,
     PiecewiseDiscontinuousPolynomialConvolution2d,
+    PiecewisePolynomialConvolution1d,
     PiecewisePolynomialConvolution2d,
 )
 from .networks import HighOrderMLP  # noqa: F401

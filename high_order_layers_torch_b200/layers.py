@@ -7,7 +7,9 @@ from __future__ import annotations
 
 import torch.nn as nn
 
-from .FunctionalConvolution import PiecewiseDiscontinuousPolynomialConvolution2d, PiecewisePolynomialConvolution2d
+from .FunctionalConvolution import (PiecewiseDiscontinuousPolynomialConvolution1d,
+                                    PiecewiseDiscontinuousPolynomialConvolution2d, PiecewisePolynomialConvolution1d,
+                                    PiecewisePolynomialConvolution2d)
 from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial
 from .utils import (l2_normalization, max_abs_normalization, max_abs_normalization_last, max_abs_normalization_nd,
                     max_center_normalization, max_center_normalization_nd)
@@ -105,7 +107,9 @@ fc_layers = {
 
 convolutional_layers = {
     "continuous2d": PiecewisePolynomialConvolution2d,
+    "continuous1d": PiecewisePolynomialConvolution1d,
     "discontinuous2d": PiecewiseDiscontinuousPolynomialConvolution2d,
+    "discontinuous1d": PiecewiseDiscontinuousPolynomialConvolution1d,
 }
 
 

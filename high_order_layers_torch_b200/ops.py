@@ -381,6 +381,47 @@ def normalize_rows(x: Tensor, kind: str, eps: float = 1e-6) -> Tensor:
     return row_norm(x, NORM_KINDS[kind], float(eps))[0]
 
 
+# ------------------------------------------------------------------------------------------
+# 1-d convolution: the fully connected layer on unfolded rows (rows = B*Lo, inputs = C*K)
+# ------------------------------------------------------------------------------------------
+def conv1d_rows(x: Tensor, kernel_size: int, stride: int, dilation: int) -> Tensor:
+    """x[B, C, L] -> im2col rows [B*Lo, C*K], column c*K + k = x[b, c, lo*stride + k*dilation]."""
+    B, C, L = x.shape
+    Lo = conv_out_size(L, kernel_size, stride, 0, dilation)
+    if Lo <= 0:
+        raise ValueError("conv1d: kernel does not fit the input")
+    taps = (torch.arange(Lo, device=x.device).unsqueeze(1) * stride
+            + torch.arange(kernel_size, device=x.device).unsqueeze(0) * dilation)            # [Lo, K]
+    return x[:, :, taps].permute(0, 2, 1, 3).reshape(B * Lo, C * kernel_size)
+
+
+def conv1d_weight_as_fc(weight: Tensor, in_channels: int, nb: int) -> Tensor:
+    """conv.weight[O, C*nb, K] (expanded channel c*nb + v) -> w_fc[O, C*K, nb]."""
+    O, _, K = weight.shape
+    return weight.view(O, in_channels, nb, K).permute(0, 1, 3, 2).reshape(O, in_channels * K, nb)
+
+
+def piecewise_polynomial_conv1d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
+                                length: float = 2.0, discontinuous: bool = False,
+                                periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
+                                dilation: int = 1, rescale: float = 1.0) -> Tensor:
+    """PiecewisePolynomialConvolution1d (reference FunctionalConvolution.py:493-519, :622-650) as the
+    fully connected kernels on unfolded rows.  The unfold is a torch gather (autograd folds dX back);
+    zero padding would need the invalid-tap flag of the 2-d path and is not supported yet."""
+    if padding != 0:
+        raise ValueError("piecewise_polynomial_conv1d: padding != 0 is not supported yet")
+    if float(length) != 2.0:
+        raise ValueError("piecewise_polynomial_conv1d: only length=2.0 is supported")
+    B, C, L = x.shape
+    O = weight.shape[0]
+    nb = _nb(n, segments, discontinuous)
+    rows = conv1d_rows(x, kernel_size, stride, dilation)
+    w_fc = conv1d_weight_as_fc(weight, C, nb)
+    y_rows = piecewise_polynomial(rows, w_fc, n, segments, 2.0, discontinuous, periodicity)
+    y = y_rows.view(B, -1, O).permute(0, 2, 1)
+    return y * rescale if rescale != 1.0 else y
+
+
 def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, discontinuous: bool, want_dx: bool = True,
                  want_dw: bool = True, prepared: bool = True) -> int:
     """Kernels of this library launched by one forward (kind 0) / backward (kind 1) call of a layer."""

@@ -427,6 +427,36 @@ def main():
     sl["hyper"] = np.array([1e-2, 0.9, 0.99, 0.1])
     np.savez_compressed(os.path.join(args.out, "sparse_lion.npz"), **sl)
 
+    # -------------------------------------------- 1-d convolutions (FunctionalConvolution.py:493-650)
+    c1 = {}
+    c1_cases = []
+    kinds1 = {"cont": R.fcv.PiecewisePolynomialConvolution1d, "disc": R.fcv.PiecewiseDiscontinuousPolynomialConvolution1d}
+    for kind, cls in kinds1.items():
+        for (n, S, C, O, K, L, B, stride, dil, resc) in [(3, 4, 2, 3, 3, 11, 2, 1, 1, False), (2, 5, 3, 2, 4, 17, 2, 2, 1, True),
+                                                         (4, 2, 1, 2, 3, 20, 3, 1, 2, False), (1, 3, 2, 2, 2, 7, 1, 1, 1, False)]:
+            layer = cls(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K, stride=stride, dilation=dil,
+                        rescale_output=resc)
+            with torch.no_grad():
+                layer.conv.weight.copy_(torch.from_numpy(
+                    rng.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)))
+            x = rng.uniform(-1.2, 1.2, size=(B, C, L)).astype(np.float32)
+            xt = torch.from_numpy(x.copy()).requires_grad_(True)
+            y = layer(xt)
+            gy = rng.standard_normal(size=tuple(y.shape)).astype(np.float32)
+            y.backward(torch.from_numpy(gy))
+            name = f"{kind}_n{n}_S{S}_K{K}"
+            c1[name + "_x"], c1[name + "_w"], c1[name + "_gy"] = x, layer.conv.weight.detach().numpy().copy(), gy
+            c1[name + "_y"] = y.detach().numpy().copy()
+            c1[name + "_dx"] = np.zeros_like(x) if xt.grad is None else xt.grad.numpy().copy()
+            c1[name + "_dw"] = layer.conv.weight.grad.numpy().copy()
+            c1[name + "_meta"] = np.array([n, S, C, O, K, L, B, stride, dil, int(resc), int(kind == "disc")], dtype=np.int64)
+            c1_cases.append(name)
+    torch.manual_seed(1234)
+    c1["init_cont_w"] = R.fcv.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3,
+                                                                kernel_size=3).conv.weight.detach().numpy().copy()
+    c1["cases"] = np.array(c1_cases)
+    np.savez_compressed(os.path.join(args.out, "conv1d.npz"), **c1)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

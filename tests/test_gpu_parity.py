@@ -519,3 +519,24 @@ def test_backward_without_the_forward_workspace(kind, n, S, I, O, B):
     assert rel_err(dx.cpu().numpy(), dx64) < TOL
     assert rel_err(dw.cpu().numpy(), dw64) < TOL
     check_zero_pattern(dw.cpu().numpy(), dw64)
+
+
+def test_conv1d_golden_all_cases():
+    """PiecewisePolynomialConvolution1d / Discontinuous1d against the reference's outputs
+    and gradients (fixture conv1d.npz): the fully connected kernels on torch-unfolded rows."""
+    g = load_golden("conv1d.npz")
+    for name in g["cases"]:
+        name = str(name)
+        n, S, C, O, K, L, B, stride, dil, resc, disc = (int(v) for v in g[name + "_meta"])
+        cls = hol.PiecewiseDiscontinuousPolynomialConvolution1d if disc else hol.PiecewisePolynomialConvolution1d
+        layer = cls(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K, stride=stride, dilation=dil,
+                    rescale_output=bool(resc), device=DEV)
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name

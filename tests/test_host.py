@@ -231,3 +231,28 @@ def test_sparse_lion_matches_reference_fixture_cpu():
     """four steps of SparseLion against the reference's (sparse_lion.py:13-92),
     including its no-op weight decay."""
     _run_sparse_lion("cpu")
+
+
+def test_conv1d_unfold_mapping_and_init_match_reference():
+    """the 1-d convolution as the fully connected layer on unfolded rows: the unfold and
+    the conv.weight -> w_fc mapping are checked on CPU with the oracle standing in for the CUDA op
+    (fixture conv1d.npz from FunctionalConvolution.py:493-650), plus the initial weights for a seed."""
+    from oracle import pw_oracle as orc
+    g = load_golden("conv1d.npz")
+    for name in g["cases"]:
+        name = str(name)
+        n, S, C, O, K, L, B, stride, dil, resc, disc = (int(v) for v in g[name + "_meta"])
+        nb = n * S if disc else (n - 1) * S + 1
+        rows = ops.conv1d_rows(torch.from_numpy(g[name + "_x"]), K, stride, dil).numpy()
+        w_fc = ops.conv1d_weight_as_fc(torch.from_numpy(g[name + "_w"]), C, nb).numpy()
+        y_rows = orc.pw_forward(rows, w_fc, n, S, 2.0, bool(disc), None, nodes=ops.lobatto_nodes(n).numpy())
+        y = y_rows.reshape(B, -1, O).transpose(0, 2, 1) * (1.0 / (C * K * K) if resc else 1.0)
+        ref = g[name + "_y"]
+        assert y.shape == ref.shape, name
+        assert np.abs(y - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), name
+    torch.manual_seed(1234)
+    layer = hol.high_order_convolution_layers("continuous1d", n=3, segments=4, in_channels=2, out_channels=3,
+                                              kernel_size=3)
+    assert np.array_equal(layer.conv.weight.detach().numpy(), g["init_cont_w"])
+    with pytest.raises(ValueError):
+        hol.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3, padding=1)
