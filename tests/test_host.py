@@ -256,3 +256,35 @@ def test_conv1d_unfold_mapping_and_init_match_reference():
     assert np.array_equal(layer.conv.weight.detach().numpy(), g["init_cont_w"])
     with pytest.raises(ValueError):
         hol.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3, padding=1)
+
+
+def test_planner_sweep_is_consistent():
+    """The host-side planner (make_shape / tc_plan / dwd_plan behind the ABI queries) over a grid of
+    shapes: every supported shape gets a non-zero workspace that grows with the batch, a positive
+    launch count and a consistent set of plan flags; nothing crashes or loops (no GPU involved)."""
+    lib = _lib.load()
+    shapes = [(B, I, O, n, S, d)
+              for B in (1, 33, 256, 257, 8192, 65536, 802816)
+              for (I, O) in ((1, 1), (3, 2), (75, 6), (150, 16), (128, 10), (784, 128), (1024, 1024), (33, 65))
+              for (n, S) in ((1, 1), (2, 1), (3, 4), (5, 8), (4, 32), (10, 3), (2, 64))
+              for d in (0, 1)]
+    for (B, I, O, n, S, d) in shapes:
+        ws = lib.hol_pw_workspace_bytes(B, I, O, n, S, d)
+        assert ws > 0, (B, I, O, n, S, d)
+        assert lib.hol_pw_workspace_bytes(2 * B, I, O, n, S, d) >= ws
+        f = ops.plan_flags(B, I, O, n, S, bool(d))
+        assert not (f["dense_dw"] and f["tc_dw"])
+        assert not f["shared_phi"] or (f["tc_forward"] and f["tc_dw"])
+        if O < 32:
+            assert not (f["tc_forward"] or f["tc_dx"] or f["tc_dw"])
+            assert f["dense_dw"] == (n <= 5 and S <= 8)
+        if f["rotated_gather"]:
+            assert S > 8
+        for kind, dx, dw in ((0, 1, 1), (1, 1, 1), (1, 0, 1), (1, 1, 0)):
+            c = lib.hol_pw_launch_count(kind, B, I, O, n, S, d, dx, dw, 1)
+            expect_some = kind == 0 or dw or (dx and n > 1)   # dX of n == 1 is a memset, not a kernel
+            assert (0 < c < 64) if expect_some else c == 0, (kind, B, I, O, n, S, d, c)
+    # conv geometry
+    for (Bi, C, H, W, O, K, st, pad, dil) in ((4, 3, 32, 32, 6, 5, 1, 0, 1), (2, 6, 14, 14, 16, 5, 1, 2, 1),
+                                            (1, 1, 7, 9, 2, 3, 2, 1, 2)):
+        assert lib.hol_pw_conv2d_workspace_bytes(Bi, C, H, W, O, K, st, pad, dil, 3, 4, 0) > 0
