@@ -277,7 +277,9 @@ def test_planner_sweep_is_consistent():
         assert not f["shared_phi"] or (f["tc_forward"] and f["tc_dw"])
         if O < 32:
             assert not (f["tc_forward"] or f["tc_dx"] or f["tc_dw"])
-            assert f["dense_dw"] == (n <= 5 and S <= 8)
+            smax = 2 if S <= 2 else (4 if S <= 4 else 8)
+            nbmax = 1 if (not d and n == 1) else (n * smax if d else (n - 1) * smax + 1)
+            assert f["dense_dw"] == (n <= 5 and S <= 8 and nbmax * 4 <= 128)   # 128 accumulators per thread
         if f["rotated_gather"]:
             assert S > 8
         for kind, dx, dw in ((0, 1, 1), (1, 1, 1), (1, 0, 1), (1, 1, 0)):
