@@ -260,7 +260,7 @@ def test_conv1d_unfold_mapping_and_init_match_reference():
 
 def test_planner_sweep_is_consistent():
     """The host-side planner (make_shape / tc_plan / dwd_plan behind the ABI queries) over a grid of
-    shapes: every supported shape gets a non-zero workspace that grows with the batch, a positive
+    shapes: every supported shape gets a non-zero workspace that fits the device, a positive
     launch count and a consistent set of plan flags; nothing crashes or loops (no GPU involved)."""
     lib = _lib.load()
     shapes = [(B, I, O, n, S, d)
@@ -271,7 +271,9 @@ def test_planner_sweep_is_consistent():
     for (B, I, O, n, S, d) in shapes:
         ws = lib.hol_pw_workspace_bytes(B, I, O, n, S, d)
         assert ws > 0, (B, I, O, n, S, d)
-        assert lib.hol_pw_workspace_bytes(2 * B, I, O, n, S, d) >= ws
+        # (not monotonic in B: above 40 GiB of Phi tiles the tensor-core path switches to batch chunks)
+        assert lib.hol_pw_workspace_bytes(2 * B, I, O, n, S, d) > 0
+        assert ws < 1.2e11, (B, I, O, n, S, d, ws)      # every planned shape fits well inside 180 GB of HBM
         f = ops.plan_flags(B, I, O, n, S, bool(d))
         assert not (f["dense_dw"] and f["tc_dw"])
         assert not f["shared_phi"] or (f["tc_forward"] and f["tc_dw"])
@@ -285,7 +287,7 @@ def test_planner_sweep_is_consistent():
         for kind, dx, dw in ((0, 1, 1), (1, 1, 1), (1, 0, 1), (1, 1, 0)):
             c = lib.hol_pw_launch_count(kind, B, I, O, n, S, d, dx, dw, 1)
             expect_some = kind == 0 or dw or (dx and n > 1)   # dX of n == 1 is a memset, not a kernel
-            assert (0 < c < 64) if expect_some else c == 0, (kind, B, I, O, n, S, d, c)
+            assert (0 < c < 512) if expect_some else c == 0, (kind, B, I, O, n, S, d, c)
     # conv geometry
     for (Bi, C, H, W, O, K, st, pad, dil) in ((4, 3, 32, 32, 6, 5, 1, 0, 1), (2, 6, 14, 14, 16, 5, 1, 2, 1),
                                             (1, 1, 7, 9, 2, 3, 2, 1, 2)):
