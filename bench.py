@@ -356,9 +356,7 @@ def run_ours(args):
     # bound in eager mode: capture the whole step (forward, backward, flat-gradient allreduce) in
     # one CUDA graph and replay it.  The single-layer configs run for tens of ms and stay eager.
     graphed = False
-    # (conv nets under torchrun stay eager: c4 with graph capture hung at 2/4/8 ranks on B200 -- the
-    # capture mixes cuBLAS, NCCL and the layer kernels; not yet root-caused)
-    if args.graph == "on" or (args.graph == "auto" and (cfg["kind"] == "mlp" or (cfg["kind"] == "conv" and world == 1))):
+    if args.graph == "on" or (args.graph == "auto" and cfg["kind"] in ("mlp", "conv")):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -494,7 +492,12 @@ def run_ours(args):
         }
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: with a CUDA graph that captured the allreduce still alive,
+        # destroy_process_group() never returned at 2/4/8 ranks (the c3 line was printed, torchrun then sat
+        # until the box limit).  Every rank has passed the barrier above and rank 0 has printed its line.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
