@@ -497,7 +497,9 @@ def run_ours(args):
         # until the box limit).  Every rank has passed the barrier above and rank 0 has printed its line.
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        if graphed:
+            os._exit(0)
+        dist.destroy_process_group()  # eager runs (the default c2 workload) tear down normally
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
