@@ -206,3 +206,25 @@ def test_row_norms_match_reference():
         assert rel_err(fwd(x), g[name + "_y"]) < 1e-6, name
         # width-1 rows: the gradient is a cancellation residue (~eps), compare absolutely
         assert np.abs(bwd(gy, x) - g[name + "_dx"]).max() < 1e-6 * max(np.abs(g[name + "_dx"]).max(), 1.0), name
+
+
+def test_dx_is_invariant_under_a_constant_per_link():
+    """The tcgen05 dX GEMM runs on link-centred weights (w - mean over the link's nodes, csrc/tc_build.cuh):
+    inside every segment sum_j phi'_j = 0 (up to the rounding of the fp32 node table), so a constant per
+    (output, input) link does not change dX -- continuous and discontinuous layers, any n > 1 and S."""
+    rng = np.random.default_rng(3)
+    for disc in (False, True):
+        for n, S in ((2, 3), (3, 4), (5, 8), (8, 2)):
+            I, O, B = 6, 5, 40
+            nb = orc.weights_per_link(n, S, disc)
+            x = rng.uniform(-1.2, 1.2, size=(B, I)).astype(np.float32)
+            w = rng.uniform(-1, 1, size=(O, I, nb))
+            gy = rng.standard_normal(size=(B, O))
+            shift = rng.uniform(-5, 5, size=(O, I, 1))
+            nodes = orc.lobatto_nodes_f32(n)
+            dx0, dw0 = orc.pw_backward(gy, x, w, n, S, 2.0, disc, None, nodes=nodes)
+            dx1, dw1 = orc.pw_backward(gy, x, w + shift, n, S, 2.0, disc, None, nodes=nodes)
+            # not exactly: the reference's fp32 denominators make sum_j phi_j = 1 + O(1e-7), so a shift of
+            # 5x the weight range moves dX by ~1e-7 relative -- the size of the artefact the centring drops
+            assert np.abs(dx1 - dx0).max() < 1e-6 * np.abs(dx0).max(), (disc, n, S)
+            assert np.array_equal(dw0, dw1)   # dW does not depend on w at all
