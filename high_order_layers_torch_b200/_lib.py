@@ -14,6 +14,11 @@ from ._build import LIB_PATH
 HOL_MAX_N = 10
 HOL_MAX_SEGMENTS = 4096
 HOL_WS_PREPARED = 1
+# hol_set_plan_overrides bits (diagnostic: tests / A-B runs force a kernel family)
+HOL_PLAN_DISABLE_TENSOR_CORES = 1
+HOL_PLAN_DISABLE_DENSE_DW = 2
+HOL_PLAN_NO_SHARED_PHI = 4
+HOL_PLAN_FLUSH_SHIFT = 8
 
 _c_f32p = ctypes.c_void_p
 _lock = threading.Lock()
@@ -25,6 +30,7 @@ _i32, _i64, _f32, _vp, _sz, _u32 = (ctypes.c_int32, ctypes.c_int64, ctypes.c_flo
 SIGNATURES = {
     "hol_abi_version": (ctypes.c_int, []),
     "hol_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "hol_set_plan_overrides": (_u32, [_u32]),
     "hol_pw_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "hol_pw_segment_index_i64": (ctypes.c_int, [_vp, _vp, _i64, _i32, _f32, _f32, _vp]),
     "hol_pw_forward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _f32,

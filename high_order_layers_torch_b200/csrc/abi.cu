@@ -3,7 +3,14 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "kernels.cuh"
+
+// The one piece of process-wide state: a diagnostic mask that forces a kernel family (tests, A/B
+// runs).  Read once per call when the plan is made; 0 (the default) = the planner's own choice.
+static std::atomic<uint32_t> g_plan_overrides{0};
+uint32_t hol_plan_overrides() { return g_plan_overrides.load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -102,7 +109,8 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     const bool bucketed = !s.dwd.enabled;
     ws.order = bucketed ? (uint32_t*)take((size_t)s.I * s.Bp * sizeof(uint32_t)) : nullptr;
     ws.offs = bucketed ? (uint32_t*)take((size_t)s.I * s.nchunks * (s.Seff + 1) * sizeof(uint32_t)) : nullptr;
-    const int parts = bucketed ? s.ksplit : s.dwd.ksplit;
+    int parts = bucketed ? s.ksplit : s.dwd.ksplit;
+    if (s.tc.dw) parts = s.tc.dw_ksplit;  // tensor-core dW: batch split over several CTAs per tile
     ws.dw_part = parts > 1 ? (float*)take((size_t)parts * s.O * s.I * s.nb * sizeof(float)) : nullptr;
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
     ws.xl_img = conv ? (float*)take((size_t)conv_pixels * sizeof(float)) : nullptr;
@@ -112,6 +120,7 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
     ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
     ws.tc_wmean = (s.tc.enabled && s.tc.dx) ? (float*)take((size_t)s.O * s.I * sizeof(float)) : nullptr;
+    ws.prof = nullptr;
     ws.total = off;
     return off;
 }
@@ -126,22 +135,20 @@ int conv_out(int H, int K, int stride, int padding, int dilation) {
         if (_e != HOL_OK) return _e; \
     } while (0)
 
+// One memset per forward zeroes the device scalars of the tensor-core passes (maxima, outlier count)
+int reset_scalars(const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
+    if (!s.tc.enabled) return HOL_OK;
+    return (int)cudaMemsetAsync(ws.tc_scalars, 0, 256, st);
+}
+
 // `packed`: the gather-path weight packing (wk) in the workspace is valid
-// `prepared`: the workspace still holds the forward's state (Phi tiles on the shared-Phi path)
+// `prepared`: the workspace still holds the forward's state (Phi tiles on the shared-Phi path, max |w|
+// and the link means).
+// dW runs first: under data parallelism its all-reduce can then start while dX is still computing.
 int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, const float* w, float* dx,
                     int dx_transposed, float* dw, bool packed, bool prepared, cudaStream_t st) {
-    if (dx) {
-        if (s.n == 1) {
-            const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
-            cudaError_t e = cudaMemsetAsync(dx, 0, bytes, st);
-            if (e != cudaSuccess) return (int)e;
-        } else if (s.tc.dx) {
-            HOL_TRY(launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, dx_transposed, st));
-        } else {
-            if (!packed) HOL_TRY(launch_pack(w, s, ws, st));
-            HOL_TRY(launch_backward_dx(s, ws, gy, dx, dx_transposed, st));
-        }
-    }
+    const bool tc_dx = dx && s.n > 1 && s.tc.dx, tc_dw = dw && s.tc.dw;
+    if (tc_dx || tc_dw) HOL_TRY(launch_tc_gy_absmax(s, ws, gy, st));
     if (dw) {
         if (s.tc.dw) {
             HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, prepared && s.tc.fwd, st));
@@ -152,6 +159,18 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
             HOL_TRY(launch_backward_dw(s, ws, gy, dw, st));
         }
     }
+    if (dx) {
+        if (s.n == 1) {
+            const size_t bytes = dx_transposed ? (size_t)s.I * s.Bp * 4 : (size_t)s.B * s.I * 4;
+            cudaError_t e = cudaMemsetAsync(dx, 0, bytes, st);
+            if (e != cudaSuccess) return (int)e;
+        } else if (s.tc.dx) {
+            HOL_TRY(launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, dx_transposed, prepared && s.tc.fwd, st));
+        } else {
+            if (!packed) HOL_TRY(launch_pack(w, s, ws, st));
+            HOL_TRY(launch_backward_dx(s, ws, gy, dx, dx_transposed, st));
+        }
+    }
     return HOL_OK;
 }
 
@@ -160,6 +179,8 @@ int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, co
 extern "C" {
 
 int hol_abi_version(void) { return HOL_ABI_VERSION; }
+
+uint32_t hol_set_plan_overrides(uint32_t mask) { return g_plan_overrides.exchange(mask, std::memory_order_relaxed); }
 
 const char* hol_error_string(int code) {
     switch (code) {
@@ -197,6 +218,7 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     PwWorkspace ws;
     if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    HOL_TRY(reset_scalars(s, ws, st));
     HOL_TRY(launch_prep_fc(x, s, ws, st));
     if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w, y, st);
     HOL_TRY(launch_pack(w, s, ws, st));
@@ -206,20 +228,23 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
 int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const float* nodes_host, float* dx, float* dw,
                         int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
                         float periodicity, void* ws_ptr, size_t ws_bytes, uint32_t flags, void* stream) {
-    if (!gy || !x || !w || !nodes_host || !ws_ptr) return B == 0 && !dw ? HOL_OK : HOL_EINVAL;
-    PwShape s;
-    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
     cudaStream_t st = (cudaStream_t)stream;
-    if (B == 0) {
+    if (B == 0) {  // empty batch (its tensors have null data pointers): dX is empty, dW is all zeros
+        PwShape s0;
+        HOL_TRY(make_shape(s0, 0, I, O, n, S, discontinuous, length, periodicity, nullptr));
         if (dw) {
-            cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)O * I * s.nb * 4, st);
+            cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)O * I * s0.nb * 4, st);
             if (e != cudaSuccess) return (int)e;
         }
         return HOL_OK;
     }
+    if (!gy || !x || !w || !nodes_host || !ws_ptr) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
     PwWorkspace ws;
     if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
+        HOL_TRY(reset_scalars(s, ws, st));
         HOL_TRY(launch_prep_fc(x, s, ws, st));
     }
     return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd,
@@ -252,6 +277,7 @@ int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* no
     PwWorkspace ws;
     if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    HOL_TRY(reset_scalars(s, ws, st));
     HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
     HOL_TRY(launch_pack(w_fc, s, ws, st));
@@ -263,23 +289,26 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
                                int32_t K, int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
                                float length, int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes,
                                uint32_t flags, void* stream) {
-    if (!gy_rows || !x || !w_fc || !nodes_host || !ws_ptr) return HOL_EINVAL;
     if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return HOL_EINVAL;
     const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
     if (Ho <= 0 || Wo <= 0) return HOL_EINVAL;
-    PwShape s;
-    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
     cudaStream_t st = (cudaStream_t)stream;
-    if (s.B == 0) {
+    if (Bimg == 0) {  // empty batch: dX is empty, dW is all zeros
+        PwShape s0;
+        HOL_TRY(make_shape(s0, 0, C * K * K, O, n, S, discontinuous, length, periodicity, nullptr));
         if (dw_fc) {
-            cudaError_t e = cudaMemsetAsync(dw_fc, 0, (size_t)O * s.I * s.nb * 4, st);
+            cudaError_t e = cudaMemsetAsync(dw_fc, 0, (size_t)O * s0.I * s0.nb * 4, st);
             if (e != cudaSuccess) return (int)e;
         }
         return HOL_OK;
     }
+    if (!gy_rows || !x || !w_fc || !nodes_host || !ws_ptr) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
     PwWorkspace ws;
     if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
+        HOL_TRY(reset_scalars(s, ws, st));
         HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     }
     HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc,
@@ -303,19 +332,24 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
         if (cudaEventCreate(&ev[k]) != cudaSuccess) return (int)cudaGetLastError();
     int rc = HOL_OK;
     auto mark = [&](int k) { cudaEventRecord(ev[k], st); };
-    tc_prof_begin();
+    TcProf prof;
+    prof.count = 0;
+    ws.prof = &prof;  // the GEMM launchers record an event pair per launch
     mark(0);
-    rc = launch_prep_fc(x, s, ws, st);
+    rc = reset_scalars(s, ws, st);
+    if (rc == HOL_OK) rc = launch_prep_fc(x, s, ws, st);
     mark(1);
     if (rc == HOL_OK && !(s.tc.fwd && (s.tc.dx || n == 1))) rc = launch_pack(w, s, ws, st);
     mark(2);
     if (rc == HOL_OK) rc = s.tc.fwd ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
     mark(3);
+    if (rc == HOL_OK && ((s.tc.dx && n > 1) || s.tc.dw)) rc = launch_tc_gy_absmax(s, ws, gy, st);
     if (rc == HOL_OK) {
         if (n == 1)
             cudaMemsetAsync(dx, 0, (size_t)B * I * 4, st);
         else
-            rc = s.tc.dx ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, st) : launch_backward_dx(s, ws, gy, dx, 0, st);
+            rc = s.tc.dx ? launch_backward_dx_tc(s, ws, s.tc, w, gy, dx, 0, s.tc.fwd, st)
+                         : launch_backward_dx(s, ws, gy, dx, 0, st);
     }
     mark(4);
     if (rc == HOL_OK && !s.tc.dw && !s.dwd.enabled) rc = launch_bucket_sort(s, ws, st);
@@ -333,7 +367,7 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     }
     for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
     float g3[3];
-    tc_prof_end(g3);
+    tc_prof_end(&prof, g3);
     ms_out_host[6] = g3[0];  // tensor-core GEMM inside "forward"
     ms_out_host[7] = g3[2];  // ... inside "dx"
     ms_out_host[8] = g3[1];  // ... inside "dw"
@@ -344,7 +378,8 @@ int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int
     PwShape s;
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
     return (s.tc.fwd ? 1 : 0) | (s.tc.dx ? 2 : 0) | (s.tc.dw ? 4 : 0) | (s.dwd.enabled ? 8 : 0) |
-           ((s.tc.enabled && s.tc.share_phi) ? 16 : 0) | (s.rot ? 32 : 0);
+           ((s.tc.enabled && s.tc.share_phi) ? 16 : 0) | (s.rot ? 32 : 0) |
+           ((s.tc.dw ? (s.tc.dw_ksplit & 255) : 0) << 8);
 }
 
 int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous,
@@ -352,11 +387,13 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     PwShape s;
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
     const bool prepared = (flags & HOL_WS_PREPARED) != 0;
-    if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0) : 2);  // prep + (pack, forward)
+    if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0, false) : 2);  // prep + (pack, forward)
     int c = prepared ? 0 : 1;  // prep
-    if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1) : ((prepared && !s.tc.fwd) ? 1 : 2);
+    const bool tc_dx = want_dx && n > 1 && s.tc.dx, tc_dw = want_dw && s.tc.dw;
+    if (tc_dx || tc_dw) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
+    if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2);
     if (want_dw)
-        c += s.tc.dw ? tc_launch_count(s, s.tc, 2) + ((s.tc.share_phi && !(prepared && s.tc.fwd)) ? 1 : 0)
+        c += s.tc.dw ? tc_launch_count(s, s.tc, 2, prepared)
                      : (s.dwd.enabled ? 1 + (s.dwd.ksplit > 1 ? 1 : 0) : 2 + (s.ksplit > 1 ? 1 : 0));
     return c;
 }

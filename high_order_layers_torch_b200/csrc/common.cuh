@@ -5,10 +5,18 @@
 
 #include "hol_b200.h"
 
-// seg_t entries (uint16): segment index in the low 14 bits plus two flags.
-#define HOL_SEG_MASK 0x3fffu
+// seg_t entries (uint16): segment index in the low 12 bits (S <= 4096) plus three flags.
+#define HOL_SEG_MASK 0x0fffu
+#define HOL_SEG_OUTLIER 0x2000u  // |xl| beyond the range the split-fp16 tensor-core operands can carry: the
+                                 // tensor-core passes skip the element, an fp32 fix-up kernel adds it (tc_fixup.cu)
 #define HOL_SEG_INVALID 0x4000u  // padding row / zero-padded conv tap: contributes nothing
 #define HOL_SEG_MIRROR 0x8000u   // make_periodic took the mirrored branch: d fold / d x = -1
+
+// diagnostic plan overrides (hol_set_plan_overrides): tests and A/B runs force a kernel family
+#define HOL_OVR_DISABLE_TC HOL_PLAN_DISABLE_TENSOR_CORES
+#define HOL_OVR_DISABLE_DWD HOL_PLAN_DISABLE_DENSE_DW
+#define HOL_OVR_NO_SHARE_PHI HOL_PLAN_NO_SHARED_PHI
+#define HOL_OVR_FLUSH_SHIFT HOL_PLAN_FLUSH_SHIFT
 
 #define HOL_WARPS_SORT 8
 #define HOL_SORT_CHUNK 8192  // samples per bucket-sort CTA / dW split unit
@@ -18,22 +26,25 @@ struct BasisTab {
     float C[HOL_MAX_N];  // C[j] = 1 / prod_{m != j} (X_j - X_m)
 };
 
-// Plan of the tensor-core (tcgen05) forward for layers with few segments (tc.cu).
+// Plan of the tensor-core (tcgen05) passes for layers with few segments (tc_gemm.cu).
 struct TcPlan {
     bool enabled;             // any pass on the tensor cores
     bool fwd, dx, dw;         // per pass (thresholds fitted to the c5 sweep, see tc_plan)
-    bool gen;                 // Phi / Phi^T tiles are generated inside the GEMM (Kin >= 16), never materialised
     bool share_phi;           // Phi tiles of the WHOLE batch are built once by the forward and read again by dW
                               // (MN-major A operand), so Phi^T is never built
     int nkc_pad;              // share_phi: k-chunks per batch tile in the Phi storage (nkc rounded up to even)
     size_t phi_bytes;         // share_phi: Phi storage for the whole batch
     int Kin;                  // dense columns per input: weights per link padded to 8
-    int BN, nNT;              // output tile width and count
+    int BN, nNT;              // forward: output tile width and count
+    int BNw, nNTw;            // dW: output tile width and count
     int nkc;                  // 64-wide K chunks
     int BNx, nNTx, noc;       // dX: N tile over the dense columns (multiple of 2*Kin), its count, 64-wide output chunks
     int nMTw;                 // dW: 128-row M tiles over the dense columns
+    int dw_ksplit;            // dW: the batch (K) is split over this many CTAs per tile (partials -> dw_part)
+    int flush_chunks;         // k-chunks accumulated in TMEM between drains
     int64_t rows_per_launch;  // batch rows expanded + multiplied per launch (bounds the Phi tiles)
     size_t a_bytes, b_bytes;  // Phi tile / W tile storage
+    float xl_limit;           // |xl| above this marks the element HOL_SEG_OUTLIER (fp32 fix-up instead of the GEMM)
 };
 
 // Plan of the dense-register dW kernel for narrow layers (dwd.cu).
@@ -84,8 +95,9 @@ struct PwWorkspace {
     void* tc_phi;     // tensor-core path, share_phi: Phi tiles of the whole batch (forward -> dW)
     void* tc_a;       // tensor-core path: Phi / Phi^T / gy tiles (fp16 hi/lo shared-memory images)
     void* tc_b;       // tensor-core path: W tiles
-    void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|)
+    void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|, max |gy|, outlier count)
     float* tc_wmean;  // tensor-core dX: mean weight of every link [O][I] (the W^T tiles hold w - mean)
+    void* prof;       // HOST pointer, normally null: hol_pw_profile_f32 collects per-GEMM events here
     size_t total;
 };
 

@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(256) pw_dw_dense_kernel(const __grid_constant_
 // segment bound; NB(SMAX) * OC <= 128 accumulators.
 bool dwd_plan(int n, int S, int O, int disc, int64_t B, int I, DwdPlan& d) {
     d.enabled = false;
-    const char* off = getenv("HOL_DISABLE_DWD");
-    if (off && off[0] == '1') return false;
+    if (hol_plan_overrides() & HOL_OVR_DISABLE_DWD) return false;
     if (n > 5 || S > 8 || O >= 32 || B < 1) return false;
     const int smax = S <= 2 ? 2 : (S <= 4 ? 4 : 8);
     const int nbmax = (!disc && n == 1) ? 1 : (disc ? n * smax : (n - 1) * smax + 1);
@@ -216,7 +215,8 @@ static int launch_dwd_t(const PwShape& s, const PwWorkspace& ws, const float* gy
         p.tab = s.tab;
         const size_t smem = (size_t)p.R * p.P * sizeof(float);
         auto kern = pw_dw_dense_kernel<N, SMAX, OC, DISC>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static std::atomic<uint64_t> attr_done{0};
+        cudaError_t e = hol_ensure_max_smem(kern, attr_done);
         if (e != cudaSuccess) return (int)e;
         dim3 grid((unsigned)(s.dwd.nig * s.dwd.nog), (unsigned)s.dwd.nkg);
         kern<<<grid, 256, smem, st>>>(p);

@@ -199,7 +199,8 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
         if ((s.Bp / BT) * ((s.I + it_eff - 1) / it_eff) < 2 * 148) BT = 128;
     }
     auto kern = pw_dx_kernel<N, OT, IT, ROT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<uint64_t> attr_done{0};
+    cudaError_t e = hol_ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return (int)e;
     // input groups are walked by the CTA; grid.y only has to fill the machine (~4 CTAs per SM)
     const int ngroups = (s.I + it_eff - 1) / it_eff;

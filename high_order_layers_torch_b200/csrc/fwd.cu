@@ -189,7 +189,8 @@ static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
         while (BT > 128 && (s.Bp / BT) * s.nOT < 2 * 148) BT >>= 1;
     }
     auto kern = pw_fwd_kernel<N, OT, ROT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<uint64_t> attr_done{0};
+    cudaError_t e = hol_ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)(s.Bp / BT), (unsigned)s.nOT);
     kern<<<grid, BT, smem, st>>>(p);

@@ -1,5 +1,7 @@
 // HBM-bound helper stages: local-coordinate prep (bit-exact segment index), weight packing,
 // stable per-input bucket sort for dW, col2im for the conv input gradient.
+#include <math.h>
+
 #include "kernels.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -11,6 +13,7 @@
 // ---------------------------------------------------------------------------------------
 struct PrepConst {
     float length, half, Sf, half_per, two_per, per;
+    float xl_limit;  // tensor-core plans: |xl| above this is flagged HOL_SEG_OUTLIER (INFINITY otherwise)
     int S, periodic;
 };
 
@@ -22,6 +25,7 @@ static PrepConst make_prep_const(const PwShape& s) {
     c.half_per = s.half_per;
     c.two_per = s.two_per;
     c.per = s.periodicity;
+    c.xl_limit = s.tc.enabled ? s.tc.xl_limit : INFINITY;
     c.S = s.S;
     c.periodic = s.periodic;
     return c;
@@ -52,7 +56,31 @@ __device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& x
     float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), c.Sf), 2.0f), 1.0f);
     float de = __fsub_rn(e1, e0);
     xl = __fsub_rn(__fmul_rn(c.length, __fdiv_rn(__fsub_rn(xv, e0), de)), c.half);
+    if (fabsf(xl) > c.xl_limit) flags |= HOL_SEG_OUTLIER;  // NaN is not an outlier: it propagates like in the reference
     sg = (uint32_t)s | flags;
+}
+
+// Statistics the tensor-core passes need, gathered while the coordinates are in registers: the
+// largest |xl| among the elements that stay in the GEMM, and how many were flagged as outliers.
+// stats == nullptr on layers without a tensor-core pass.
+__device__ __forceinline__ void prep_stats(float amax, unsigned nout, unsigned* stats) {
+    if (!stats) return;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+        nout += __shfl_xor_sync(0xffffffffu, nout, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (amax > 0.0f) atomicMax(stats + 0, __float_as_uint(amax));  // TcScalars::max_xl
+        if (nout) atomicAdd(stats + 3, nout);                           // TcScalars::n_outliers
+    }
+}
+__device__ __forceinline__ void prep_track(float xl, uint32_t sg, float& amax, unsigned& nout) {
+    if (sg & HOL_SEG_OUTLIER) ++nout;
+    else if (!(sg & HOL_SEG_INVALID)) {
+        const float a = fabsf(xl);
+        if (a < 3.0e38f) amax = fmaxf(amax, a);
+    }
 }
 
 __global__ void __launch_bounds__(256) pw_segment_index_kernel(const float* __restrict__ x, int64_t* __restrict__ seg,
@@ -71,12 +99,14 @@ __global__ void __launch_bounds__(256) pw_segment_index_kernel(const float* __re
 // lanes are samples, read them coalesced).  32x32 tile through shared memory.
 __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict__ x, float* __restrict__ xl_t,
                                                          uint16_t* __restrict__ seg_t, int64_t B, int64_t Bp, int I,
-                                                         PrepConst c) {
+                                                         PrepConst c, unsigned* stats) {
     __shared__ float t_xl[32][33];
     __shared__ uint16_t t_sg[32][34];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t b0 = (int64_t)blockIdx.x * 32;
     const int i0 = blockIdx.y * 32;
+    float amax = 0.0f;
+    unsigned nout = 0;
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int64_t b = b0 + r;
@@ -84,9 +114,11 @@ __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict
         float xl = 0.0f;
         uint32_t sg = HOL_SEG_INVALID;
         if (i < I && b < B) prep_elem(x[b * I + i], c, xl, sg);
+        prep_track(xl, sg, amax, nout);
         t_xl[tx][r] = xl;
         t_sg[tx][r] = (uint16_t)sg;
     }
+    prep_stats(amax, nout, stats);
     __syncthreads();
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
@@ -107,14 +139,19 @@ struct ConvGeom {
 
 // Stage 1: the elementwise recipe once per pixel, image layout kept (NCHW).
 __global__ void __launch_bounds__(256) pw_prep_image_kernel(const float* __restrict__ x, float* __restrict__ xl_img,
-                                                            uint16_t* __restrict__ seg_img, int64_t count, PrepConst c) {
+                                                            uint16_t* __restrict__ seg_img, int64_t count, PrepConst c,
+                                                            unsigned* stats) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
-    float xl;
-    uint32_t sg;
-    prep_elem(x[e], c, xl, sg);
-    xl_img[e] = xl;
-    seg_img[e] = (uint16_t)sg;
+    float xl = 0.0f, amax = 0.0f;
+    uint32_t sg = HOL_SEG_INVALID;
+    unsigned nout = 0;
+    if (e < count) {
+        prep_elem(x[e], c, xl, sg);
+        xl_img[e] = xl;
+        seg_img[e] = (uint16_t)sg;
+    }
+    prep_track(xl, sg, amax, nout);
+    prep_stats(amax, nout, stats);
 }
 
 // Stage 2: unfold the prepared image into xl_t / seg_t [I][Bp].  One thread = one row (b, ho, wo),
@@ -300,7 +337,8 @@ int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwSh
 
 int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
     dim3 grid((unsigned)(s.Bp / 32), (unsigned)((s.I + 31) / 32));
-    pw_prep_fc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s));
+    pw_prep_fc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s),
+                                                    (unsigned*)ws.tc_scalars);
     return (int)cudaGetLastError();
 }
 
@@ -310,7 +348,7 @@ int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, in
     const int64_t count = Bimg * C * H * W;
     if (count > 0) {
         pw_prep_image_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, ws.xl_img, ws.seg_img, count,
-                                                                              make_prep_const(s));
+                                                                              make_prep_const(s), (unsigned*)ws.tc_scalars);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
@@ -336,7 +374,8 @@ int launch_pack(const float* w, const PwShape& s, const PwWorkspace& ws, cudaStr
 int launch_bucket_sort(const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
     const size_t smem = (size_t)HOL_WARPS_SORT * s.Seff * sizeof(uint32_t);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pw_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static std::atomic<uint64_t> attr_done{0};
+        cudaError_t e = hol_ensure_max_smem(pw_bucket_sort_kernel, attr_done);
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid((unsigned)s.nchunks, (unsigned)s.I);

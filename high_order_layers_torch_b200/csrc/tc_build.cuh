@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restri
             ok = false;
             if (i < I && b < Bp) {
                 const uint32_t sg = seg_t[(int64_t)i * Bp + b];
-                ok = !(sg & HOL_SEG_INVALID);
+                ok = !(sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER));
                 a0 = (int)(sg & HOL_SEG_MASK) * stride;
                 lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
             }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) pw_tc_expand_t_kernel(const float* __rest
             for (int e = 0; e < 8; ++e) {
                 const uint32_t sg = (sw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
                 const int j = v - (int)(sg & HOL_SEG_MASK) * stride;
-                if (!(sg & HOL_SEG_INVALID) && j >= 0 && j < N) {
+                if (!(sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) && j >= 0 && j < N) {
                     float prod = 1.0f, cj = 0.0f;
 #pragma unroll
                     for (int m = 0; m < N; ++m) {
@@ -128,19 +128,29 @@ __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restri
     }
 }
 
-// Mean weight of every link (o, i) over its nb nodes: one warp per link.  dX only needs the weights
-// up to a constant per link -- sum_j phi'_j = 0 inside every segment -- and centred weights remove the
-// cancellation that otherwise amplifies the rounding of T = gy W^T (same-sign weights: 1e-5 -> 1e-6).
-__global__ void __launch_bounds__(256) pw_tc_link_mean_kernel(const float* __restrict__ w, float* __restrict__ wmean,
-                                                              int64_t links, int nb) {
-    const int64_t link = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (link >= links) return;
+// One pass over the weights in the forward: the mean of every link (o, i) over its nb nodes (one warp
+// per link) and max |w|.  dX only needs the weights up to a constant per link -- sum_j phi'_j = 0 inside
+// every segment -- and centred weights remove the cancellation that otherwise amplifies the rounding
+// of T = gy W^T (same-sign weights: 1e-5 -> 1e-6); max |w| sets the power-of-two scale of the W tiles.
+__global__ void __launch_bounds__(256) pw_tc_wstats_kernel(const float* __restrict__ w, float* __restrict__ wmean,
+                                                           unsigned* max_w, int64_t links, int nb) {
     const int lane = threadIdx.x & 31;
-    float s = 0.0f;
-    for (int v = lane; v < nb; v += 32) s += w[link * nb + v];
+    float amax = 0.0f;
+    for (int64_t link = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); link < links; link += (int64_t)gridDim.x * 8) {
+        float s = 0.0f;
+        for (int v = lane; v < nb; v += 32) {
+            const float x = w[link * nb + v];
+            s += x;
+            const float a = fabsf(x);
+            if (a < 3.0e38f) amax = fmaxf(amax, a);
+        }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if (lane == 0) wmean[link] = s / (float)nb;
+        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0 && wmean) wmean[link] = s / (float)nb;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+    if (lane == 0 && amax > 0.0f) atomicMax(max_w, __float_as_uint(amax));
 }
 
 // dX B: (W - link mean)^T tiles [n-tile (BN rows k = i*Kin+v)][o-chunk (64 outputs)]

@@ -21,53 +21,82 @@
 //
 // Operands are stored in global memory as ready-made shared-memory images (K-major, no-swizzle
 // UMMA core-matrix layout: [k/8][row][8 x fp16]), so one 1-D TMA bulk copy per operand per
-// pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 =
+// pipeline stage fills the stage -- no tensor maps.  Warp roles: warp 0 = producer, warp 1 =
 // MMA issuer (one elected lane), warps 2-9 = epilogue (tcgen05.ld -> fp32 register sums -> global).
+//
+// Elements whose |xl| is beyond what the fp16 tiles can carry are left out of the tiles and added
+// in fp32 by the fix-up kernels (tc_fixup.cuh), so samples stay independent of one another.
 #include <string.h>
 
 #include "tc_build.cuh"
 
+#include "tc_fixup.cuh"
 #include "tc_kernel.cuh"
 
 // ---------------------------------------------------------------------------------------
 // planning + launch
 // ---------------------------------------------------------------------------------------
-static int tc_bn_for(int O) { return O > 128 ? 256 : (O > 64 ? 128 : 64); }
+static int sm_count() {
+    static std::atomic<int> cached{0};
+    int n = cached.load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    int dev = 0;
+    n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cached.store(n, std::memory_order_relaxed);
+    return n;
+}
+
+// Output tile width.  A 128 x BN x 16 MMA takes ~BN/2 cycles down to BN = 128; at BN = 64 the shared-
+// memory read of the A tile binds (~48 instead of 32 cycles).  The forward has no split over K, so when
+// the batch gives too few tiles for the 148 SMs a narrower tile that doubles the CTA count wins.
+static int tc_bn_for(int O, int64_t mtiles, bool may_shrink) {
+    const int bn_max = O > 128 ? 256 : (O > 64 ? 128 : 64);
+    if (!may_shrink) return bn_max;
+    int best = bn_max;
+    double best_cost = 1e30;
+    for (int bn = bn_max; bn >= 64; bn >>= 1) {
+        const int64_t tiles = mtiles * ((O + bn - 1) / bn);
+        const double waves = (double)((tiles + 147) / 148);
+        const double cost = waves * (bn == 256 ? 1.0 : (bn == 128 ? 0.5 : 0.375));
+        if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
+    }
+    return best;
+}
 
 bool tc_plan(const PwShape& s, TcPlan& t) {
-    t.enabled = t.fwd = t.dx = t.dw = false;
-    const char* off = getenv("HOL_DISABLE_TC");
-    if (off && off[0] == '1') return false;
+    memset(&t, 0, sizeof(t));
+    const uint32_t ovr = hol_plan_overrides();
+    if (ovr & HOL_OVR_DISABLE_TC) return false;
     t.Kin = (s.nb + 7) / 8 * 8;
     if (s.O < 32 || s.I * (int64_t)t.Kin < 256) return false;  // too narrow to be worth a tile
     // The dense form costs 3*Kin tensor MACs per n useful fp32 FMAs, so its time grows with Kin (i.e.
     // with the segment count) while the gather kernels' does not.  Cross-over points measured on
-    // B200 (c5 sweep, profiles/r1_sweep_c5.md): forward/dX gather run at ~7-16 TFLOP/s useful, the
+    // B200 (c5 sweep, profiles/r1c_sweep_c5.jsonl): forward/dX gather run at ~7-16 TFLOP/s useful, the
     // bucketed dW gather at ~25-40, the tensor path at ~1.3 PFLOP/s executed.
     t.fwd = t.Kin <= 40 * s.n;
     t.dx = t.fwd && t.Kin <= 128 && s.n > 1;  // the dX epilogue keeps whole inputs per thread (Kin <= 128)
     t.dw = t.Kin <= 44 + 7 * s.n;
     if (!t.fwd && !t.dw) return false;
-    t.BN = tc_bn_for(s.O);
-    t.nNT = (s.O + t.BN - 1) / t.BN;
     const int64_t K = (int64_t)s.I * t.Kin;
+    const int64_t mtiles_all = (s.Bp + TC_BM - 1) / TC_BM;
     t.nkc = (int)((K + TC_BK - 1) / TC_BK);
+    t.BN = tc_bn_for(s.O, mtiles_all, true);
+    t.nNT = (s.O + t.BN - 1) / t.BN;
     // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kin (and of 16), <= 256
     t.BNx = t.Kin <= 128 ? (256 / (2 * t.Kin)) * (2 * t.Kin) : 256;
     t.nNTx = (int)((K + t.BNx - 1) / t.BNx);
     t.noc = (s.O + TC_BK - 1) / TC_BK;
-    // dW: M tiles over the dense columns
+    // dW: M tiles over the dense columns; when they are too few to fill the GPU the batch (K) is split
     t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
-    // In-kernel generation of the Phi / Phi^T tiles (two generator warps, <= TC_GEN_PMAX (sample, input)
-    // pairs per thread and k-chunk, Kin >= 16).  Measured on B200 at C2 it is generator-bound (forward
-    // GEMM 36.9 ms against 11.6 ms with materialised tiles, dW 31.7 against 11.8), so it is opt-in
-    // (HOL_TC_GEN=1) until the generator keeps up with the MMA warp; the default materialises the tiles.
-    const char* gen = getenv("HOL_TC_GEN");
-    t.gen = gen && gen[0] == '1' && t.Kin >= 16;
-    // rows per launch: everything at once when the operand is generated in the kernel, else bound the
-    // Phi tiles to ~8 GiB
+    t.BNw = tc_bn_for(s.O, t.nMTw, false);
+    t.nNTw = (s.O + t.BNw - 1) / t.BNw;
+    t.flush_chunks = 4;
+    if (const int fc = (int)((ovr >> HOL_OVR_FLUSH_SHIFT) & 15u)) t.flush_chunks = fc > 8 ? 8 : fc;
+    // rows per launch: bound the Phi tiles to ~8 GiB
     int64_t rows = s.Bp;
-    if (!t.gen) {
+    {
         const int64_t bytes_per_row = (int64_t)t.nkc * TC_BK * 2 * 2;
         rows = (int64_t)(8ll << 30) / bytes_per_row / 512 * 512;
         if (rows < 512) return false;
@@ -76,13 +105,10 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     // Shared Phi: when forward and dW both run on the tensor cores, the forward materialises the Phi
     // tiles of the WHOLE batch once and dW reads the same tiles as its MN-major A operand -- no Phi^T
     // builder, no batch chunking.  Bounded to 40 GiB of tiles; larger layers keep the chunked scheme.
-    t.share_phi = false;
     t.nkc_pad = (t.nkc + 1) & ~1;
-    t.phi_bytes = 0;
     {
-        const char* off2 = getenv("HOL_TC_SHARE_PHI");
-        const size_t all = (size_t)((s.Bp + TC_BM - 1) / TC_BM) * t.nkc_pad * 2 * TC_A_IMG;
-        if (!(off2 && off2[0] == '0') && t.fwd && t.dw && !t.gen && all <= ((size_t)40 << 30)) {
+        const size_t all = (size_t)mtiles_all * t.nkc_pad * 2 * TC_A_IMG;
+        if (!(ovr & HOL_OVR_NO_SHARE_PHI) && t.fwd && t.dw && all <= ((size_t)40 << 30)) {
             t.share_phi = true;
             t.phi_bytes = all;
             rows = s.Bp;
@@ -90,25 +116,36 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     }
     rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
     t.rows_per_launch = rows;
+    t.dw_ksplit = 1;
+    if (t.share_phi && t.dw) {
+        const int64_t tiles = (int64_t)(t.nkc_pad / 2) * t.nNTw;
+        const int64_t nbc = (s.Bp + TC_BK - 1) / TC_BK;  // 64-sample stages
+        int64_t ks = sm_count() / tiles;
+        if (ks > nbc / 8) ks = nbc / 8;  // at least 8 stages per split
+        if (ks > 16) ks = 16;
+        if (ks >= 2) t.dw_ksplit = (int)ks;
+    }
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
-    size_t a = (t.gen || t.share_phi) ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
-    const size_t a_t = (t.gen || t.share_phi) ? 0 : (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;  // Phi^T
-    const size_t a_gy = t.dx ? mtiles * t.noc * 2 * TC_A_IMG : 0;                 // gy
+    size_t a = t.share_phi ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
+    const size_t a_t = t.share_phi ? 0 : (size_t)t.nMTw * bchunks * 2 * TC_A_IMG;  // Phi^T
+    const size_t a_gy = t.dx ? mtiles * t.noc * 2 * TC_A_IMG : 0;                  // gy
     if (a_t > a) a = a_t;
     if (a_gy > a) a = a_gy;
-    size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);           // W
-    const size_t b_gyt = (size_t)t.nNT * bchunks * 2 * ((size_t)t.BN * TC_BK * 2);  // gy^T
+    size_t bb = (size_t)t.nNT * t.nkc * 2 * ((size_t)t.BN * TC_BK * 2);             // W
+    const size_t b_gyt = (size_t)t.nNTw * bchunks * 2 * ((size_t)t.BNw * TC_BK * 2);  // gy^T
     const size_t b_wt = t.dx ? (size_t)t.nNTx * t.noc * 2 * ((size_t)t.BNx * TC_BK * 2) : 0;  // W^T
     if (b_gyt > bb) bb = b_gyt;
     if (b_wt > bb) bb = b_wt;
     t.a_bytes = a > 0 ? a : 256;
     t.b_bytes = bb;
+    t.xl_limit = tc_xl_limit(s.tab, s.n);
     t.enabled = true;
     return true;
 }
 
 static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws, const TcPlan& t) {
+    memset(&p, 0, sizeof(p));
     p.a_tiles = (const unsigned char*)ws.tc_a;
     p.b_tiles = (const unsigned char*)ws.tc_b;
     p.sc = (const TcScalars*)ws.tc_scalars;
@@ -120,47 +157,31 @@ static void fill_common(TcGemmParams& p, const PwShape& s, const PwWorkspace& ws
     p.nb = s.nb;
     p.Kin = t.Kin;
     p.stride = s.stride;
+    p.nseg = s.Seff;
     p.transposed = 0;
     p.length = s.length;
     p.Sf = (float)s.S;
     p.tab = s.tab;
+    p.flush_chunks = t.flush_chunks;
+    p.ksplit = 1;
     p.a_nkc = 0;  // set by the launchers
 }
 
-// diagnostic timing of the GEMM launches (only while hol_pw_profile_f32 runs on this thread)
-struct TcProf {
-    int active, count;
-    cudaEvent_t ev[48][2];
-    int kind[48];
-};
-static thread_local TcProf g_prof = {0, 0, {}, {}};
-
-void tc_prof_begin() {
-    g_prof.active = 1;
-    g_prof.count = 0;
-}
-// ms3[k] = summed duration of the GEMM launches with epilogue k (EPI_Y, EPI_DW, EPI_DX); call after a sync
-void tc_prof_end(float* ms3) {
+// diagnostic timing of the GEMM launches: hol_pw_profile_f32 hands a TcProf through PwWorkspace::prof
+void tc_prof_end(TcProf* prof, float* ms3) {
     ms3[0] = ms3[1] = ms3[2] = 0.0f;
-    for (int k = 0; k < g_prof.count; ++k) {
+    for (int k = 0; k < prof->count; ++k) {
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, g_prof.ev[k][0], g_prof.ev[k][1]) == cudaSuccess) ms3[g_prof.kind[k]] += ms;
-        cudaEventDestroy(g_prof.ev[k][0]);
-        cudaEventDestroy(g_prof.ev[k][1]);
+        if (cudaEventElapsedTime(&ms, prof->ev[k][0], prof->ev[k][1]) == cudaSuccess) ms3[prof->kind[k]] += ms;
+        cudaEventDestroy(prof->ev[k][0]);
+        cudaEventDestroy(prof->ev[k][1]);
     }
-    g_prof.active = 0;
-    g_prof.count = 0;
-}
-
-static int sm_count() {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
+    prof->count = 0;
 }
 
 template <int EPI, int N, int AMODE>
-static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_t st) {
-    constexpr bool GEN = AMODE == A_GEN;
+static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, int ksplit, TcProf* prof, cudaStream_t st) {
+    static std::atomic<uint64_t> attr_done{0};
     if (p.a_nkc == 0) p.a_nkc = p.nkc;
     const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
     int nst = (HOL_SMEM_BUDGET - 1024) / stage;
@@ -168,47 +189,47 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, cudaStream_
     if (nst < 2) return HOL_EUNSUPPORTED;
     const size_t smem = 1024 + (size_t)nst * stage;
     p.nst = nst;
-    // k-chunks accumulated in TMEM between drains: 4 chunks = 48 chained MMA instructions.  The tensor
-    // core accumulates with round-toward-zero (bias ~ chain length); measured against the fp64 oracle
-    // with same-sign operands (the worst case, tools/check_flush_error.py): y / dX / dW relative error
-    // 1.4e-6 / 1.7e-6 / 5e-7 at 2 chunks, 1.3e-6 / 2.3e-6 / 9e-7 at 4, while draining half as often
+    // flush_chunks = k-chunks accumulated in TMEM between drains: 4 chunks = 48 chained MMA instructions.
+    // The tensor core accumulates with round-toward-zero (bias ~ chain length); measured against the fp64
+    // oracle with same-sign operands (the worst case, tools/check_flush_error.py): y / dX / dW relative
+    // error 1.4e-6 / 1.7e-6 / 5e-7 at 2 chunks, 1.3e-6 / 2.3e-6 / 9e-7 at 4, while draining half as often
     // takes the dX GEMM of C2 from 15.7 to 13.6 ms.
-    p.flush_chunks = 4;
-    if (const char* fc = getenv("HOL_TC_FLUSH")) {  // experiment knob: k-chunks per accumulator drain
-        const int v = atoi(fc);
-        if (v >= 1 && v <= 8) p.flush_chunks = v;
-    }
     p.ntile_n = ntiles_n;
     p.ntile_m = mtiles;
     p.ntiles = mtiles * ntiles_n;
+    p.ksplit = ksplit < 1 ? 1 : ksplit;
+    p.kc_per_split = (p.nkc + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (p.nkc + p.kc_per_split - 1) / p.kc_per_split;  // no empty work items
+    p.nitems = p.ntiles * p.ksplit;
     p.group_m = ntiles_n >= 12 ? 12 : (148 + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
     if (p.group_m > mtiles) p.group_m = (int)mtiles;
     if (p.group_m < 1) p.group_m = 1;
     auto kern = pw_tc_gemm_kernel<EPI, N, AMODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = hol_ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return (int)e;
     const int64_t sms = sm_count();
-    const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);  // persistent: one CTA per SM
-    const bool prof = g_prof.active && g_prof.count < 48;
-    if (prof) {
-        cudaEventCreate(&g_prof.ev[g_prof.count][0]);
-        cudaEventCreate(&g_prof.ev[g_prof.count][1]);
-        g_prof.kind[g_prof.count] = EPI;
-        cudaEventRecord(g_prof.ev[g_prof.count][0], st);
+    const unsigned grid = (unsigned)(p.nitems < sms ? p.nitems : sms);  // persistent: one CTA per SM
+    const bool rec = prof && prof->count < 48;
+    if (rec) {
+        cudaEventCreate(&prof->ev[prof->count][0]);
+        cudaEventCreate(&prof->ev[prof->count][1]);
+        prof->kind[prof->count] = EPI;
+        cudaEventRecord(prof->ev[prof->count][0], st);
     }
-    kern<<<grid, GEN ? 384 : 320, smem, st>>>(p);
-    if (prof) cudaEventRecord(g_prof.ev[g_prof.count++][1], st);
+    kern<<<grid, TC_THREADS, smem, st>>>(p);
+    if (rec) cudaEventRecord(prof->ev[prof->count++][1], st);
     return (int)cudaGetLastError();
 }
 
-// kernels of ours per call (bench.py's gpu_launches): kind 0 forward, 1 dX, 2 dW (prep not included)
-int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
+// kernels of ours per call (bench.py's gpu_launches): kind 0 forward, 1 dX, 2 dW, 3 the shared
+// max|gy| pass of a backward with any tensor-core part (prep not included)
+int tc_launch_count(const PwShape& s, const TcPlan& t, int kind, bool prepared) {
     const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
-    const int ex = t.gen ? 0 : 1;          // Phi / Phi^T expansion kernel (absent when generated in the GEMM)
-    if (kind == 0) return 2 + 1 + nl * (1 + ex);  // absmax x2, pack_w, ([expand,] gemm) per batch chunk
-    if (kind == 1) return 2 + 2 + nl * 2;         // absmax x2, link mean, pack_wt, (pack_gy, gemm)
-    if (t.share_phi) return 2 + 2;                // absmax x2, pack_gyt, gemm (the Phi tiles come from the forward)
-    return 2 + nl * (2 + ex);                     // absmax x2, ([expand_t,] pack_gyt, gemm)
+    if (kind == 0) return 2 + nl * 2 + 1;                          // wstats, pack_w, (expand, gemm) per batch chunk, fix_y
+    if (kind == 1) return (prepared ? 0 : 1) + 1 + nl * 2 + 1;     // [wstats], pack_wt, (pack_gy, gemm), fix_dx
+    if (kind == 3) return 1;
+    if (t.share_phi) return (prepared && t.fwd ? 0 : 1) + 2 + (t.dw_ksplit > 1 ? 1 : 0) + 1;  // [expand], pack_gyt, gemm, [reduce], fix_dw
+    return nl * 3 + 1;                                             // (expand_t, pack_gyt, gemm), fix_dw
 }
 
 #define DISPATCH_N(n, CALL)                       \
@@ -226,18 +247,61 @@ int tc_launch_count(const PwShape& s, const TcPlan& t, int kind) {
         default: rc = HOL_EUNSUPPORTED;           \
     }
 
-static int tc_absmax(const float* v, int64_t count, unsigned* out, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned), st);
-    if (e != cudaSuccess) return (int)e;
-    pw_absmax_kernel<<<148 * 4, 256, 0, st>>>(v, count, out);
+static void fill_fix(FixParams& f, const PwShape& s, const PwWorkspace& ws, const float* w, const float* gy, float* out,
+                     int transposed) {
+    f.xl_t = ws.xl_t;
+    f.seg_t = ws.seg_t;
+    f.w = w;
+    f.gy = gy;
+    f.out = out;
+    f.sc = (const TcScalars*)ws.tc_scalars;
+    f.B = s.B;
+    f.Bp = s.Bp;
+    f.I = s.I;
+    f.O = s.O;
+    f.nb = s.nb;
+    f.stride = s.stride;
+    f.n = s.n;
+    f.transposed = transposed;
+    f.length = s.length;
+    f.Sf = (float)s.S;
+    f.tab = s.tab;
+}
+
+// max |w| and the link means (one pass over the weights; the forward leaves both in the workspace)
+int launch_tc_wstats(const PwShape& s, const PwWorkspace& ws, const float* w, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    const int64_t links = (int64_t)s.O * s.I;
+    int64_t blocks = (links + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pw_tc_wstats_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, ws.tc_wmean, &sc->max_w, links, s.nb);
     return (int)cudaGetLastError();
+}
+
+int launch_tc_gy_absmax(const PwShape& s, const PwWorkspace& ws, const float* gy, cudaStream_t st) {
+    TcScalars* sc = (TcScalars*)ws.tc_scalars;
+    const int64_t count = s.B * (int64_t)s.O;
+    int64_t blocks = (count + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    pw_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(gy, count, &sc->max_gy);
+    return (int)cudaGetLastError();
+}
+
+static int launch_expand(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, unsigned char* phi, int64_t row0,
+                         int64_t rows, int ekc, cudaStream_t st) {
+    const TcScalars* sc = (const TcScalars*)ws.tc_scalars;
+    dim3 egrid((unsigned)(rows / TC_BM), (unsigned)ekc);
+    int rc = HOL_OK;
+#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, phi, sc, s.Bp, row0, s.I, t.Kin, ekc, s.stride, s.tab), (int)cudaGetLastError())
+    DISPATCH_N(s.n, EXPAND)
+#undef EXPAND
+    return rc;
 }
 
 int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
-    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
-    if (rc != HOL_OK) return rc;
-    rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
+    int rc = launch_tc_wstats(s, ws, w, st);
     if (rc != HOL_OK) return rc;
     dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc);
     pw_tc_pack_w_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.nkc, t.BN);
@@ -249,13 +313,7 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         // shared Phi: one launch builds the tiles of the whole batch (k-chunks padded to even with zero tiles)
         const int ekc = t.share_phi ? t.nkc_pad : t.nkc;
         unsigned char* phi = (unsigned char*)(t.share_phi ? ws.tc_phi : ws.tc_a);
-        dim3 egrid((unsigned)(rows / TC_BM), (unsigned)ekc);
-        rc = HOL_OK;
-        if (!t.gen) {
-#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, phi, sc, s.Bp, row0, s.I, t.Kin, ekc, s.stride, s.tab), (int)cudaGetLastError())
-            DISPATCH_N(s.n, EXPAND)
-#undef EXPAND
-        }
+        rc = launch_expand(s, ws, t, phi, row0, rows, ekc, st);
         if (rc != HOL_OK) return rc;
         TcGemmParams p;
         fill_common(p, s, ws, t);
@@ -268,88 +326,93 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         p.nkc = t.nkc;
         p.a_nkc = ekc;
         p.a_tiles = phi;
-        rc = t.gen ? launch_gemm<EPI_Y, 0, A_GEN>(p, rows / TC_BM, t.nNT, st)
-                   : launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, st);
+        rc = launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, 1, (TcProf*)ws.prof, st);
         if (rc != HOL_OK) return rc;
     }
-    return HOL_OK;
+    FixParams f;
+    fill_fix(f, s, ws, w, nullptr, y, 0);
+    pw_tc_fix_rows_kernel<false><<<(unsigned)((s.B + 255) / 256), 256, 0, st>>>(f);
+    return (int)cudaGetLastError();
 }
 
+// `gy` statistics (TcScalars::max_gy) must have been taken by launch_tc_gy_absmax before this call
 int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* gy, float* dw,
                           bool phi_valid, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
-    int rc = tc_absmax(ws.xl_t, (int64_t)s.I * s.Bp, &sc->max_xl, st);
-    if (rc != HOL_OK) return rc;
-    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
-    if (rc != HOL_OK) return rc;
+    int rc = HOL_OK;
+    FixParams f;
+    fill_fix(f, s, ws, nullptr, gy, dw, 0);
     if (t.share_phi) {
         const int64_t mtiles = (s.Bp + TC_BM - 1) / TC_BM;
         if (!phi_valid) {  // backward without the forward's workspace: build the Phi tiles first
-            dim3 egrid((unsigned)mtiles, (unsigned)t.nkc_pad);
-#define EXPAND(NN) (pw_tc_expand_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_phi, sc, s.Bp, (int64_t)0, s.I, t.Kin, t.nkc_pad, s.stride, s.tab), (int)cudaGetLastError())
-            DISPATCH_N(s.n, EXPAND)
-#undef EXPAND
+            rc = launch_expand(s, ws, t, (unsigned char*)ws.tc_phi, 0, mtiles * TC_BM, t.nkc_pad, st);
             if (rc != HOL_OK) return rc;
         }
         const int nbc = (int)((s.Bp + TC_BK - 1) / TC_BK);
-        dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
-        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, (int64_t)0, s.O, nbc, t.BN);
+        dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc);
+        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, (int64_t)0, s.O, nbc, t.BNw);
         rc = (int)cudaGetLastError();
         if (rc != HOL_OK) return rc;
         TcGemmParams p;
         fill_common(p, s, ws, t);
         p.a_tiles = (const unsigned char*)ws.tc_phi;
         p.a_nkc = t.nkc_pad;
-        p.out = dw;
+        const bool split = t.dw_ksplit > 1;
+        p.out = split ? ws.dw_part : dw;
+        p.part_stride = (int64_t)s.O * s.I * s.nb;
         p.row0 = 0;
         p.rows_valid = 0;
-        p.BN = t.BN;
+        p.BN = t.BNw;
         p.n_valid = s.O;
         p.ld = 0;
         p.nkc = nbc;  // 64-sample stages: stage sc = samples 64*(sc & 1).. of batch tile sc >> 1
-        return launch_gemm<EPI_DW, 0, A_PHI_MN>(p, t.nkc_pad / 2, t.nNT, st);
-    }
-    for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
-        int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
-        const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
-        dim3 egrid((unsigned)t.nMTw, (unsigned)nbc);
-        rc = HOL_OK;
-        if (!t.gen) {
+        rc = launch_gemm<EPI_DW, 0, A_PHI_MN>(p, t.nkc_pad / 2, t.nNTw, t.dw_ksplit, (TcProf*)ws.prof, st);
+        if (rc != HOL_OK) return rc;
+        if (split) {
+            const int ks = (nbc + ((nbc + t.dw_ksplit - 1) / t.dw_ksplit) - 1) / ((nbc + t.dw_ksplit - 1) / t.dw_ksplit);
+            rc = launch_dw_reduce(ws.dw_part, dw, (int64_t)s.O * s.I * s.nb, ks, st);
+            if (rc != HOL_OK) return rc;
+        }
+    } else {
+        for (int64_t row0 = 0; row0 < s.Bp; row0 += t.rows_per_launch) {
+            int64_t rows = s.Bp - row0 < t.rows_per_launch ? s.Bp - row0 : t.rows_per_launch;
+            const int nbc = (int)((rows + TC_BK - 1) / TC_BK);
+            dim3 egrid((unsigned)t.nMTw, (unsigned)nbc);
+            rc = HOL_OK;
 #define EXPANDT(NN) (pw_tc_expand_t_kernel<NN><<<egrid, 256, 0, st>>>(ws.xl_t, ws.seg_t, (unsigned char*)ws.tc_a, sc, s.Bp, row0, s.I, t.Kin, nbc, s.stride, s.tab), (int)cudaGetLastError())
             DISPATCH_N(s.n, EXPANDT)
 #undef EXPANDT
+            if (rc != HOL_OK) return rc;
+            dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc);
+            pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BNw);
+            rc = (int)cudaGetLastError();
+            if (rc != HOL_OK) return rc;
+            TcGemmParams p;
+            fill_common(p, s, ws, t);
+            p.out = dw;
+            p.row0 = row0;  // > 0: accumulate onto the previous batch chunk's result
+            p.rows_valid = 0;
+            p.BN = t.BNw;
+            p.n_valid = s.O;
+            p.ld = 0;
+            p.nkc = nbc;
+            rc = launch_gemm<EPI_DW, 0, A_TILES>(p, t.nMTw, t.nNTw, 1, (TcProf*)ws.prof, st);
+            if (rc != HOL_OK) return rc;
         }
-        if (rc != HOL_OK) return rc;
-        dim3 ggrid((unsigned)t.nNT, (unsigned)nbc);
-        pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BN);
-        rc = (int)cudaGetLastError();
-        if (rc != HOL_OK) return rc;
-        TcGemmParams p;
-        fill_common(p, s, ws, t);
-        p.out = dw;
-        p.row0 = row0;  // > 0: accumulate onto the previous batch chunk's result
-        p.rows_valid = 0;
-        p.BN = t.BN;
-        p.n_valid = s.O;
-        p.ld = 0;
-        p.nkc = nbc;
-        rc = t.gen ? launch_gemm<EPI_DW, 0, A_GEN>(p, t.nMTw, t.nNT, st) : launch_gemm<EPI_DW, 0, A_TILES>(p, t.nMTw, t.nNT, st);
-        if (rc != HOL_OK) return rc;
     }
-    return HOL_OK;
+    pw_tc_fix_dw_kernel<<<(unsigned)((s.I + 7) / 8), 256, 0, st>>>(f);
+    return (int)cudaGetLastError();
 }
 
+// `wstats_valid`: TcScalars::max_w and the link means in ws.tc_wmean are those of `w` (left by the forward)
 int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
-                          float* dx, int transposed, cudaStream_t st) {
+                          float* dx, int transposed, bool wstats_valid, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
-    int rc = tc_absmax(w, (int64_t)s.O * s.I * s.nb, &sc->max_w, st);
-    if (rc != HOL_OK) return rc;
-    rc = tc_absmax(gy, s.B * (int64_t)s.O, &sc->max_gy, st);
-    if (rc != HOL_OK) return rc;
-    const int64_t links = (int64_t)s.O * s.I;
-    pw_tc_link_mean_kernel<<<(unsigned)((links + 7) / 8), 256, 0, st>>>(w, ws.tc_wmean, links, s.nb);
-    rc = (int)cudaGetLastError();
-    if (rc != HOL_OK) return rc;
+    int rc = HOL_OK;
+    if (!wstats_valid) {
+        rc = launch_tc_wstats(s, ws, w, st);
+        if (rc != HOL_OK) return rc;
+    }
     dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc);
     pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, ws.tc_wmean, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc,
                                                 t.BNx);
@@ -372,10 +435,13 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.ld = 0;
         p.nkc = t.noc;
         p.transposed = transposed;
-#define GEMM_DX(NN) launch_gemm<EPI_DX, NN, A_TILES>(p, rows / TC_BM, t.nNTx, st)
+#define GEMM_DX(NN) launch_gemm<EPI_DX, NN, A_TILES>(p, rows / TC_BM, t.nNTx, 1, (TcProf*)ws.prof, st)
         DISPATCH_N(s.n, GEMM_DX)
 #undef GEMM_DX
         if (rc != HOL_OK) return rc;
     }
-    return HOL_OK;
+    FixParams f;
+    fill_fix(f, s, ws, w, gy, dx, transposed);
+    pw_tc_fix_rows_kernel<true><<<(unsigned)((s.B + 255) / 256), 256, 0, st>>>(f);
+    return (int)cudaGetLastError();
 }

@@ -1,6 +1,5 @@
 #pragma once
-// Persistent split-fp16 tcgen05 GEMM with three epilogues and in-kernel generation of the
-// segment-expanded operand (design notes: tc_gemm.cu).
+// Persistent split-fp16 tcgen05 GEMM with three epilogues (design notes: tc_gemm.cu).
 #include "tc_build.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -54,23 +53,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-#define TC_GEN_THREADS 64  // two generator warps
-#define TC_GEN_PMAX 10     // (sample, input) pairs per generator thread and k-chunk (planner keeps it <= this)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 struct TcGemmParams {
-    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows (unused when the A operand is generated)
+    const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
     const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
-    float* out;                    // EPI_Y: y[rows][ld]; EPI_DW: dw[O][I][nb]; EPI_DX: dx[B][I] or dx_t[I][Bp]
+    float* out;                    // EPI_Y: y[rows][ld]; EPI_DW: dw[O][I][nb] (or its partials); EPI_DX: dx[B][I] or dx_t[I][Bp]
     const TcScalars* sc;
-    const float* xl_t;             // EPI_DX epilogue and the generators
+    const float* xl_t;             // EPI_DX epilogue
     const uint16_t* seg_t;
     int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
     int64_t ntiles;                // m-tiles * n-tiles
+    int64_t nitems;                // ntiles * ksplit
     int64_t ntile_m;
+    int64_t part_stride;           // EPI_DW, ksplit > 1: floats between the partial results of two k-splits
     int ntile_n, group_m;          // rasterisation: groups of group_m m-tiles, m fastest inside a group
+    int ksplit, kc_per_split;      // the k-chunks of a tile are split over ksplit work items
     int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
     int a_nkc;                     // k-chunks per m-tile in the A tile storage (>= nkc: shared Phi pads to even)
-    int I, nb, Kin, stride, transposed;
+    int I, nb, Kin, stride, nseg, transposed;
     float length, Sf;
     BasisTab tab;
 };
@@ -87,118 +97,61 @@ __device__ __forceinline__ void tile_coords(const TcGemmParams& p, int64_t tile,
     mt = first_m + local % gsize;
     nt = (int)(local / gsize);
 }
-
-// phi_j(t) for a run-time basis size n <= HOL_MAX_N (prefix/suffix products like lagrange_basis<N>;
-// fully unrolled to the maximum with guards, so everything stays in registers)
-__device__ __forceinline__ void lagrange_basis_rt(float t, const BasisTab& tab, int n, float (&phi)[HOL_MAX_N]) {
-    float d[HOL_MAX_N];
-#pragma unroll
-    for (int m = 0; m < HOL_MAX_N; ++m) d[m] = (m < n) ? t - tab.X[m] : 1.0f;
-    float run = 1.0f;
-#pragma unroll
-    for (int j = 0; j < HOL_MAX_N; ++j) {
-        phi[j] = run;
-        run *= d[j];
-    }
-    run = 1.0f;
-#pragma unroll
-    for (int j = HOL_MAX_N - 1; j >= 0; --j) {
-        phi[j] = (j < n) ? phi[j] * (run * tab.C[j]) : 0.0f;
-        run *= d[j];
-    }
-    if (n == 1) phi[0] = 1.0f;
+// work item -> (m-tile, n-tile, k-chunk range)
+__device__ __forceinline__ void item_coords(const TcGemmParams& p, int64_t item, int64_t& mt, int& nt, int& ks, int& kc_lo,
+                                            int& kc_hi) {
+    ks = (int)(item % p.ksplit);
+    tile_coords(p, item / p.ksplit, mt, nt);
+    kc_lo = ks * p.kc_per_split;
+    kc_hi = min(p.nkc, kc_lo + p.kc_per_split);
 }
 
-// One generator thread's share of a stage: which (row/column, input) pairs it owns and their
-// coordinates, loaded one k-chunk ahead of use.
-struct GenPairs {
-    float xl[TC_GEN_PMAX];
-    uint32_t sg[TC_GEN_PMAX];
-};
-
-// EPI_Y  : A tile = Phi  [128 samples (rows)] x [64 dense columns k0..k0+63]; pair = (sample r, input i)
-// EPI_DW : A tile = Phi^T[128 dense columns R0..R0+127 (rows)] x [64 samples c0..c0+63]; pair = (sample e, input i)
-template <int EPI>
-__device__ __forceinline__ void gen_load(const TcGemmParams& p, int gt, int64_t mt, int kc, GenPairs& g) {
-    const int span = (EPI == EPI_Y) ? TC_BK : TC_BM;                 // dense columns covered by the tile
-    const int64_t d0 = (EPI == EPI_Y) ? (int64_t)kc * TC_BK : mt * TC_BM;
-    const int i_lo = (int)(d0 / p.Kin);
-    const int i_hi = (int)min((int64_t)p.I - 1, (d0 + span - 1) / p.Kin);
-    const int nsamp = (EPI == EPI_Y) ? TC_BM : TC_BK;
-    const int64_t b0 = (EPI == EPI_Y) ? p.row0 + mt * TC_BM : p.row0 + (int64_t)kc * TC_BK;
-    const int npairs = nsamp * (i_hi - i_lo + 1);
+// r[j] = racc[base + j], j < N, for a run-time `base`: a switch over the 128 possible bases whose
+// cases index the register sums with compile-time constants.  (Indexing racc with a run-time value
+// would move the whole array to local memory -- which is what the first version of the dX epilogue
+// did: 15.7 GB of L1->L2 write-through traffic per pass at C2.)  `base` differs between the lanes of a
+// warp (it depends on the sample's segment), so a warp walks one case per distinct segment.  The
+// moves are volatile asm so that the compiler keeps the branches instead of evaluating all 128
+// cases and selecting.
+#define TC_DX_CASE(k)                                                                                  \
+    case (k): {                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < N; ++j)                                                  \
+            asm volatile("mov.b32 %0, %1;" : "=f"(r[j]) : "f"(racc[((k) + j) < TC_MAXHALF ? ((k) + j) : 0])); \
+        break;                                                                                         \
+    }
+#define TC_DX_CASE8(k) TC_DX_CASE(k) TC_DX_CASE(k + 1) TC_DX_CASE(k + 2) TC_DX_CASE(k + 3) TC_DX_CASE(k + 4) TC_DX_CASE(k + 5) TC_DX_CASE(k + 6) TC_DX_CASE(k + 7)
+#define TC_DX_CASE32(k) TC_DX_CASE8(k) TC_DX_CASE8(k + 8) TC_DX_CASE8(k + 16) TC_DX_CASE8(k + 24)
+template <int N>
+__device__ __forceinline__ void dx_pick(const float (&racc)[TC_MAXHALF], int base, float (&r)[N]) {
 #pragma unroll
-    for (int q = 0; q < TC_GEN_PMAX; ++q) {
-        const int pidx = gt + TC_GEN_THREADS * q;
-        g.sg[q] = HOL_SEG_INVALID;
-        g.xl[q] = 0.0f;
-        if (pidx < npairs) {
-            const int e = pidx % nsamp, i = i_lo + pidx / nsamp;
-            const int64_t b = b0 + e;
-            if (b < p.Bp) {
-                const int64_t idx = (int64_t)i * p.Bp + b;
-                g.sg[q] = p.seg_t[idx];
-                g.xl[q] = p.xl_t[idx];
-            }
-        }
+    for (int j = 0; j < N; ++j) r[j] = 0.0f;
+    switch (base) {
+        TC_DX_CASE32(0)
+        TC_DX_CASE32(32)
+        TC_DX_CASE32(64)
+        TC_DX_CASE32(96)
     }
 }
 
-template <int EPI>
-__device__ __forceinline__ void gen_scatter(const TcGemmParams& p, int gt, int64_t mt, int kc, const GenPairs& g,
-                                            unsigned char* img_hi, float scale) {
-    const int span = (EPI == EPI_Y) ? TC_BK : TC_BM;
-    const int64_t d0 = (EPI == EPI_Y) ? (int64_t)kc * TC_BK : mt * TC_BM;
-    const int i_lo = (int)(d0 / p.Kin);
-    const int nsamp = (EPI == EPI_Y) ? TC_BM : TC_BK;
-    unsigned char* img_lo = img_hi + TC_A_IMG;
-#pragma unroll
-    for (int q = 0; q < TC_GEN_PMAX; ++q) {
-        const uint32_t sg = g.sg[q];
-        if (sg & HOL_SEG_INVALID) continue;
-        const int pidx = gt + TC_GEN_THREADS * q;
-        const int e = pidx % nsamp, i = i_lo + pidx / nsamp;
-        float phi[HOL_MAX_N];
-        lagrange_basis_rt(g.xl[q], p.tab, p.n_basis, phi);
-        const int64_t kbase = (int64_t)i * p.Kin + (int)(sg & HOL_SEG_MASK) * p.stride - d0;  // dense column - d0
-#pragma unroll
-        for (int j = 0; j < HOL_MAX_N; ++j) {
-            const int64_t dc = kbase + j;
-            if (j < p.n_basis && dc >= 0 && dc < span) {
-                const float a = phi[j] * scale;
-                const __half h = __float2half_rn(a);
-                const __half l = __float2half_rn(a - __half2float(h));
-                // image layout [k/8][row][8 x fp16]: EPI_Y row = sample, k = dense column; EPI_DW row = dense column, k = sample
-                const int row = (EPI == EPI_Y) ? e : (int)dc;
-                const int kk = (EPI == EPI_Y) ? (int)dc : e;
-                const int off = (kk >> 3) * (TC_BM * 16) + row * 16 + (kk & 7) * 2;
-                *reinterpret_cast<__half*>(img_hi + off) = h;
-                *reinterpret_cast<__half*>(img_lo + off) = l;
-            }
-        }
-    }
-}
-
-// Persistent: grid = min(#tiles, #SMs); every role walks the same tile sequence
-// tile = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring (full/empty) and the two TMEM
-// accumulators (tmem_full/tmem_empty) run continuously across tiles, so the epilogue of tile t
+// Persistent: grid = min(#items, #SMs); every role walks the same work-item sequence
+// item = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring (full/empty) and the two TMEM
+// accumulators (tmem_full/tmem_empty) run continuously across items, so the epilogue of tile t
 // overlaps the main loop of tile t+1.
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue, (GEN) 10..11 = operand generators that
-// zero-fill the A half of a stage and scatter the n non-zero basis values of every (sample, input)
-// pair into it, so Phi / Phi^T never exist in global memory.  N = basis size for the EPI_DX gather.
+// Warps: 0 = producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle (warpgroup 0, trimmed to 56
+// registers per thread with setmaxnreg), 4..11 = epilogue (warpgroups 1-2, raised to 224 registers:
+// 128 running sums + the gather state without spills).  N = basis size for the EPI_DX gather.
 // AMODE: where the A operand of a stage comes from
 //   A_TILES  one bulk copy of a ready-made K-major tile image (Phi, Phi^T or gy tiles)
-//   A_GEN    generated in the kernel by two extra warps (opt-in, see tc_plan)
 //   A_PHI_MN EPI_DW only: the FORWARD's Phi tiles [128 samples][64 dense columns] read as the
 //            MN-major operand Phi^T: a stage = 128 dense columns (two forward k-chunks) x 64
 //            samples (half a batch tile), gathered by the producer warp with 16-byte cp.async copies
 //            into the canonical MN-major no-swizzle layout
 //            [image][column group of 8][64 samples][8 x fp16]  (SBO = 1024 B, LBO = 128 B)
-enum { A_TILES = 0, A_GEN = 1, A_PHI_MN = 2 };
+enum { A_TILES = 0, A_PHI_MN = 2 };
+#define TC_THREADS 384
 
 template <int EPI, int N, int AMODE>
-__global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
-    constexpr bool GEN = AMODE == A_GEN;
+__global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int BN = p.BN;
     const int B_IMG = BN * TC_BK * 2;
@@ -214,13 +167,14 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nst = p.nst;
     const int FG = p.flush_chunks;
-    const int ngroups = (p.nkc + FG - 1) / FG;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;  // two accumulators; power of two >= 32
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) {
-            mbar_init(&full[s], (GEN || AMODE == A_PHI_MN) ? 2 : 1);  // TMA producer (+ generators / cp.async gather)
+            // A_PHI_MN: the bulk copy of B (expect_tx arrival of lane 0) + one asynchronous arrival per
+            // producer lane when its cp.async copies of the stage have landed
+            mbar_init(&full[s], AMODE == A_PHI_MN ? 33 : 1);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -240,21 +194,27 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register re-allocation between the warpgroups (the launch gives every thread 168): issued inside
+    // each role's branch -- ptxas budgets a region by the setmaxnreg that dominates it, and a join of the
+    // two settings before the role dispatch would cap every role at the smaller one.
     if (warp == 0 && AMODE == A_PHI_MN) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // The whole producer warp gathers the A half of a stage with 16-byte cp.async copies (2048
         // per stage, 64 per lane, 512 contiguous bytes per warp instruction): the pieces that are
         // contiguous in the forward's tile storage are only 1 KB long, and 32 bulk copies of 1 KB
         // (14.6 ms at C2) or four tiled TMA boxes with 16-byte rows (17.2 ms) cost more than the
-        // MMAs of the stage (11.8 ms with one 32 KB bulk copy of a K-major tile).
+        // MMAs of the stage.  The copies of a stage complete asynchronously on its `full` barrier
+        // (cp.async.mbarrier.arrive.noinc), so the warp runs ahead over the whole ring instead of
+        // waiting for every stage to land before issuing the next one.
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            int nt;
+        for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            int nt, ks, kc_lo, kc_hi;
             int64_t mt;
-            tile_coords(p, tile, mt, nt);
+            item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
             const unsigned char* a_mt = p.a_tiles + (2 * mt) * (int64_t)(2 * TC_A_IMG) + lane * 16;
             const int64_t a_bt = (int64_t)p.a_nkc * (2 * TC_A_IMG);  // bytes per batch tile
             const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
-            for (int sc = 0; sc < p.nkc; ++sc, ++it) {
+            for (int sc = kc_lo; sc < kc_hi; ++sc, ++it) {
                 const int st = it % nst;
                 mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
                 unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
@@ -273,37 +233,32 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                                  "l"(src + (c2 * 2 + img) * TC_A_IMG + kg * (TC_BM * 16) + rr * 16)
                                  : "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[st]);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[st])) : "memory");
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");  // nothing in flight when the CTA exits
     } else if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (elect_one()) {
             int it = 0;
-            for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                int nt;
+            for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+                int nt, ks, kc_lo, kc_hi;
                 int64_t mt;
-                tile_coords(p, tile, mt, nt);
+                item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
                 const unsigned char* a_src = p.a_tiles + (mt * p.a_nkc) * (int64_t)(2 * TC_A_IMG);
                 const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
-                for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+                for (int kc = kc_lo; kc < kc_hi; ++kc, ++it) {
                     const int st = it % nst;
                     mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
                     unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
-                    if (GEN) {
-                        mbar_expect_tx(&full[st], (uint32_t)(2 * B_IMG));
-                    } else {
-                        mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
-                        bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
-                    }
+                    mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
+                    bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
                     bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
                 }
             }
         }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (elect_one()) {
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             // (A_PHI_MN: a_major bit 15 = MN-major)
@@ -313,16 +268,20 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
             const uint32_t LBO_A = AMODE == A_PHI_MN ? 128u : TC_BM * 16, SBO_A = AMODE == A_PHI_MN ? 1024u : 128u;
             const uint32_t LBO_B = (uint32_t)BN * 16, SBO = 128;
             int it = 0, g = 0;
-            for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+            for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+                const int ks = (int)(item % p.ksplit);
+                const int kc_lo = ks * p.kc_per_split, kc_hi = min(p.nkc, kc_lo + p.kc_per_split);
+                for (int kc = kc_lo; kc < kc_hi; ++kc, ++it) {
                     const int st = it % nst;
                     const int acc = g & 1;
-                    const bool first = (kc % FG) == 0;
+                    const int rel = kc - kc_lo;
+                    const bool first = (rel % FG) == 0;
                     if (first) {
                         mbar_wait(&tmem_empty[acc], (uint32_t)(((g >> 1) & 1) ^ 1));  // drained by the epilogue
                         tc_fence_after();
                     }
                     mbar_wait(&full[st], (uint32_t)((it / nst) & 1));
+                    if (AMODE == A_PHI_MN) fence_proxy_async_smem();  // the A half was written by cp.async (generic proxy)
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stages + (size_t)st * STAGE_BYTES);
                     const uint32_t sb = sa + 2 * TC_A_IMG;
@@ -338,62 +297,20 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                         umma_f16(td, a_lo, b_hi, idesc, 1u);
                     }
                     umma_commit(&empty[st]);  // arrives when the MMAs above have finished reading this stage
-                    if ((kc % FG) == FG - 1 || kc == p.nkc - 1) {
+                    if ((rel % FG) == FG - 1 || kc == kc_hi - 1) {
                         umma_commit(&tmem_full[acc]);
                         ++g;
                     }
                 }
             }
         }
-    } else if (GEN && warp >= 10) {
-        // operand generators: stay one k-chunk ahead with the coordinate loads
-        const int gt = threadIdx.x - 320;
-        const float scale = phi_scale(__uint_as_float(p.sc->max_xl), p.tab, p.n_basis);
-        int it = 0;
-        GenPairs cur, nxt;
-        int64_t tile = blockIdx.x;
-        int kc = 0;
-        int64_t mt = 0;
-        int nt = 0;
-        if (tile < p.ntiles) {
-            tile_coords(p, tile, mt, nt);
-            gen_load<EPI>(p, gt, mt, 0, cur);
-        }
-        while (tile < p.ntiles) {
-            // coordinates of the chunk after this one
-            int64_t ntile = tile, nmt = mt;
-            int nkc2 = kc + 1;
-            if (nkc2 == p.nkc) {
-                nkc2 = 0;
-                ntile = tile + gridDim.x;
-                if (ntile < p.ntiles) tile_coords(p, ntile, nmt, nt);
-            }
-            if (ntile < p.ntiles) gen_load<EPI>(p, gt, nmt, nkc2, nxt);
-
-            const int st = it % nst;
-            mbar_wait(&empty[st], (uint32_t)(((it / nst) & 1) ^ 1));
-            unsigned char* img = stages + (size_t)st * STAGE_BYTES;
-            // zero both images (32 KB) cooperatively, then scatter the non-zeros
-            uint4* z = reinterpret_cast<uint4*>(img);
-            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 4
-            for (int e = gt; e < 2 * TC_A_IMG / 16; e += TC_GEN_THREADS) z[e] = zero;
-            asm volatile("bar.sync 2, 64;" ::: "memory");
-            gen_scatter<EPI>(p, gt, mt, kc, cur, img, scale);
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 2, 64;" ::: "memory");
-            if (gt == 0) mbar_arrive(&full[st]);
-
-            cur = nxt;
-            tile = ntile;
-            mt = nmt;
-            kc = nkc2;
-            ++it;
-        }
-    } else if (warp >= 2 && warp < 10) {
-        // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // epilogue warps 4..11: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4
         const int q = warp & 3;
-        const int h = (warp - 2) >> 2;
+        const int h = (warp - 4) >> 2;
         const int rl = q * 32 + lane;  // row inside the 128-row tile
         int g = 0;
         // scale factors (device scalars written before this launch)
@@ -405,10 +322,11 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
         else
             inv = 1.0f / (pow2_scale_for(__uint_as_float(p.sc->max_gy)) * pow2_scale_for(__uint_as_float(p.sc->max_w)));
 
-        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            int nt;
+        for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            int nt, ks, kc_lo, kc_hi;
             int64_t mt;
-            tile_coords(p, tile, mt, nt);
+            item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
+            const int ngroups = (kc_hi - kc_lo + FG - 1) / FG;
             float racc[TC_MAXHALF];
 #pragma unroll
             for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
@@ -436,13 +354,25 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                 mbar_wait(&tmem_full[acc], (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * HALF);
+                if (EPI == EPI_DX) {  // 16 columns per load: the gather state leaves no room for 32 more registers
 #pragma unroll
-                for (int c0 = 0; c0 < TC_MAXHALF; c0 += 32) {
-                    if (c0 < HALF) {
-                        uint32_t v[32];
-                        tmem_ld32(t0 + (uint32_t)c0, v);
+                    for (int c0 = 0; c0 < TC_MAXHALF; c0 += 16) {
+                        if (c0 < HALF) {
+                            uint32_t v[16];
+                            tmem_ld16(t0 + (uint32_t)c0, v);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) racc[c0 + e] += __uint_as_float(v[e]);  // columns >= HALF: unused
+                            for (int e = 0; e < 16; ++e) racc[c0 + e] += __uint_as_float(v[e]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < TC_MAXHALF; c0 += 32) {
+                        if (c0 < HALF) {
+                            uint32_t v[32];
+                            tmem_ld32(t0 + (uint32_t)c0, v);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) racc[c0 + e] += __uint_as_float(v[e]);  // columns >= HALF: unused
+                        }
                     }
                 }
                 tc_fence_before();
@@ -474,29 +404,27 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                 }
             } else if (EPI == EPI_DW) {
                 // row = dense column k = i*Kin + v, columns = outputs; write the reference layout dw[o][i][v]
+                // (or, when the batch is split over several work items, this split's partial result)
                 const int i = (int)(row / p.Kin), v = (int)(row % p.Kin);
                 if (i < p.I && v < p.nb) {
                     const bool accumulate = p.row0 > 0;
+                    float* outp = p.out + (int64_t)ks * p.part_stride;
 #pragma unroll
                     for (int e = 0; e < TC_MAXHALF; ++e) {
                         if (e < HALF) {
                             const int o = colbase + e;
                             if (o < p.n_valid) {
-                                float* dst = p.out + ((int64_t)o * p.I + i) * p.nb + v;
+                                float* dst = outp + ((int64_t)o * p.I + i) * p.nb + v;
                                 *dst = accumulate ? *dst + racc[e] * inv : racc[e] * inv;
                             }
                         }
                     }
                 }
             } else {
-                // EPI_DX: this thread holds T[b][k] for HALF/Kin whole inputs.  The n active columns
-                // of an input depend on the sample's segment, so the finished sums are parked once per
-                // tile in a per-thread local array (L1/L2-backed, 512 B) and gathered with dynamic
-                // indices in a compact loop over the inputs.
+                // EPI_DX: this thread holds T[b][k] for HALF/Kin whole inputs.  The n active columns of an
+                // input depend on the sample's segment: dx_pick moves them out of the register sums
+                // through a switch, so every register index stays static.
                 constexpr int NB = N > 0 ? N : 1;
-                float T[TC_MAXHALF];
-#pragma unroll
-                for (int e = 0; e < TC_MAXHALF; ++e) T[e] = racc[e];
                 const int64_t b = p.row0 + row;
                 const int ninp = HALF / p.Kin;
                 if (b < p.Bp) {
@@ -510,8 +438,8 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                         if (ii < PF) {
                             sg = pf_sg[0], xlv = pf_xl[0];
 #pragma unroll
-                            for (int q = 1; q < PF; ++q)
-                                if (ii == q) sg = pf_sg[q], xlv = pf_xl[q];
+                            for (int qq = 1; qq < PF; ++qq)
+                                if (ii == qq) sg = pf_sg[qq], xlv = pf_xl[qq];
                         } else {
                             sg = p.seg_t[idx];
                             xlv = p.xl_t[idx];
@@ -519,15 +447,17 @@ __global__ void __launch_bounds__(AMODE == A_GEN ? 384 : 320, 1) pw_tc_gemm_kern
                         const int s = (int)(sg & HOL_SEG_MASK);
                         float dphi[NB];
                         lagrange_basis_derivative<NB>(xlv, p.tab, dphi);
-                        const float* Tr = T + ii * p.Kin + s * p.stride;
+                        float tv[NB];
+                        dx_pick<NB>(racc, ii * p.Kin + s * p.stride, tv);
                         float sum = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < NB; ++j) sum = fmaf(dphi[j], Tr[j], sum);
+                        for (int j = 0; j < NB; ++j) sum = fmaf(dphi[j], tv[j], sum);
                         const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
                         const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
                         float chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
                         if (sg & HOL_SEG_MIRROR) chain = -chain;
-                        const float outv = (sg & HOL_SEG_INVALID) ? 0.0f : sum * inv * chain;
+                        // outliers are written by the fp32 fix-up kernel after this launch
+                        const float outv = (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) ? 0.0f : sum * inv * chain;
                         if (p.transposed)
                             p.out[idx] = outv;
                         else if (row < p.rows_valid)

@@ -64,6 +64,13 @@ def _nb(n: int, segments: int, discontinuous: bool) -> int:
     return n * segments if discontinuous else (n - 1) * segments + 1
 
 
+def set_plan_overrides(mask: int) -> int:
+    """Diagnostic (tests, A/B measurements): force kernel families for the calls that follow
+    (``_lib.HOL_PLAN_*`` bits, 0 = the planner's own choice); returns the previous mask.  Must not
+    change between a forward and its backward."""
+    return int(_lib.load().hol_set_plan_overrides(int(mask)))
+
+
 # ------------------------------------------------------------------------------------------
 # segment index (Piecewise.which_segment)
 # ------------------------------------------------------------------------------------------
@@ -177,7 +184,7 @@ class _PiecewiseFn(torch.autograd.Function):
             rdx, rdw = pw_backward(gy, x, w, ctx.ws, *ctx.args, need_dx, need_dw, True)
             dx = rdx if need_dx else None
             dw = rdw if need_dw else None
-        ctx.ws = None
+        # the workspace stays with the graph node (a second backward with retain_graph=True reuses it)
         return dx, dw, None, None, None, None, None
 
 
@@ -296,7 +303,6 @@ class _PiecewiseConvRowsFn(torch.autograd.Function):
             rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ctx.ws, *ctx.args, need_dx, need_dw, True)
             dx = rdx if need_dx else None
             dw = rdw if need_dw else None
-        ctx.ws = None
         return (dx, dw) + (None,) * 9
 
 
@@ -435,13 +441,12 @@ def plan_flags(B: int, I: int, O: int, n: int, segments: int, discontinuous: boo
     if f < 0:
         raise ValueError("plan_flags: shape outside the envelope")
     return {"tc_forward": bool(f & 1), "tc_dx": bool(f & 2), "tc_dw": bool(f & 4), "dense_dw": bool(f & 8),
-            "shared_phi": bool(f & 16), "rotated_gather": bool(f & 32)}
+            "shared_phi": bool(f & 16), "rotated_gather": bool(f & 32), "tc_dw_ksplit": (f >> 8) & 255}
 
 
 def uses_tensor_cores(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> bool:
     """True when the layer shape is planned onto the tcgen05 path (csrc/tc_gemm.cu: tc_plan)."""
-    lib = _lib.load()
-    return lib.hol_pw_launch_count(0, B, I, O, n, segments, int(discontinuous), 1, 1, 0) > 3
+    return bool(_lib.load().hol_pw_plan_flags(B, I, O, n, segments, int(discontinuous)) & 7)
 
 
 def profile_layer(x: Tensor, w: Tensor, gy: Tensor, n: int, segments: int, length: float = 2.0,

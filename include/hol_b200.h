@@ -24,8 +24,10 @@
  *     default stream: every launch goes to `stream` (a cudaStream_t passed as void*);
  *   - every buffer is a caller-owned DEVICE pointer, contiguous row-major, 16-byte aligned
  *     (torch's caching allocator gives 512-byte alignment);
- *   - re-entrant, no mutable global state (the node table is an argument); safe to call
- *     from several host threads on different streams;
+ *   - re-entrant (the node table is an argument); safe to call from several host threads on
+ *     different streams.  The only process-wide state is the diagnostic plan-override mask of
+ *     hol_set_plan_overrides (0 unless a test sets it) and write-once caches (SM count, "shared
+ *     memory opt-in done" bits); no environment variable is read;
  *   - fp32 arithmetic, fp32 accumulation, no fast-math; segment indices follow the
  *     reference's three separately rounded fp32 ops + truncation + clamp bit for bit
  *     (CPU semantics: true divisions), finite inputs only (NaN -> segment 0; +-inf is
@@ -64,6 +66,15 @@ extern "C" {
 int hol_abi_version(void);
 const char* hol_error_string(int code);
 
+/* DIAGNOSTIC: force kernel families for the calls that follow (tests, A/B measurements); returns the
+ * previous mask.  0 = the planner's own choice.  Must not change between a forward and the backward
+ * that reuses its workspace (the workspace layout depends on the plan). */
+#define HOL_PLAN_DISABLE_TENSOR_CORES 1u /* gather kernels everywhere                                */
+#define HOL_PLAN_DISABLE_DENSE_DW 2u     /* bucketed dW instead of the dense-register dW              */
+#define HOL_PLAN_NO_SHARED_PHI 4u        /* chunked Phi / Phi^T tiles instead of the shared Phi tiles */
+#define HOL_PLAN_FLUSH_SHIFT 8           /* bits 8..11: k-chunks per TMEM drain (0 = default 4)       */
+uint32_t hol_set_plan_overrides(uint32_t mask);
+
 /* Bytes of scratch the forward/backward pair needs for one layer call (same for both). */
 size_t hol_pw_workspace_bytes(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
                               int32_t discontinuous);
@@ -82,7 +93,10 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
 
 /* Backward of the above.  dx and/or dw may be NULL (gradient not needed).  dw is written
  * densely (exact zeros where no sample touched a weight), dx includes the chain factors
- * length/(eta(s+1)-eta(s)) and the +-1 of the periodic fold; dx == 0 for n == 1. */
+ * length/(eta(s+1)-eta(s)) and the +-1 of the periodic fold; dx == 0 for n == 1.  dw is computed
+ * before dx, so a caller may split the call in two (dw only, then dx only, both with
+ * HOL_WS_PREPARED) and start the data-parallel all-reduce of dw while dx is still running.
+ * B == 0: dw (if requested) is zero-filled and nothing else is touched (pointers may be NULL). */
 int hol_pw_backward_f32(const float* gy, const float* x, const float* w,
                         const float* nodes_host, float* dx, float* dw, int64_t B, int32_t I,
                         int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
@@ -120,8 +134,8 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
  * with CUDA events between the kernels and returns their durations in milliseconds in
  * ms_out_host[9] = {prep, pack, forward, dx, bucket_sort, dw, gemm_fwd, gemm_dx, gemm_dw}: the
  * first six bracket the stages (for a tensor-core layer "forward"/"dx"/"dw" include the operand
- * builders), the last three are the tcgen05 GEMM launches alone (0 on the gather path).  Used by
- * bench.py for the per-kernel roofline numbers; not part of the drop-in path. */
+ * builders and the outlier fix-up), the last three are the tcgen05 GEMM launches alone (0 on the
+ * gather path).  Used by bench.py for the per-kernel roofline numbers; not part of the drop-in path. */
 int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const float* nodes_host,
                        float* y, float* dx, float* dw, int64_t B, int32_t I, int32_t O, int32_t n,
                        int32_t S, float length, int32_t discontinuous, float periodicity, void* ws,
@@ -134,7 +148,8 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
 
 /* Which kernels the planner picks for a layer shape (diagnostic, used by bench.py): bit 0 / 1 / 2 =
  * forward / dX / dW on the tcgen05 path, bit 3 = dense-register dW (narrow layers), bit 4 = the
- * forward's Phi tiles are shared with dW, bit 5 = lane-rotated gather kernels (S > 8); -1 = bad shape. */
+ * forward's Phi tiles are shared with dW, bit 5 = lane-rotated gather kernels (S > 8), bits 8..15 =
+ * k-split of the tensor-core dW GEMM; -1 = bad shape. */
 int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous);
 
 /* ---- per-sample normalisations between layers ------------------------------

@@ -32,22 +32,22 @@ def test_workspace_queries_need_no_gpu():
     lib = _lib.load()
     c2 = lib.hol_pw_workspace_bytes(65536, 1024, 1024, 5, 8, 1)
     assert 5e8 < c2 < 2e10      # tensor-core path: + the Phi tiles of the whole batch (10.7 GB) and the operand tiles
-    os.environ["HOL_DISABLE_TC"] = "1"
+    prev = ops.set_plan_overrides(_lib.HOL_PLAN_DISABLE_TENSOR_CORES)
     try:
         assert 5e8 < lib.hol_pw_workspace_bytes(65536, 1024, 1024, 5, 8, 1) < 2e9   # gather path only
     finally:
-        del os.environ["HOL_DISABLE_TC"]
+        assert ops.set_plan_overrides(prev) == _lib.HOL_PLAN_DISABLE_TENSOR_CORES
     assert lib.hol_pw_workspace_bytes(8, 4, 4, 11, 2, 0) == 0          # n above the compiled envelope
     assert lib.hol_pw_workspace_bytes(8, 4, 4, 3, 5000, 0) == 0        # too many segments
     assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 32, 32, 6, 5, 1, 0, 1, 3, 4, 0) > 0
     assert lib.hol_pw_conv2d_workspace_bytes(4, 3, 4, 4, 6, 5, 1, 0, 1, 3, 4, 0) == 0   # kernel larger than image
     assert lib.hol_pw_launch_count(0, 64, 8, 4, 3, 2, 0, 1, 1, 0) == 3       # prep, pack, forward (gather path)
     assert lib.hol_pw_launch_count(1, 64, 8, 4, 3, 2, 0, 1, 1, 1) == 2       # dX, dense-register dW (narrow layer)
-    os.environ["HOL_DISABLE_DWD"] = "1"
+    prev = ops.set_plan_overrides(_lib.HOL_PLAN_DISABLE_DENSE_DW)
     try:
         assert lib.hol_pw_launch_count(1, 64, 8, 4, 3, 2, 0, 1, 1, 1) == 3   # dX, bucket sort, bucketed dW
     finally:
-        del os.environ["HOL_DISABLE_DWD"]
+        ops.set_plan_overrides(prev)
     assert lib.hol_pw_launch_count(0, 65536, 1024, 1024, 5, 8, 1, 1, 1, 0) > 3   # tensor-core path
 
 

@@ -1,5 +1,5 @@
 """Accuracy of the split-fp16 tcgen05 path against the fp64 oracle as a function of the number of
-k-chunks accumulated in TMEM between drains (HOL_TC_FLUSH): the tensor core accumulates with
+k-chunks accumulated in TMEM between drains (hol_set_plan_overrides, HOL_PLAN_FLUSH_SHIFT): the tensor core accumulates with
 round-toward-zero, so the bias grows with the chain length; worst case = same-sign terms."""
 import os
 import sys
@@ -22,7 +22,7 @@ for label, wgen, ggen in (("random signs", lambda s: rng.uniform(-1, 1, size=s),
     y64 = orc.pw_forward(x, w, n, S, 2.0, disc, None, nodes=nodes)
     dx64, dw64 = orc.pw_backward(gy, x, w, n, S, 2.0, disc, None, nodes=nodes)
     for fc in sys.argv[1:] or ["2", "4", "8"]:
-        os.environ["HOL_TC_FLUSH"] = fc
+        ops.set_plan_overrides(int(fc) << 8)
         xt = torch.from_numpy(x).cuda().requires_grad_(True)
         wt = torch.from_numpy(w).cuda().requires_grad_(True)
         y = ops.piecewise_polynomial(xt, wt, n, S, 2.0, disc, None)
