@@ -1,12 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the piecewise-polynomial hot path (fwd+bwd samples/s) -- see DESIGN.md "Measurement".
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5|c1] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config all|c1|c2|c3|c4|c5] [--impl ours|reference]
 
-Default workload (N=1 and every N of the scaling run): BASELINE.json configs[1] ("c2"), one
-PiecewiseDiscontinuousPolynomial layer, batch 65536 per GPU, in=out=1024, n=5, segments=8, fp32.
-A step = zero grads, forward, backward with a supplied upstream gradient (dX and dW), and for
-N>1 the NCCL sum-allreduce of dW (weak scaling: per-GPU batch fixed).  One JSON line on rank 0.
+Default (`--config all`, N=1 and every N of the scaling run): the headline line is the workload
+BASELINE.json's metric is quoted on -- "piecewise-poly MLP 1/2/4/8 x B200" = config 3, the
+invariant-MNIST-shaped HighOrderMLP 784->128->128->10 (continuous, n=4, segments=4, max_abs), batch
+8192 per GPU, whole step (forward, CE loss, backward, per-layer NCCL all-reduce of dW overlapped
+with the rest of the backward) captured in one CUDA graph -- and the same JSON line carries the other
+named configs as sub-blocks under "configs": c2 (single 1024->1024 n=5 S=8 layer, batch 65536), c4
+(LeNet-style conv net, batch 1024) and one c5 sweep point (4096->4096 n=4 S=64, batch 32768), each
+with its own ms_per_step / value / roofline / plan, measured the same way in the same process.
+`--config cX` runs a single workload as the line itself.
+
+A step = zero grads, forward, backward with a supplied upstream gradient or loss (dX and dW), and
+for N>1 the NCCL all-reduce of dW (weak scaling: per-GPU batch fixed).  One JSON line on rank 0.
 
 `--impl reference` times the reference's own CPU implementation of the same path on the host
 cores (the unmodified reference from baseline/_ref when it is present, otherwise the numpy
@@ -188,19 +196,19 @@ def build_workload(torch, cfg, device, rank, args):
         flat = FlatGradients(layer.parameters())
 
         def step():
-            flat.zero_()
+            flat.begin()
             x.grad = None
             y = layer(x)
             y.backward(gy)
-            flat.allreduce(average=True)
+            flat.finish()
 
         def e2e_compute(dev):
             xd = dev["x"].detach().requires_grad_(True)
-            flat.zero_()
+            flat.begin()
             y = layer(xd)
             loss = (y * dev["gy"]).sum()     # d loss / d y = gy: the same backward as the device-resident step
             loss.backward()
-            flat.allreduce(average=True)
+            flat.finish()
             return loss
 
         by, fl = layer_bytes_flops(B, I, O, n, S, disc)
@@ -229,17 +237,17 @@ def build_workload(torch, cfg, device, rank, args):
         flat = FlatGradients(net.parameters())
 
         def step():
-            flat.zero_()
+            flat.begin()
             loss = lossf(net(x), target)
             loss.backward()
-            flat.allreduce(average=True)
+            flat.finish()
             return loss
 
         def e2e_compute(dev):
-            flat.zero_()
+            flat.begin()
             loss = lossf(net(dev["x"]), dev["t"])
             loss.backward()
-            flat.allreduce(average=True)
+            flat.finish()
             return loss
 
         dims = list(zip(wd[:-1], wd[1:]))
@@ -254,7 +262,7 @@ def build_workload(torch, cfg, device, rank, args):
                   # + one fused normalisation kernel each way between consecutive layers (csrc/norm.cu)
                   launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False)
                   + 2 * (len(dims) - 1),
-                  layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x)
+                  layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x, first_needs_dx=False)
         return wl
 
     if cfg["kind"] == "conv":
@@ -286,17 +294,17 @@ def build_workload(torch, cfg, device, rank, args):
         flat = FlatGradients(net.parameters())
 
         def step():
-            flat.zero_()
+            flat.begin()
             loss = torch.nn.functional.cross_entropy(net(x), target)
             loss.backward()
-            flat.allreduce(average=True)
+            flat.finish()
             return loss
 
         def e2e_compute(dev):
-            flat.zero_()
+            flat.begin()
             loss = torch.nn.functional.cross_entropy(net(dev["x"]), dev["t"])
             loss.backward()
-            flat.allreduce(average=True)
+            flat.finish()
             return loss
 
         rows1, rows2 = B * 28 * 28, B * 10 * 10
@@ -307,9 +315,160 @@ def build_workload(torch, cfg, device, rank, args):
                   h2d=x.numel() * 4 + target.numel() * 8, d2h=4, bytes=b1 + b2, flops=f1 + f2,
                   launches=count_launches([(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)],
                                           first_needs_dx=False, conv=True),
-                  layers=[(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)], x=x)
+                  layers=[(rows1, 75, 6, n, S, False), (rows2, 150, 16, n, S, False)], x=x, first_needs_dx=False)
         return wl
     raise KeyError(cfg["kind"])
+
+
+SUB_STEPS = {"c2": 5, "c4": 20, "c5": 2, "c3": 20, "c1": 20}  # timed steps of a workload run as a sub-block
+
+
+def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, args, with_e2e=True):
+    """Build one workload, time `steps` steps of it (CUDA events, barrier + synchronize on both sides,
+    max over ranks), optionally its end-to-end leg, and its per-kernel roofline block."""
+    local_rank = device.index
+    wl = build_workload(torch, cfg, device, rank, args)
+    wl["key"] = key if not (args.n or args.segments or args.batch) or key != args.config else None
+    step = wl["step"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    # Small-step workloads (MLP / conv nets: ~1 ms of GPU work in ~50 launches) are launch-latency
+    # bound in eager mode: capture the whole step (forward, backward, the overlapped all-reduces) in
+    # one CUDA graph and replay it.  The single-layer configs run for tens of ms and stay eager.
+    graphed, graph = False, None
+    if args.graph == "on" or (args.graph == "auto" and cfg["kind"] in ("mlp", "conv")):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            step = graph.replay
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            graphed = True
+        except Exception as e:  # capture is an optimisation, never a requirement
+            if rank == 0:
+                print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e)[:120]}); running eagerly",
+                      file=sys.stderr)
+            torch.cuda.synchronize()
+            graph = None
+            step = wl["step"]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public module API: pinned host inputs -> H2D -> fwd+bwd -> loss D2H
+    # Every step copies ITS inputs from pinned host memory and reads ITS loss back; the copy of step
+    # k+1 runs on a second stream into the other of two device buffers while step k computes (the
+    # usual input prefetch), the first copy and every read-back are exposed.
+    e2e_steps, e2e_ms = 0, 0.0
+    if with_e2e:
+        e2e_steps = max(1, min(steps, 10))
+        host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        main_stream = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream()
+        dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in wl["host"].items()}
+                    for _ in range(2)]
+
+        def run_e2e(nsteps):
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [None, None]
+
+            def prefetch(slot):
+                with torch.cuda.stream(copy_stream):
+                    if consumed[slot] is not None:
+                        copy_stream.wait_event(consumed[slot])
+                    for k, v in wl["host"].items():
+                        dev_bufs[slot][k].copy_(v, non_blocking=True)
+                    ready[slot].record(copy_stream)
+
+            prefetch(0)
+            last = None
+            for k in range(nsteps):
+                slot = k & 1
+                if k + 1 < nsteps:
+                    prefetch(slot ^ 1)
+                main_stream.wait_event(ready[slot])
+                loss = wl["e2e_compute"](dev_bufs[slot])
+                ev = torch.cuda.Event()
+                ev.record(main_stream)
+                consumed[slot] = ev
+                host_loss.copy_(loss.detach(), non_blocking=True)
+                main_stream.synchronize()
+                last = float(host_loss)
+            return last
+
+        run_e2e(2)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        del dev_bufs
+
+    tm = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = (float(v) for v in tm.tolist())
+    ms_per_step = ms_total / steps
+    res = {
+        "workload": cfg["name"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "value": wl["samples"] * world / (ms_per_step / 1e3),
+        "unit": "samples/s", "cuda_graph": graphed, "gpu_launches_per_step": wl["launches"],
+        "l2": "inputs larger than L2 (no flush needed)" if wl["bytes"] > 3 * 126e6
+              else "working set fits L2; no flush between steps",
+        "clocks": clocks,
+    }
+    if with_e2e:
+        res["e2e"] = {"value": wl["samples"] * world / (e2e_ms / e2e_steps / 1e3), "unit": "samples/s",
+                      "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
+                      "note": "module API; pinned-host inputs copied H2D and the loss read back D2H every step; "
+                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch)"}
+    peaks = load_peaks()
+    res["step_algorithmic"] = {
+        "bytes": wl["bytes"], "flops": wl["flops"],
+        "hbm_frac_of_measured": wl["bytes"] / (ms_per_step / 1e3) / (peaks["hbm_gbs"] * 1e9),
+        "fp32_simt_frac_of_74.4TF": wl["flops"] / (ms_per_step / 1e3) / (FP32_PEAK_TFLOPS * 1e12),
+        "binding_roof": "compute (tensor pipe on the tcgen05 path, fp32 FMA issue / shared memory on the gather "
+                        "path), not HBM"}
+    if rank == 0:
+        try:
+            res["roofline"] = measure_roofline(torch, wl, ms_per_step)
+        except torch.OutOfMemoryError as e:  # the largest sweep points leave no room for a second workspace
+            res["roofline"] = {"error": f"out of memory in the diagnostic pass: {str(e)[:80]}"}
+    # release everything of this workload before the next one is built
+    if graph is not None:
+        graph.reset()
+    del graph, step, wl
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    barrier()
+    return res
 
 
 def run_ours(args):
@@ -331,185 +490,89 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
-    cfg = dict(CONFIGS[args.config])
-    if args.n:
-        cfg["n"] = args.n
-    if args.segments:
-        cfg["S"] = args.segments
-    if args.batch:
-        cfg["B"] = args.batch
-    wl = build_workload(torch, cfg, device, rank, args)
-    wl["key"] = args.config if not (args.n or args.segments or args.batch) else None
-    step = wl["step"]
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
+    head_key = "c3" if args.config == "all" else args.config
+    cfg = dict(CONFIGS[head_key])
+    if args.config != "all":
+        if args.n:
+            cfg["n"] = args.n
+        if args.segments:
+            cfg["S"] = args.segments
+        if args.batch:
+            cfg["B"] = args.batch
+    head = time_workload(torch, dist, head_key, cfg, device, rank, world, steps, warmup, args)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    subs = {}
+    if args.config == "all":
+        for key, over in (("c2", {}), ("c4", {}), ("c5", {"n": 4, "S": 64})):
+            scfg = dict(CONFIGS[key])
+            scfg.update(over)
+            if over:
+                scfg["name"] = scfg["name"].replace("sweep point (n, segments from --n/--segments)",
+                                                    f"sweep point n={over['n']} segments={over['S']}")
+            try:
+                subs[key if not over else f"c5_n{over['n']}_s{over['S']}"] = time_workload(
+                    torch, dist, key, scfg, device, rank, world, SUB_STEPS[key], 3, args, with_e2e=(key != "c5"))
+            except Exception as e:  # a sub-block never costs the headline line
+                torch.cuda.synchronize()
+                subs[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
-    for _ in range(warmup):
-        step()
-    barrier()
-    # Small-step workloads (MLP / conv nets: ~1 ms of GPU work in ~50 launches) are launch-latency
-    # bound in eager mode: capture the whole step (forward, backward, flat-gradient allreduce) in
-    # one CUDA graph and replay it.  The single-layer configs run for tens of ms and stay eager.
-    graphed = False
-    if args.graph == "on" or (args.graph == "auto" and cfg["kind"] in ("mlp", "conv")):
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            eager_step = step
-            step = graph.replay
-            for _ in range(2):
-                step()
-            torch.cuda.synchronize()
-            graphed = True
-        except Exception as e:  # capture is an optimisation, never a requirement
-            if rank == 0:
-                print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e)[:120]}); running eagerly",
-                      file=sys.stderr)
-            torch.cuda.synchronize()
-            step = wl["step"]
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(steps):
-        step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # end to end through the public module API: pinned host inputs -> H2D -> fwd+bwd -> loss D2H
-    # Every step copies ITS inputs from pinned host memory and reads ITS loss back; the copy of step
-    # k+1 runs on a second stream into the other of two device buffers while step k computes (the
-    # usual input prefetch), the first copy and every read-back are exposed.
-    e2e_steps = max(1, min(steps, 10))
-    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
-    main_stream = torch.cuda.current_stream()
-    copy_stream = torch.cuda.Stream()
-    dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in wl["host"].items()}
-                for _ in range(2)]
-
-    def run_e2e(nsteps):
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [None, None]
-
-        def prefetch(slot):
-            with torch.cuda.stream(copy_stream):
-                if consumed[slot] is not None:
-                    copy_stream.wait_event(consumed[slot])
-                for k, v in wl["host"].items():
-                    dev_bufs[slot][k].copy_(v, non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        prefetch(0)
-        last = None
-        for k in range(nsteps):
-            slot = k & 1
-            if k + 1 < nsteps:
-                prefetch(slot ^ 1)
-            main_stream.wait_event(ready[slot])
-            loss = wl["e2e_compute"](dev_bufs[slot])
-            ev = torch.cuda.Event()
-            ev.record(main_stream)
-            consumed[slot] = ev
-            host_loss.copy_(loss.detach(), non_blocking=True)
-            main_stream.synchronize()
-            last = float(host_loss)
-        return last
-
-    run_e2e(2)
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-
-    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = (float(v) for v in tm.tolist())
-    ms_per_step = ms_total / steps
-    value = wl["samples"] * world / (ms_per_step / 1e3)
-    e2e_value = wl["samples"] * world / (e2e_ms / e2e_steps / 1e3)
-
-    roof = None
     cpu = None
     ref_cuda = None
     if rank == 0:
-        try:
-            roof = measure_roofline(torch, wl, ms_per_step)
-        except torch.OutOfMemoryError as e:  # the largest sweep points leave no room for a second workspace
-            roof = {"error": f"out of memory in the diagnostic pass: {str(e)[:80]}"}
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(cfg, budget_s=args.cpu_budget)
+            cpu = cpu_baseline(cfg, budget_s=args.cpu_budget, key=head_key)
         if world == 1 and not args.no_ref_cuda:
-            ref_cuda = ref_torch_cuda(cfg, args.config)
+            ref_cuda = ref_torch_cuda(cfg, head_key)
+            if "c2" in subs and "error" not in subs["c2"]:
+                subs["c2"]["ref_torch_cuda"] = ref_torch_cuda(dict(CONFIGS["c2"]), "c2")
     if world > 1:
         dist.barrier()
 
     if rank == 0:
-        peaks = load_peaks()
         out = {
-            "metric": "fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "per_gpu_batch": cfg["B"], "global_batch": cfg["B"] * world,
-                       "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)"
-                       if wl["bytes"] > 3 * 126e6 else "working set fits L2; no flush between steps",
-                       "allreduce": "one flat fp32 NCCL sum-allreduce of dW per step" if world > 1 else "none",
-                       "cuda_graph": graphed},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": wl["h2d"],
-                    "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
-                    "note": "module API; pinned-host inputs copied H2D and the loss read back D2H every step; the "
-                            "copy of step k+1 overlaps the compute of step k (double-buffered prefetch)"},
-            "gpu_launches": wl["launches"] * steps,
-            "gpu_launches_per_step": wl["launches"],
-            "clocks": clocks,
-            "roofline": roof,
+            "metric": "fwd+bwd samples/sec", "value": head["value"], "unit": "samples/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": head["workload"], "per_gpu_batch": head["per_gpu_batch"],
+                       "global_batch": head["global_batch"], "parallelism": f"dp{world}", "l2": head["l2"],
+                       "allreduce": "per-layer fp32 NCCL all-reduce (avg) of dW on a side stream, issued right after the "
+                                    "layer's dW kernels and overlapped with the rest of the backward"
+                       if world > 1 else "none", "cuda_graph": head["cuda_graph"]},
+            "e2e": head.get("e2e"),
+            "gpu_launches": head["gpu_launches_per_step"] * steps,
+            "gpu_launches_per_step": head["gpu_launches_per_step"],
+            "clocks": head["clocks"],
+            "roofline": head.get("roofline"),
             "cpu_baseline": cpu,
             "ref_torch_cuda": ref_cuda,
-            "step_algorithmic": {"bytes": wl["bytes"], "flops": wl["flops"],
-                                 "hbm_frac_of_measured": wl["bytes"] / (ms_per_step / 1e3) / (peaks["hbm_gbs"] * 1e9),
-                                 "fp32_frac_of_74.4TF": wl["flops"] / (ms_per_step / 1e3) / (FP32_PEAK_TFLOPS * 1e12),
-                                 "binding_roof": "compute (tensor pipe on the tcgen05 path, fp32 FMA issue / shared "
-                                                 "memory on the gather path), not HBM"},
+            "step_algorithmic": head["step_algorithmic"],
+            "configs": subs,
         }
         print(json.dumps(out))
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        # Leave without tearing NCCL down: with a CUDA graph that captured the allreduce still alive,
-        # destroy_process_group() never returned at 2/4/8 ranks (the c3 line was printed, torchrun then sat
-        # until the box limit).  Every rank has passed the barrier above and rank 0 has printed its line.
-        sys.stdout.flush()
-        sys.stderr.flush()
-        if graphed:
+        # Round 1: with a CUDA graph that captured the all-reduce still alive, destroy_process_group() never
+        # returned.  The graphs are reset above (time_workload); should the teardown hang all the same, a
+        # watchdog ends the process -- every rank has passed the barrier and rank 0 has printed its line.
+        def _bail():
+            time.sleep(20.0)
             os._exit(0)
-        dist.destroy_process_group()  # eager runs (the default c2 workload) tear down normally
+        threading.Thread(target=_bail, daemon=True).start()
+        dist.destroy_process_group()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture of the same command (profiles/r1c_tc_ncu_full_summary.md); keyed by
-# (config, dominant pass).  None where no capture exists.
+# `ncu --set full` capture of the same command; keyed by (config, dominant pass).  None where no
+# capture exists.  r1c values (profiles/r1c_tc_ncu_full_summary.md) until the r2 capture replaces them.
 NCU_TRAFFIC = {
     ("c2", "forward"): 22.096271e9 + 0.278053e9,
     ("c2", "dx"): 7.899103e9 + 0.397953e9,
     ("c2", "dw"): 13.179519e9 + 0.167509e9,
 }
+NCU_TRAFFIC_SOURCE = "profiles/r1c_tc_ncu_full_summary.md (ncu --set full, same command)"
 
 
 def load_peaks():
@@ -524,13 +587,21 @@ def load_peaks():
 
 def measure_roofline(torch, wl, ms_per_step):
     """Per-kernel CUDA-event times of the widest layer of the workload (hol_pw_profile_f32 records
-    events between the kernels on the launching stream); the dominant kernel is reported against
-    the measured HBM peak with its ALGORITHMIC bytes (and, because this path is FMA/shared-memory
-    bound, its flops against the 74.4 TFLOP/s fp32 SIMT peak)."""
+    events between the kernels and around every GEMM launch on the launching stream).
+
+    `frac` is the contract's roofline fraction of the dominant kernel: its ALGORITHMIC flops
+    (tensor-core GEMM: 2*B*I*O*n of the pass) or bytes (gather kernels) per launch divided by
+    its measured duration and by the measured peak.  The tensor pipe's utilisation by the flops the
+    split-fp16 dense form actually executes (3*Kin/n times the algorithmic ones) is reported beside
+    it as `tensor_pipe_util`.  Only passes the real step runs are considered (the first layer of a
+    network has no dX)."""
     from high_order_layers_torch_b200 import ops
 
     peaks = load_peaks()
-    B, I, O, n, S, disc = max(wl["layers"], key=lambda t: t[0] * t[1] * t[2] * t[3])
+    layers = wl["layers"]
+    k_big = max(range(len(layers)), key=lambda k: layers[k][0] * layers[k][1] * layers[k][2] * layers[k][3])
+    B, I, O, n, S, disc = layers[k_big]
+    runs_dx = wl.get("first_needs_dx", True) or k_big > 0
     dev = wl["x"].device
     if wl["cfg"]["kind"] == "layer":
         # reuse the workload's own tensors (the 4096x4096 sweep points do not fit twice) and drop its gradients
@@ -551,46 +622,53 @@ def measure_roofline(torch, wl, ms_per_step):
     for _ in range(reps):
         for k, v in ops.profile_layer(x, w, gy, n, S, 2.0, disc, None).items():
             acc[k] = acc.get(k, 0.0) + v / reps
-    layer = {"B": B, "I": I, "O": O, "n": n, "segments": S, "discontinuous": disc}
+    layer = {"B": B, "I": I, "O": O, "n": n, "segments": S, "discontinuous": disc,
+             "passes_in_the_step": ["forward", "dw"] + (["dx"] if runs_dx else [])}
+    plan = ops.plan_flags(B, I, O, n, S, disc)
+    tc_of = {"forward": plan["tc_forward"], "dx": plan["tc_dx"], "dw": plan["tc_dw"]}
+    gemm_key = {"forward": "gemm_fwd", "dx": "gemm_dx", "dw": "gemm_dw"}
+    kname = {"forward": "pw_fwd_kernel", "dx": "pw_dx_kernel", "dw": "pw_dw_dense_kernel" if plan["dense_dw"] else "pw_dw_kernel"}
+    passes = {}
+    for ps in layer["passes_in_the_step"]:
+        by, fl = kernel_bytes_flops(ps, B, I, O, n, S, disc)
+        ms = acc[gemm_key[ps]] if tc_of[ps] and acc.get(gemm_key[ps], 0.0) > 0.0 else acc[ps]
+        t = max(ms, 1e-6) / 1e3
+        traffic = NCU_TRAFFIC.get((wl.get("key"), ps))
+        passes[ps] = {"kernel": f"pw_tc_gemm_kernel ({ps})" if tc_of[ps] else kname[ps], "launch_ms": ms,
+                      "stage_ms": acc[ps], "algorithmic_bytes": by, "algorithmic_flops": fl,
+                      "useful_tflops": fl / t / 1e12, "algorithmic_gbs": by / t / 1e9,
+                      "hbm_frac": by / t / 1e9 / peaks["hbm_gbs"],
+                      "fp32_simt_frac_of_74.4TF": fl / t / 1e12 / FP32_PEAK_TFLOPS,
+                      "traffic": traffic, "traffic_ratio": (traffic / by) if traffic else None}
+        if tc_of[ps]:
+            executed = tc_gemm_flops(ps, B, I, O, n, S, disc)
+            tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+            passes[ps]["tensor_pipe_util"] = {"executed_flops": executed, "executed_tflops": executed / t / 1e12,
+                                              "peak": tpeak, "frac": executed / t / 1e12 / tpeak}
+    dom = max(passes, key=lambda k: passes[k]["launch_ms"])
+    d = passes[dom]
     hbm_note = ("this contraction is compute bound (arithmetic intensity >> ridge), so the HBM fraction of its "
                 "algorithmic bytes is small by construction")
-    if acc.get("gemm_fwd", 0.0) > 0.0:
-        # tensor-core path: the dominant kernel is the split-fp16 tcgen05 GEMM
-        names = {"forward": "gemm_fwd", "dx": "gemm_dx", "dw": "gemm_dw"}
-        dom = max(names, key=lambda k: acc[names[k]])
-        t = acc[names[dom]] / 1e3
-        executed = tc_gemm_flops(dom, B, I, O, n, S, disc)
-        by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        achieved = executed / t / 1e12
-        return {"bound": "tensor", "kernel": f"pw_tc_gemm_kernel ({dom} pass: split-fp16 hi*hi + hi*lo + lo*hi)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step); burst "
-                               f"{peaks['bf16_tflops']}",
-                "traffic": NCU_TRAFFIC.get((wl.get("key"), dom)),
-                "traffic_source": "profiles/r1c_tc_ncu_full_summary.md (ncu --set full, same command)"
-                if (wl.get("key"), dom) in NCU_TRAFFIC else None,
-                "executed_tensor_flops_per_launch_set": executed, "launch_ms": acc[names[dom]],
-                "useful": {"flops": fl, "tflops": fl / t / 1e12,
-                           "note": "2*B*I*O*n useful flops of this pass; the dense segment-expanded form executes "
-                                   "3*Kin/n times as many on the tensor pipe"},
-                "hbm": {"algorithmic_bytes": by, "achieved_gbs": by / t / 1e9, "frac": by / t / 1e9 / peaks["hbm_gbs"],
-                        "note": hbm_note},
-                "kernel_ms": acc, "layer": layer, "plan": ops.plan_flags(B, I, O, n, S, disc)}
-    dom = max(("forward", "dx", "dw"), key=lambda k: acc[k])
-    by, fl = kernel_bytes_flops(dom, B, I, O, n, S, disc)
-    t = acc[dom] / 1e3
-    achieved = by / t / 1e9
-    plan = ops.plan_flags(B, I, O, n, S, disc)
-    return {"bound": "hbm", "kernel": {"forward": "pw_fwd_kernel", "dx": "pw_dx_kernel",
-                                       "dw": "pw_dw_dense_kernel" if plan["dense_dw"] else "pw_dw_kernel"}[dom],
-            "plan": plan,
-            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "peak_source": peaks["source"], "traffic": None,
-            "algorithmic_bytes_per_launch": by, "launch_ms": acc[dom],
-            "fp32": {"achieved_tflops": fl / t / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
-                     "frac": fl / t / 1e12 / FP32_PEAK_TFLOPS, "flops_per_launch": fl},
-            "kernel_ms": acc, "layer": layer, "note": hbm_note + "; see fp32.frac"}
+    if tc_of[dom]:
+        tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        out = {"bound": "tensor", "kernel": f"pw_tc_gemm_kernel ({dom} pass: split-fp16 hi*hi + hi*lo + lo*hi)",
+               "achieved": d["useful_tflops"], "peak": tpeak, "unit": "TFLOP/s", "frac": d["useful_tflops"] / tpeak,
+               "definition": "algorithmic flops of the pass (2*B*I*O*n) / CUDA-event duration of the GEMM launch / "
+                             "measured cuBLAS bf16 rate; the executed-flops utilisation is tensor_pipe_util",
+               "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step); burst "
+                              f"{peaks['bf16_tflops']}",
+               "tensor_pipe_util": d["tensor_pipe_util"]}
+    else:
+        out = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["algorithmic_gbs"], "peak": peaks["hbm_gbs"],
+               "unit": "GB/s", "frac": d["hbm_frac"], "peak_source": peaks["source"],
+               "fp32": {"achieved_tflops": d["useful_tflops"], "peak_tflops": FP32_PEAK_TFLOPS,
+                        "frac": d["fp32_simt_frac_of_74.4TF"]},
+               "note": hbm_note + "; the gather kernels are bound by one shared-memory word per FMA: see fp32.frac"}
+    out.update({"traffic": d["traffic"], "traffic_ratio": d["traffic_ratio"],
+                "traffic_source": NCU_TRAFFIC_SOURCE if d["traffic"] else None,
+                "dominant_pass": dom, "launch_ms": d["launch_ms"], "passes": passes, "kernel_ms": acc,
+                "layer": layer, "plan": plan})
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -862,12 +940,13 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cfg = dict(CONFIGS[args.config])
+    key = "c3" if args.config == "all" else args.config   # the headline workload of the default run
+    cfg = dict(CONFIGS[key])
     if args.n:
         cfg["n"] = args.n
     if args.segments:
         cfg["S"] = args.segments
-    chunk = CPU_CHUNK[args.config]
+    chunk = CPU_CHUNK[key]
     fn, kind, samples = cpu_step_factory(cfg, chunk)
     import torch
     warmup = max(1, min(args.warmup, 3))
@@ -903,7 +982,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="all", choices=["all"] + sorted(CONFIGS),
+                    help="all (default): config 3 as the headline + c2 / c4 / one c5 point as sub-blocks")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="override n (c5 sweep)")
     ap.add_argument("--segments", type=int, default=0, help="override segments (c5 sweep)")

@@ -90,8 +90,9 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], float scale, u
         const float a = v[2 * e] * scale, b = v[2 * e + 1] * scale;
         const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
         __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-        if (v[2 * e] != 0.0f && __half2float(ha) == 0.0f && __half2float(la) == 0.0f) la = v[2 * e] > 0.0f ? tiny : ntiny;
-        if (v[2 * e + 1] != 0.0f && __half2float(hb) == 0.0f && __half2float(lb) == 0.0f) lb = v[2 * e + 1] > 0.0f ? tiny : ntiny;
+        // |a| < 2^-25 rounds to hi = lo = 0: keep the sign and the smallest subnormal instead
+        if (fabsf(a) <= 2.9802323e-8f && a != 0.0f) la = a > 0.0f ? tiny : ntiny;
+        if (fabsf(b) <= 2.9802323e-8f && b != 0.0f) lb = b > 0.0f ? tiny : ntiny;
         h[e] = __halves2half2(ha, hb);
         l[e] = __halves2half2(la, lb);
     }

@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Register re-allocation between the warpgroups (the launch gives every thread 168): issued inside
-    // each role's branch -- ptxas budgets a region by the setmaxnreg that dominates it, and a join of the
-    // two settings before the role dispatch would cap every role at the smaller one.
+    // Register re-allocation between the warpgroups (the launch gives every thread 168).  All four warps
+    // of a warpgroup execute the SAME setmaxnreg instruction (.aligned), and the roles are dispatched
+    // INSIDE the two branches: ptxas budgets a region by the setmaxnreg that dominates it, so a join of
+    // the two settings before the role dispatch would cap every role at the smaller one.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0 && AMODE == A_PHI_MN) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // The whole producer warp gathers the A half of a stage with 16-byte cp.async copies (2048
         // per stage, 64 per lane, 512 contiguous bytes per warp instruction): the pieces that are
         // contiguous in the forward's tile storage are only 1 KB long, and 32 bulk copies of 1 KB
@@ -238,7 +240,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
         }
         asm volatile("cp.async.wait_all;" ::: "memory");  // nothing in flight when the CTA exits
     } else if (warp == 0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (elect_one()) {
             int it = 0;
             for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
@@ -258,7 +259,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (elect_one()) {
             // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             // (A_PHI_MN: a_major bit 15 = MN-major)
@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                 }
             }
         }
-    } else if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // epilogue warps 4..11: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4

@@ -97,18 +97,23 @@ def _(x, segments, length, periodicity):
 # ------------------------------------------------------------------------------------------
 def fc_workspace(x: Tensor, w: Tensor, n: int, segments: int, discontinuous: bool) -> Tensor:
     """Scratch for one layer call (hol_pw_workspace_bytes), from torch's caching allocator."""
-    nbytes = _lib.load().hol_pw_workspace_bytes(x.shape[0], x.shape[1], w.shape[0], n, segments, int(discontinuous))
-    if nbytes == 0:
-        _lib.check(-2 if (n > _lib.HOL_MAX_N or segments > _lib.HOL_MAX_SEGMENTS) else -1, "hol_pw_workspace_bytes")
+    nbytes = _fc_workspace_bytes(x.shape[0], x.shape[1], w.shape[0], n, segments, discontinuous)
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
 
 
-@torch.library.custom_op("hol::pw_forward", mutates_args=("ws",), device_types="cuda")
-def pw_forward(x: Tensor, w: Tensor, ws: Tensor, n: int, segments: int, length: float, discontinuous: bool,
-               periodicity: Optional[float]) -> Tensor:
-    """-> y[B, O].  `ws` (a mutated input, see fc_workspace) keeps the prepared state (transposed
-    local coordinates, packed weights) for ``hol::pw_backward``; it is an input rather than an
-    output so that autograd never materialises a multi-GB zero "gradient" for it."""
+def _fc_workspace_bytes(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> int:
+    nbytes = _lib.load().hol_pw_workspace_bytes(B, I, O, n, segments, int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2 if (n > _lib.HOL_MAX_N or segments > _lib.HOL_MAX_SEGMENTS) else -1, "hol_pw_workspace_bytes")
+    return int(nbytes)
+
+
+@torch.library.custom_op("hol::pw_forward", mutates_args=(), device_types="cuda")
+def pw_forward(x: Tensor, w: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+               periodicity: Optional[float]) -> Tuple[Tensor, Tensor]:
+    """-> (y[B, O], ws).  `ws` is the scratch workspace of the call (hol_pw_workspace_bytes, from torch's
+    caching allocator): it keeps the prepared state (transposed local coordinates, packed weights, Phi
+    tiles) that ``hol::pw_backward`` reuses.  A uint8 tensor, so autograd never tracks it."""
     _check_inputs(x, w, "pw_forward")
     if x.dim() != 2:
         raise ValueError(f"pw_forward: x must be [batch, in_features], got {tuple(x.shape)}")
@@ -120,17 +125,21 @@ def pw_forward(x: Tensor, w: Tensor, ws: Tensor, n: int, segments: int, length: 
     lib = _lib.load()
     xc, wc = x.contiguous(), w.contiguous()
     y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    ws = torch.empty(_fc_workspace_bytes(B, I, O, n, segments, discontinuous), dtype=torch.uint8, device=x.device)
     nodes = lobatto_nodes(n, 2.0)  # FC layers always build LagrangePoly(n) with length 2 (PolynomialLayers.py:234)
     with torch.cuda.device(x.device):
         _lib.check(lib.hol_pw_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, I, O, n, segments, length,
                                           int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(), _stream(x)),
                    "hol_pw_forward_f32")
-    return y
+    return y, ws
 
 
 @pw_forward.register_fake
-def _(x, w, ws, n, segments, length, discontinuous, periodicity):
-    return torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+def _(x, w, n, segments, length, discontinuous, periodicity):
+    B, I = x.shape
+    nbytes = _fc_workspace_bytes(int(B), int(I), int(w.shape[0]), n, segments, discontinuous)
+    return (torch.empty((B, w.shape[0]), dtype=torch.float32, device=x.device),
+            torch.empty((nbytes,), dtype=torch.uint8, device=x.device))
 
 
 @torch.library.custom_op("hol::pw_backward", mutates_args=("ws",), device_types="cuda")
@@ -160,42 +169,83 @@ def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, ne
     return (torch.empty_like(x) if need_dx else e, torch.empty_like(w) if need_dw else e)
 
 
-class _PiecewiseFn(torch.autograd.Function):
-    """Autograd glue: forward = hol::pw_forward (fills the workspace), backward = hol::pw_backward
-    (reuses it).  The ops themselves are plain torch.library ops; the scratch buffer is a mutated
-    op argument, never an op output, so autograd does not materialise a zero gradient for it."""
+@torch.library.custom_op("hol::pw_backward_dw_into", mutates_args=("ws", "dw_out"), device_types="cuda")
+def pw_backward_dw_into(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, dw_out: Tensor, n: int, segments: int,
+                        length: float, discontinuous: bool, periodicity: Optional[float], ws_prepared: bool) -> None:
+    """dW only, written (not accumulated) into `dw_out` -- a caller-owned contiguous fp32 tensor of
+    w's shape, e.g. the parameter's slice of a flat data-parallel gradient buffer (parallel.py)."""
+    _check_inputs(x, w, "pw_backward_dw_into")
+    if dw_out.dtype != torch.float32 or not dw_out.is_contiguous() or dw_out.shape != w.shape:
+        raise ValueError("pw_backward_dw_into: dw_out must be a contiguous float32 tensor of the weight's shape")
+    B, I = x.shape
+    O = w.shape[0]
+    lib = _lib.load()
+    gyc, xc, wc = gy.contiguous(), x.contiguous(), w.contiguous()
+    nodes = lobatto_nodes(n, 2.0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes), _ptr(None), _ptr(dw_out), B, I, O,
+                                           n, segments, length, int(discontinuous), _per(periodicity), _ptr(ws),
+                                           ws.numel(), _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                   "hol_pw_backward_f32")
 
-    @staticmethod
-    def forward(ctx, x, w, n, segments, length, discontinuous, periodicity):
-        ws = fc_workspace(x, w, n, segments, discontinuous)
-        y = pw_forward(x, w, ws, n, segments, length, discontinuous, periodicity)
-        ctx.save_for_backward(x, w)
-        ctx.ws = ws
-        ctx.args = (n, segments, length, discontinuous, periodicity)
-        return y
 
-    @staticmethod
-    @torch.autograd.function.once_differentiable
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dx = dw = None
-        if need_dx or need_dw:
-            rdx, rdw = pw_backward(gy, x, w, ctx.ws, *ctx.args, need_dx, need_dw, True)
-            dx = rdx if need_dx else None
-            dw = rdw if need_dw else None
-        # the workspace stays with the graph node (a second backward with retain_graph=True reuses it)
-        return dx, dw, None, None, None, None, None
+@pw_backward_dw_into.register_fake
+def _(gy, x, w, ws, dw_out, n, segments, length, discontinuous, periodicity, ws_prepared):
+    return None
+
+
+def _grad_sink(w: Tensor):
+    """A data-parallel gradient buffer that wants dW of this parameter written straight into it
+    (parallel.FlatGradients sets ``w._hol_grad_sink``), with the tensor to write into -- or (None, None)."""
+    sink = getattr(w, "_hol_grad_sink", None)
+    if sink is None:
+        return None, None
+    out = sink.target(w)
+    return (sink, out) if out is not None else (None, None)
+
+
+def _pw_setup(ctx, inputs, output):
+    x, w, n, segments, length, discontinuous, periodicity = inputs
+    ctx.save_for_backward(x, w)
+    ctx.ws = output[1]       # plain attribute: the backward ops mutate the workspace (no version check wanted)
+    ctx.set_materialize_grads(False)
+    ctx.w_ref = w            # the caller's tensor object (carries the gradient-sink attribute)
+    ctx.args = (n, segments, length, discontinuous, periodicity)
+
+
+def _pw_bwd(ctx, gy, _gws=None):
+    """Backward of hol::pw_forward.  dW first (csrc/abi.cu): when the weight has a gradient sink the
+    slice's all-reduce is issued between the dW and the dX launches and overlaps the latter."""
+    x, w = ctx.saved_tensors
+    ws = ctx.ws
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dx = dw = None
+    if gy is None:  # y did not take part in the loss
+        return (None,) * 7
+    sink, out = _grad_sink(ctx.w_ref) if need_dw else (None, None)
+    if sink is not None:
+        pw_backward_dw_into(gy, x, w, ws, out, *ctx.args, True)
+        sink.ready(ctx.w_ref)
+        if need_dx:
+            dx = pw_backward(gy, x, w, ws, *ctx.args, True, False, True)[0]
+    elif need_dx or need_dw:
+        rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True)
+        dx = rdx if need_dx else None
+        dw = rdw if need_dw else None
+    return dx, dw, None, None, None, None, None
+
+
+pw_forward.register_autograd(_pw_bwd, setup_context=_pw_setup)
 
 
 def piecewise_polynomial(x: Tensor, w: Tensor, n: int, segments: int, length: float = 2.0,
                          discontinuous: bool = False, periodicity: Optional[float] = None) -> Tensor:
-    """Functional form of the layer: y = Piecewise(n, segments)(x) with weights w[O, I, nb]."""
-    if x.is_meta:  # shape propagation only (register_fake)
-        return pw_forward(x, w, torch.empty((0,), dtype=torch.uint8, device=x.device), n, segments, float(length),
-                          bool(discontinuous), periodicity)
-    _check_inputs(x, w, "piecewise_polynomial")
-    return _PiecewiseFn.apply(x, w, n, segments, float(length), bool(discontinuous), periodicity)
+    """Functional form of the layer: y = Piecewise(n, segments)(x) with weights w[O, I, nb].
+    ``hol::pw_forward`` is a functional, differentiable op (torch.library.register_autograd); its second
+    output is the scratch workspace the backward reuses."""
+    if not x.is_meta:
+        _check_inputs(x, w, "piecewise_polynomial")
+    return pw_forward(x, w, n, segments, float(length), bool(discontinuous), periodicity)[0]
 
 
 # ------------------------------------------------------------------------------------------
@@ -208,18 +258,25 @@ def conv_out_size(h: int, k: int, stride: int, padding: int, dilation: int) -> i
 def conv_workspace(x: Tensor, w_fc: Tensor, n: int, segments: int, discontinuous: bool, kernel_size: int,
                    stride: int, padding: int, dilation: int) -> Tensor:
     B, C, H, W = x.shape
-    nbytes = _lib.load().hol_pw_conv2d_workspace_bytes(B, C, H, W, w_fc.shape[0], kernel_size, stride, padding,
-                                                       dilation, n, segments, int(discontinuous))
-    if nbytes == 0:
-        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
+    nbytes = _conv_workspace_bytes(B, C, H, W, w_fc.shape[0], kernel_size, stride, padding, dilation, n, segments,
+                                   discontinuous)
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
 
 
-@torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=("ws",), device_types="cuda")
-def pw_conv2d_rows(x: Tensor, w_fc: Tensor, ws: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+def _conv_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments, discontinuous) -> int:
+    nbytes = _lib.load().hol_pw_conv2d_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments,
+                                                       int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
+    return int(nbytes)
+
+
+@torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=(), device_types="cuda")
+def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float, discontinuous: bool,
                    periodicity: Optional[float], kernel_size: int, stride: int, padding: int,
-                   dilation: int) -> Tensor:
-    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> y_rows[B*Ho*Wo, O]; `ws` from conv_workspace (mutated)."""
+                   dilation: int) -> Tuple[Tensor, Tensor]:
+    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> (y_rows[B*Ho*Wo, O], ws): the workspace of the call, reused by
+    ``hol::pw_conv2d_rows_backward``."""
     _check_inputs(x, w_fc, "pw_conv2d_rows")
     if x.dim() != 4:
         raise ValueError(f"pw_conv2d_rows: x must be [B, C, H, W], got {tuple(x.shape)}")
@@ -233,23 +290,27 @@ def pw_conv2d_rows(x: Tensor, w_fc: Tensor, ws: Tensor, n: int, segments: int, l
         raise ValueError("pw_conv2d_rows: kernel does not fit the input")
     lib = _lib.load()
     xc, wc = x.contiguous(), w_fc.contiguous()
-    nbytes = ws.numel()
+    ws = torch.empty(_conv_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments, discontinuous),
+                     dtype=torch.uint8, device=x.device)
     y = torch.empty((B * Ho * Wo, O), dtype=torch.float32, device=x.device)
     nodes = lobatto_nodes(n, length)  # conv builds its basis with the layer's length (LagrangePolynomial.py:242-246)
     with torch.cuda.device(x.device):
         _lib.check(lib.hol_pw_conv2d_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, C, H, W, O, K, stride,
                                                  padding, dilation, n, segments, length, int(discontinuous),
-                                                 _per(periodicity), _ptr(ws), nbytes, _stream(x)),
+                                                 _per(periodicity), _ptr(ws), ws.numel(), _stream(x)),
                    "hol_pw_conv2d_forward_f32")
-    return y
+    return y, ws
 
 
 @pw_conv2d_rows.register_fake
-def _(x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
+def _(x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
     B, C, H, W = x.shape
     Ho = conv_out_size(H, kernel_size, stride, padding, dilation)
     Wo = conv_out_size(W, kernel_size, stride, padding, dilation)
-    return torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device)
+    nbytes = _conv_workspace_bytes(int(B), int(C), int(H), int(W), int(w_fc.shape[0]), kernel_size, stride, padding,
+                                   dilation, n, segments, discontinuous)
+    return (torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device),
+            torch.empty((nbytes,), dtype=torch.uint8, device=x.device))
 
 
 @torch.library.custom_op("hol::pw_conv2d_rows_backward", mutates_args=("ws",), device_types="cuda")
@@ -282,28 +343,27 @@ def _(gy, x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_s
     return (torch.empty_like(x) if need_dx else e, torch.empty_like(w_fc) if need_dw else e)
 
 
-class _PiecewiseConvRowsFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
-        ws = conv_workspace(x, w_fc, n, segments, discontinuous, kernel_size, stride, padding, dilation)
-        y = pw_conv2d_rows(x, w_fc, ws, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding,
-                           dilation)
-        ctx.save_for_backward(x, w_fc)
-        ctx.ws = ws
-        ctx.args = (n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation)
-        return y
+def _conv_setup(ctx, inputs, output):
+    x, w_fc = inputs[:2]
+    ctx.save_for_backward(x, w_fc)
+    ctx.ws = output[1]
+    ctx.args = tuple(inputs[2:])
+    ctx.set_materialize_grads(False)
 
-    @staticmethod
-    @torch.autograd.function.once_differentiable
-    def backward(ctx, gy):
-        x, w_fc = ctx.saved_tensors
-        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dx = dw = None
-        if need_dx or need_dw:
-            rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ctx.ws, *ctx.args, need_dx, need_dw, True)
-            dx = rdx if need_dx else None
-            dw = rdw if need_dw else None
-        return (dx, dw) + (None,) * 9
+
+def _conv_bwd(ctx, gy, _gws=None):
+    x, w_fc = ctx.saved_tensors
+    ws = ctx.ws
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dx = dw = None
+    if gy is not None and (need_dx or need_dw):
+        rdx, rdw = pw_conv2d_rows_backward(gy, x, w_fc, ws, *ctx.args, need_dx, need_dw, True)
+        dx = rdx if need_dx else None
+        dw = rdw if need_dw else None
+    return (dx, dw) + (None,) * 9
+
+
+pw_conv2d_rows.register_autograd(_conv_bwd, setup_context=_conv_setup)
 
 
 def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
@@ -317,8 +377,8 @@ def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int
     nb = _nb(n, segments, discontinuous)
     w_fc = weight.view(O, C, nb, K, K).permute(0, 1, 3, 4, 2).reshape(O, C * K * K, nb)
     _check_inputs(x, w_fc, "piecewise_polynomial_conv2d")
-    y_rows = _PiecewiseConvRowsFn.apply(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K,
-                                        stride, padding, dilation)
+    y_rows = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K, stride,
+                            padding, dilation)[0]
     Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
     y = y_rows.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
     if rescale != 1.0:

@@ -45,6 +45,34 @@ def _worker(rank, world, port, ret):
         flat.params[0].grad.add_(1.0)
         flat.allreduce(average=False)
         assert torch.allclose(flat.params[0].grad, torch.full_like(flat.params[0], float(world)))
+        # the layers' gradient-sink protocol (ops._pw_bwd): target() hands out the parameter's slice, the dW
+        # kernel overwrites it, ready() starts the slice's all-reduce at once, finish() reduces the rest
+        flat.average = True
+        flat.begin()
+        p0, p1, p2 = flat.params
+        out = flat.target(p0)
+        assert out is not None and out.data_ptr() == p0.grad.data_ptr()
+        out.copy_(torch.full_like(p0, float(rank + 1)))
+        flat.ready(p0)
+        p1.grad.add_(10.0 * (rank + 1))          # autograd route
+        p2.grad.add_(100.0 * (rank + 1))
+        flat.finish()
+        mean = sum(r + 1 for r in range(world)) / world
+        assert torch.allclose(p0.grad, torch.full_like(p0, mean))
+        assert torch.allclose(p1.grad, torch.full_like(p1, 10.0 * mean))
+        assert torch.allclose(p2.grad, torch.full_like(p2, 100.0 * mean))
+        flat.begin()                              # the sink-written slice is not re-zeroed (it is overwritten) ...
+        assert torch.allclose(p0.grad, torch.full_like(p0, mean)) and not p1.grad.any() and not p2.grad.any()
+        try:                                      # ... and a second gradient for it within one step is refused
+            flat.ready(p0)
+            flat.target(p0)
+            raise AssertionError("expected RuntimeError")
+        except RuntimeError:
+            pass
+        # set_to_none breaks the aliasing; begin()/finish() re-home a freshly allocated gradient
+        p1.grad = None
+        flat.begin()
+        assert p1.grad.data_ptr() == flat.flat[flat._range[id(p1)][0]:].data_ptr()
         lo, hi = shard_range(65536 + 3, rank, world)
         t = torch.tensor([hi - lo], dtype=torch.int64)
         dist.all_reduce(t)

@@ -141,8 +141,14 @@ def test_fake_tensor_shapes():
     assert y.shape == (7, 3) and y.dtype == torch.float32
     xi = torch.empty(2, 3, 8, 8, device="meta")
     wf = torch.empty(4, 27, 9, device="meta")
-    yr = ops.pw_conv2d_rows(xi, wf, torch.empty(0, dtype=torch.uint8, device="meta"), 3, 4, 2.0, False, None, 3, 1, 0, 1)
-    assert yr.shape == (2 * 6 * 6, 4)
+    yr, ws = ops.pw_conv2d_rows(xi, wf, 3, 4, 2.0, False, None, 3, 1, 0, 1)
+    assert yr.shape == (2 * 6 * 6, 4) and ws.dtype == torch.uint8
+    assert ws.numel() == _lib.load().hol_pw_conv2d_workspace_bytes(2, 3, 8, 8, 4, 3, 1, 0, 1, 3, 4, 0)
+    # autograd through the fake ops (shape propagation of the gradients)
+    xm = torch.empty(7, 5, device="meta", requires_grad=True)
+    wm = torch.empty(3, 5, 9, device="meta", requires_grad=True)
+    ym = ops.piecewise_polynomial(xm, wm, 3, 4, 2.0, False, None)
+    assert ym.requires_grad
 
 
 def test_variant_layers_host_side():
