@@ -394,6 +394,27 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in wl["host"].items()}
                     for _ in range(2)]
 
+        # launch-bound workloads replay the captured step here too: one graph per input buffer
+        e2e_graphs = None
+        if graphed:
+            try:
+                e2e_graphs = []
+                for slot in (0, 1):
+                    for k, v in wl["host"].items():
+                        dev_bufs[slot][k].copy_(v)
+                    torch.cuda.synchronize()
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        loss2 = wl["e2e_compute"](dev_bufs[slot])
+                    e2e_graphs.append((g2, loss2))
+                torch.cuda.synchronize()
+            except Exception as e:
+                if rank == 0:
+                    print(f"bench.py: e2e graph capture failed ({type(e).__name__}: {str(e)[:120]}); eager e2e",
+                          file=sys.stderr)
+                torch.cuda.synchronize()
+                e2e_graphs = None
+
         def run_e2e(nsteps):
             ready = [torch.cuda.Event(), torch.cuda.Event()]
             consumed = [None, None]
@@ -413,7 +434,11 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                 if k + 1 < nsteps:
                     prefetch(slot ^ 1)
                 main_stream.wait_event(ready[slot])
-                loss = wl["e2e_compute"](dev_bufs[slot])
+                if e2e_graphs is not None:
+                    e2e_graphs[slot][0].replay()
+                    loss = e2e_graphs[slot][1]
+                else:
+                    loss = wl["e2e_compute"](dev_bufs[slot])
                 ev = torch.cuda.Event()
                 ev.record(main_stream)
                 consumed[slot] = ev
@@ -428,7 +453,10 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         run_e2e(e2e_steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        del dev_bufs
+        if e2e_graphs is not None:
+            for g2, _ in e2e_graphs:
+                g2.reset()
+        del dev_bufs, e2e_graphs
 
     tm = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -447,7 +475,8 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         res["e2e"] = {"value": wl["samples"] * world / (e2e_ms / e2e_steps / 1e3), "unit": "samples/s",
                       "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
                       "note": "module API; pinned-host inputs copied H2D and the loss read back D2H every step; "
-                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch)"}
+                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch)"
+                              + ("; the step is replayed from a CUDA graph captured per input buffer" if graphed else "")}
     peaks = load_peaks()
     res["step_algorithmic"] = {
         "bytes": wl["bytes"], "flops": wl["flops"],

@@ -14,6 +14,7 @@ from ._build import LIB_PATH
 HOL_MAX_N = 10
 HOL_MAX_SEGMENTS = 4096
 HOL_WS_PREPARED = 1
+HOL_GY_STATS_VALID = 2
 # hol_set_plan_overrides bits (diagnostic: tests / A-B runs force a kernel family)
 HOL_PLAN_DISABLE_TENSOR_CORES = 1
 HOL_PLAN_DISABLE_DENSE_DW = 2

@@ -146,9 +146,9 @@ int reset_scalars(const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
 // and the link means).
 // dW runs first: under data parallelism its all-reduce can then start while dX is still computing.
 int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, const float* w, float* dx,
-                    int dx_transposed, float* dw, bool packed, bool prepared, cudaStream_t st) {
+                    int dx_transposed, float* dw, bool packed, bool prepared, bool gy_stats_valid, cudaStream_t st) {
     const bool tc_dx = dx && s.n > 1 && s.tc.dx, tc_dw = dw && s.tc.dw;
-    if (tc_dx || tc_dw) HOL_TRY(launch_tc_gy_absmax(s, ws, gy, st));
+    if ((tc_dx || tc_dw) && !gy_stats_valid) HOL_TRY(launch_tc_gy_absmax(s, ws, gy, st));
     if (dw) {
         if (s.tc.dw) {
             HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, prepared && s.tc.fwd, st));
@@ -248,7 +248,7 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
         HOL_TRY(launch_prep_fc(x, s, ws, st));
     }
     return backward_common(s, ws, gy, w, dx, 0, dw, (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd,
-                           (flags & HOL_WS_PREPARED) != 0, st);
+                           (flags & HOL_WS_PREPARED) != 0, (flags & HOL_GY_STATS_VALID) != 0, st);
 }
 
 size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
@@ -312,7 +312,8 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
         HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     }
     HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc,
-                            (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, (flags & HOL_WS_PREPARED) != 0, st));
+                            (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, (flags & HOL_WS_PREPARED) != 0,
+                            (flags & HOL_GY_STATS_VALID) != 0, st));
     if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
     return HOL_OK;
 }
@@ -390,7 +391,7 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0, false) : 2);  // prep + (pack, forward)
     int c = prepared ? 0 : 1;  // prep
     const bool tc_dx = want_dx && n > 1 && s.tc.dx, tc_dw = want_dw && s.tc.dw;
-    if (tc_dx || tc_dw) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
+    if ((tc_dx || tc_dw) && !(flags & HOL_GY_STATS_VALID)) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
     if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2);
     if (want_dw)
         c += s.tc.dw ? tc_launch_count(s, s.tc, 2, prepared)

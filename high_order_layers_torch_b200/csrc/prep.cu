@@ -13,7 +13,8 @@
 // ---------------------------------------------------------------------------------------
 struct PrepConst {
     float length, half, Sf, half_per, two_per, per;
-    float xl_limit;  // tensor-core plans: |xl| above this is flagged HOL_SEG_OUTLIER (INFINITY otherwise)
+    float xl_limit;    // tensor-core plans: |xl| above this is flagged HOL_SEG_OUTLIER (INFINITY otherwise)
+    float inv_length;  // 1 / length when that is exact (length a power of two: 2.0 for every FC layer), else 0
     int S, periodic;
 };
 
@@ -26,6 +27,11 @@ static PrepConst make_prep_const(const PwShape& s) {
     c.two_per = s.two_per;
     c.per = s.periodicity;
     c.xl_limit = s.tc.enabled ? s.tc.xl_limit : INFINITY;
+    {
+        int e;
+        const float m = frexpf(s.length, &e);  // a power of two divides exactly like its reciprocal multiplies
+        c.inv_length = (m == 0.5f && e > -100 && e < 100) ? 1.0f / s.length : 0.0f;
+    }
     c.S = s.S;
     c.periodic = s.periodic;
     return c;
@@ -43,17 +49,25 @@ __device__ __forceinline__ float fold_periodic(float xv, const PrepConst& c, uin
 }
 
 __device__ __forceinline__ int segment_of(float xv, const PrepConst& c) {
-    float v = __fmul_rn(__fdiv_rn(__fadd_rn(xv, c.half), c.length), c.Sf);
+    const float sh = __fadd_rn(xv, c.half);
+    float v = __fmul_rn(c.inv_length != 0.0f ? __fmul_rn(sh, c.inv_length) : __fdiv_rn(sh, c.length), c.Sf);
     // .long() truncates toward zero, clamp(0, S-1) follows; NaN -> 0 like the reference on CPU
     return (v >= c.Sf) ? c.S - 1 : (v > 0.0f ? (int)v : 0);
 }
 
-__device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& xl, uint32_t& sg) {
+// eta(k) = k / float(S) * 2 - 1, the reference's three separately rounded ops (PolynomialLayers.py:338-344)
+__device__ __forceinline__ float eta_of(int k, const PrepConst& c) {
+    return __fsub_rn(__fmul_rn(__fdiv_rn((float)k, c.Sf), 2.0f), 1.0f);
+}
+
+// `eta`: optional table eta[0..S] in shared memory (the same values, computed once per CTA instead of
+// two divisions per element)
+__device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& xl, uint32_t& sg, const float* eta = nullptr) {
     uint32_t flags = 0;
     if (c.periodic) xv = fold_periodic(xv, c, flags);
     int s = segment_of(xv, c);
-    float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, c.Sf), 2.0f), 1.0f);
-    float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), c.Sf), 2.0f), 1.0f);
+    float e0 = eta ? eta[s] : eta_of(s, c);
+    float e1 = eta ? eta[s + 1] : eta_of(s + 1, c);
     float de = __fsub_rn(e1, e0);
     xl = __fsub_rn(__fmul_rn(c.length, __fdiv_rn(__fsub_rn(xv, e0), de)), c.half);
     if (fabsf(xl) > c.xl_limit) flags |= HOL_SEG_OUTLIER;  // NaN is not an outlier: it propagates like in the reference
@@ -102,7 +116,10 @@ __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict
                                                          PrepConst c, unsigned* stats) {
     __shared__ float t_xl[32][33];
     __shared__ uint16_t t_sg[32][34];
+    extern __shared__ float eta_tab[];  // [S + 1]
     const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int k = ty * 32 + tx; k <= c.S; k += 256) eta_tab[k] = eta_of(k, c);
+    __syncthreads();
     const int64_t b0 = (int64_t)blockIdx.x * 32;
     const int i0 = blockIdx.y * 32;
     float amax = 0.0f;
@@ -113,7 +130,7 @@ __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict
         const int i = i0 + tx;
         float xl = 0.0f;
         uint32_t sg = HOL_SEG_INVALID;
-        if (i < I && b < B) prep_elem(x[b * I + i], c, xl, sg);
+        if (i < I && b < B) prep_elem(x[b * I + i], c, xl, sg, eta_tab);
         prep_track(xl, sg, amax, nout);
         t_xl[tx][r] = xl;
         t_sg[tx][r] = (uint16_t)sg;
@@ -337,8 +354,8 @@ int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwSh
 
 int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
     dim3 grid((unsigned)(s.Bp / 32), (unsigned)((s.I + 31) / 32));
-    pw_prep_fc_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s),
-                                                    (unsigned*)ws.tc_scalars);
+    pw_prep_fc_kernel<<<grid, dim3(32, 8), (size_t)(s.S + 1) * sizeof(float), st>>>(
+        x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s), (unsigned*)ws.tc_scalars);
     return (int)cudaGetLastError();
 }
 

@@ -7,49 +7,64 @@
 // hi image then lo image.
 // ---------------------------------------------------------------------------------------
 
-// forward A: Phi tiles [m-tile (128 samples)][k-chunk], k = i*Kin + v
+// forward A: Phi tiles [m-tile (128 samples)][k-chunk], k = i*Kin + v.
+// One thread = one row x 32 dense columns (4 of the 8 k-groups of the chunk).  The n non-zero values
+// of an input sit at a column offset that depends on the sample's segment; instead of selecting every
+// one of the 32 columns out of the n basis values (n compares per column, the first version of this
+// kernel was issue bound at half the HBM rate), the thread scatters its (hi, lo) pairs into a private,
+// zeroed 32-word strip of shared memory -- shared memory takes run-time addresses, registers do not --
+// and reads the strip back as eight 16-byte chunks, which a byte permute splits into the hi and the lo
+// image.  HBM-bound: 16-byte coalesced stores of 2 x 32 KB per tile.
 template <int N>
 __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restrict__ xl_t, const uint16_t* __restrict__ seg_t,
                                                            unsigned char* __restrict__ tiles, const TcScalars* sc,
                                                            int64_t Bp, int64_t row0, int I, int Kin, int nkc, int stride,
                                                            const __grid_constant__ BasisTab tab) {
+    constexpr int PITCH = 36;  // words per strip: 32 columns + 4 (16-byte aligned, conflict-free LDS.128)
+    __shared__ __align__(16) uint32_t strip[256 * PITCH];
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int64_t mt = blockIdx.x;
     const int kc = blockIdx.y;
     const int64_t b = row0 + mt * TC_BM + r;
     const float scale = phi_scale(__uint_as_float(sc->max_xl), tab, N);
     unsigned char* base = tiles + ((mt * nkc + kc) * 2) * (int64_t)TC_A_IMG;
-    int cur_i = -1;
-    float phi[N];
-    int a0 = 0;
-    bool ok = false;
+    uint32_t* mine = strip + threadIdx.x * PITCH;
+    uint4* mine4 = reinterpret_cast<uint4*>(mine);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int kgl = half * 4 + q;
-        const int k0 = kc * TC_BK + kgl * 8;
-        const int i = k0 / Kin, v0 = k0 % Kin;
-        if (i != cur_i) {
-            cur_i = i;
-            ok = false;
-            if (i < I && b < Bp) {
-                const uint32_t sg = seg_t[(int64_t)i * Bp + b];
-                ok = !(sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER));
-                a0 = (int)(sg & HOL_SEG_MASK) * stride;
-                lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
+    for (int q = 0; q < 8; ++q) mine4[q] = make_uint4(0u, 0u, 0u, 0u);
+    const int c0 = kc * TC_BK + half * 32;  // first dense column of this thread's strip
+    if (b < Bp) {
+        const int i_lo = c0 / Kin, i_hi = min(I - 1, (c0 + 31) / Kin);
+        for (int i = i_lo; i <= i_hi; ++i) {
+            const uint32_t sg = seg_t[(int64_t)i * Bp + b];
+            if (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) continue;
+            float phi[N];
+            lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
+            const int col = i * Kin + (int)(sg & HOL_SEG_MASK) * stride - c0;  // strip column of phi_0
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const float a = phi[j] * scale;
+                const __half ha = __float2half_rn(a);
+                __half la = __float2half_rn(a - __half2float(ha));
+                // |a| < 2^-25 rounds to hi = lo = 0: keep the sign and the smallest subnormal (split_store8)
+                if (fabsf(a) <= 2.9802323e-8f && a != 0.0f) la = __ushort_as_half((unsigned short)(a > 0.0f ? 0x0001 : 0x8001));
+                if ((unsigned)(col + j) < 32u)
+                    mine[col + j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(la) << 16);
             }
         }
-        float v[8];
+    }
+    // strip word c = (hi | lo << 16) of column c0 + c  ->  hi image / lo image, 8 columns per 16-byte chunk
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = v0 + e - a0;
-            float val = 0.0f;
-#pragma unroll
-            for (int jj = 0; jj < N; ++jj) val = (j == jj) ? phi[jj] : val;
-            v[e] = ok ? val : 0.0f;
-        }
-        uint4* hi = reinterpret_cast<uint4*>(base + kgl * (TC_BM * 16) + r * 16);
-        uint4* lo = reinterpret_cast<uint4*>(base + TC_A_IMG + kgl * (TC_BM * 16) + r * 16);
-        split_store8(v, scale, hi, lo);
+    for (int q = 0; q < 4; ++q) {
+        const uint4 w0 = mine4[2 * q], w1 = mine4[2 * q + 1];
+        uint4 hi, lo;
+        hi.x = __byte_perm(w0.x, w0.y, 0x5410); lo.x = __byte_perm(w0.x, w0.y, 0x7632);
+        hi.y = __byte_perm(w0.z, w0.w, 0x5410); lo.y = __byte_perm(w0.z, w0.w, 0x7632);
+        hi.z = __byte_perm(w1.x, w1.y, 0x5410); lo.z = __byte_perm(w1.x, w1.y, 0x7632);
+        hi.w = __byte_perm(w1.z, w1.w, 0x5410); lo.w = __byte_perm(w1.z, w1.w, 0x7632);
+        const int kgl = half * 4 + q;
+        *reinterpret_cast<uint4*>(base + kgl * (TC_BM * 16) + r * 16) = hi;
+        *reinterpret_cast<uint4*>(base + TC_A_IMG + kgl * (TC_BM * 16) + r * 16) = lo;
     }
 }
 
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restri
     const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
     const int img = BN * TC_BK * 2;
     unsigned char* base = tiles + ((int64_t)(nt * nkc + kc) * 2) * img;
-    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < BN * 8; idx += gridDim.z * blockDim.x) {
         const int row = idx % BN, kgl = idx / BN;
         const int o = nt * BN + row;
         const int k0 = kc * TC_BK + kgl * 8;
@@ -136,17 +151,30 @@ __global__ void __launch_bounds__(256) pw_tc_wstats_kernel(const float* __restri
                                                            unsigned* max_w, int64_t links, int nb) {
     const int lane = threadIdx.x & 31;
     float amax = 0.0f;
-    for (int64_t link = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); link < links; link += (int64_t)gridDim.x * 8) {
-        float s = 0.0f;
-        for (int v = lane; v < nb; v += 32) {
-            const float x = w[link * nb + v];
-            s += x;
-            const float a = fabsf(x);
-            if (a < 3.0e38f) amax = fmaxf(amax, a);
+    if (nb <= 32) {  // short links: one thread per link (the 32 links of a warp are one contiguous stretch of w)
+        for (int64_t link = (int64_t)blockIdx.x * 256 + threadIdx.x; link < links; link += (int64_t)gridDim.x * 256) {
+            float s = 0.0f;
+            for (int v = 0; v < nb; ++v) {
+                const float x = w[link * nb + v];
+                s += x;
+                const float a = fabsf(x);
+                if (a < 3.0e38f) amax = fmaxf(amax, a);
+            }
+            if (wmean) wmean[link] = s / (float)nb;
         }
+    } else {
+        for (int64_t link = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); link < links; link += (int64_t)gridDim.x * 8) {
+            float s = 0.0f;
+            for (int v = lane; v < nb; v += 32) {
+                const float x = w[link * nb + v];
+                s += x;
+                const float a = fabsf(x);
+                if (a < 3.0e38f) amax = fmaxf(amax, a);
+            }
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-        if (lane == 0 && wmean) wmean[link] = s / (float)nb;
+            for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+            if (lane == 0 && wmean) wmean[link] = s / (float)nb;
+        }
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
@@ -162,7 +190,7 @@ __global__ void __launch_bounds__(256) pw_tc_pack_wt_kernel(const float* __restr
     const float scale = pow2_scale_for(__uint_as_float(sc->max_w));
     const int img = BN * TC_BK * 2;
     unsigned char* base = tiles + ((int64_t)(nt * noc + oc) * 2) * img;
-    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < BN * 8; idx += gridDim.z * blockDim.x) {
         const int row = idx % BN, ogl = idx / BN;
         const int R = nt * BN + row;
         const int i = R / Kin, col = R % Kin;
@@ -209,7 +237,7 @@ __global__ void __launch_bounds__(256) pw_tc_pack_gyt_kernel(const float* __rest
     const float scale = pow2_scale_for(__uint_as_float(sc->max_gy));
     const int img = BN * TC_BK * 2;
     unsigned char* base = tiles + ((int64_t)(nt * nbc + bc) * 2) * img;
-    for (int idx = threadIdx.x; idx < BN * 8; idx += blockDim.x) {
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < BN * 8; idx += gridDim.z * blockDim.x) {
         const int row = idx % BN, bgl = idx / BN;
         const int o = nt * BN + row;
         const int64_t b0 = row0 + (int64_t)bc * TC_BK + bgl * 8;

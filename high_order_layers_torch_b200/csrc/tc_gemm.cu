@@ -49,20 +49,16 @@ static int sm_count() {
 }
 
 // Output tile width.  A 128 x BN x 16 MMA takes ~BN/2 cycles down to BN = 128; at BN = 64 the shared-
-// memory read of the A tile binds (~48 instead of 32 cycles).  The forward has no split over K, so when
-// the batch gives too few tiles for the 148 SMs a narrower tile that doubles the CTA count wins.
+// memory read of the A tile binds (~48 instead of 32 cycles) and every Phi tile is fetched by twice as
+// many CTAs (measured at the 784 -> 128 layer of config 3: the forward with two 64-wide n-tiles ran at
+// the HBM rate of reading Phi twice, 128 us, against ~80 us of MMA time for one 128-wide tile on 64
+// SMs).  The forward has no split over K, so the tile is only narrowed when the batch gives fewer
+// than ~60 tiles (40 % of the SMs).
 static int tc_bn_for(int O, int64_t mtiles, bool may_shrink) {
-    const int bn_max = O > 128 ? 256 : (O > 64 ? 128 : 64);
-    if (!may_shrink) return bn_max;
-    int best = bn_max;
-    double best_cost = 1e30;
-    for (int bn = bn_max; bn >= 64; bn >>= 1) {
-        const int64_t tiles = mtiles * ((O + bn - 1) / bn);
-        const double waves = (double)((tiles + 147) / 148);
-        const double cost = waves * (bn == 256 ? 1.0 : (bn == 128 ? 0.5 : 0.375));
-        if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
-    }
-    return best;
+    int bn = O > 128 ? 256 : (O > 64 ? 128 : 64);
+    if (!may_shrink) return bn;
+    while (bn > 64 && mtiles * ((O + bn - 1) / bn) < 60 && (O + bn / 2 - 1) / (bn / 2) > (O + bn - 1) / bn) bn >>= 1;
+    return bn;
 }
 
 bool tc_plan(const PwShape& s, TcPlan& t) {
@@ -272,7 +268,7 @@ static void fill_fix(FixParams& f, const PwShape& s, const PwWorkspace& ws, cons
 int launch_tc_wstats(const PwShape& s, const PwWorkspace& ws, const float* w, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
     const int64_t links = (int64_t)s.O * s.I;
-    int64_t blocks = (links + 7) / 8;
+    int64_t blocks = s.nb <= 32 ? (links + 255) / 256 : (links + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     pw_tc_wstats_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, ws.tc_wmean, &sc->max_w, links, s.nb);
     return (int)cudaGetLastError();
@@ -303,7 +299,7 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
     int rc = launch_tc_wstats(s, ws, w, st);
     if (rc != HOL_OK) return rc;
-    dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc);
+    dim3 pgrid((unsigned)t.nNT, (unsigned)t.nkc, (unsigned)(t.BN * 8 / 256));
     pw_tc_pack_w_kernel<<<pgrid, 256, 0, st>>>(w, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.nkc, t.BN);
     rc = (int)cudaGetLastError();
     if (rc != HOL_OK) return rc;
@@ -349,7 +345,7 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
             if (rc != HOL_OK) return rc;
         }
         const int nbc = (int)((s.Bp + TC_BK - 1) / TC_BK);
-        dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc);
+        dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc, (unsigned)(t.BNw * 8 / 256));
         pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, (int64_t)0, s.O, nbc, t.BNw);
         rc = (int)cudaGetLastError();
         if (rc != HOL_OK) return rc;
@@ -383,7 +379,7 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
             DISPATCH_N(s.n, EXPANDT)
 #undef EXPANDT
             if (rc != HOL_OK) return rc;
-            dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc);
+            dim3 ggrid((unsigned)t.nNTw, (unsigned)nbc, (unsigned)(t.BNw * 8 / 256));
             pw_tc_pack_gyt_kernel<<<ggrid, 256, 0, st>>>(gy, (unsigned char*)ws.tc_b, sc, s.B, row0, s.O, nbc, t.BNw);
             rc = (int)cudaGetLastError();
             if (rc != HOL_OK) return rc;
@@ -413,7 +409,7 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         rc = launch_tc_wstats(s, ws, w, st);
         if (rc != HOL_OK) return rc;
     }
-    dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc);
+    dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc, (unsigned)((t.BNx * 8 + 255) / 256));
     pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, ws.tc_wmean, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc,
                                                 t.BNx);
     rc = (int)cudaGetLastError();

@@ -145,7 +145,10 @@ def _(x, w, n, segments, length, discontinuous, periodicity):
 @torch.library.custom_op("hol::pw_backward", mutates_args=("ws",), device_types="cuda")
 def pw_backward(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, n: int, segments: int, length: float,
                 discontinuous: bool, periodicity: Optional[float], need_dx: bool, need_dw: bool,
-                ws_prepared: bool) -> Tuple[Tensor, Tensor]:
+                ws_prepared: bool, gy_stats_valid: bool = False) -> Tuple[Tensor, Tensor]:
+    """-> (dx, dw) (an empty tensor stands for a gradient that was not asked for).  `ws_prepared`: the
+    workspace is the forward's; `gy_stats_valid`: it also holds max|gy| of this gy already (second half of
+    a backward that was split into a dW call and a dX call)."""
     _check_inputs(x, w, "pw_backward")
     B, I = x.shape
     O = w.shape[0]
@@ -158,13 +161,15 @@ def pw_backward(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, n: int, segments: 
         _lib.check(lib.hol_pw_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes), _ptr(dx if need_dx else None),
                                            _ptr(dw if need_dw else None), B, I, O, n, segments, length,
                                            int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
-                                           _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                                           (_lib.HOL_WS_PREPARED if ws_prepared else 0)
+                                           | (_lib.HOL_GY_STATS_VALID if gy_stats_valid else 0), _stream(x)),
                    "hol_pw_backward_f32")
     return dx, dw
 
 
 @pw_backward.register_fake
-def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, need_dw, ws_prepared):
+def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, need_dw, ws_prepared,
+      gy_stats_valid=False):
     e = torch.empty((0,), dtype=torch.float32, device=x.device)
     return (torch.empty_like(x) if need_dx else e, torch.empty_like(w) if need_dw else e)
 
@@ -227,7 +232,7 @@ def _pw_bwd(ctx, gy, _gws=None):
         pw_backward_dw_into(gy, x, w, ws, out, *ctx.args, True)
         sink.ready(ctx.w_ref)
         if need_dx:
-            dx = pw_backward(gy, x, w, ws, *ctx.args, True, False, True)[0]
+            dx = pw_backward(gy, x, w, ws, *ctx.args, True, False, True, True)[0]
     elif need_dx or need_dw:
         rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True)
         dx = rdx if need_dx else None

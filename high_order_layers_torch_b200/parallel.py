@@ -57,6 +57,7 @@ class FlatGradients:
         self._alias()
         self._side = torch.cuda.Stream(device=dev) if (overlap and dev.type == "cuda") else None
         self._works: list = []
+        self._side_used = False
         self._done: set = set()
         self._direct_ids: set = set()  # parameters whose layers wrote into the sink in the last step
 
@@ -117,6 +118,7 @@ class FlatGradients:
             self.flat[lo:hi].zero_()
         self._done.clear()
         self._works.clear()
+        self._side_used = False
 
     zero_ = begin  # the older name
 
@@ -146,6 +148,7 @@ class FlatGradients:
             return
         ev = torch.cuda.Event()
         ev.record()
+        self._side_used = True
         with torch.cuda.stream(self._side):
             self._side.wait_event(ev)
             self._reduce(lo, hi)
@@ -156,8 +159,10 @@ class FlatGradients:
         rest = [i for i in self._range if i not in self._done]
         if self._world() > 1:
             for lo, hi in self._ranges(rest):
-                self._reduce(lo, hi)
-        if self._side is not None:
+                self._reduce(lo, hi)          # on the current stream: nothing is left to overlap with
+        if self._side is not None and self._side_used:
+            # join the side stream (it forked from this one through an event, so the join is also valid
+            # inside a CUDA graph capture; an unused side stream must NOT be touched during a capture)
             with torch.cuda.stream(self._side):
                 for w in self._works:
                     w.wait()
@@ -166,6 +171,7 @@ class FlatGradients:
             for w in self._works:
                 w.wait()
         self._works.clear()
+        self._side_used = False
         # a parameter that was direct once but took the autograd route this time must be zero-filled again
         self._direct_ids &= self._done
 

@@ -62,6 +62,9 @@ extern "C" {
 /* flags for hol_pw_backward_f32 */
 #define HOL_WS_PREPARED 1u     /* `ws` still holds the forward's prepared state for the very
                                   same (x, w, shape): skip the prep + pack stages           */
+#define HOL_GY_STATS_VALID 2u  /* `ws` still holds max|gy| of this very gy, left by a previous
+                                  backward call of the same step (a backward split into a dw
+                                  call and a dx call takes the statistics once)              */
 
 int hol_abi_version(void);
 const char* hol_error_string(int code);

