@@ -44,10 +44,12 @@ class _PiecewiseConvolution2dBase(nn.Module):
         self._n = n
         self._segments = segments
         self._length = length
+        # the reference takes an int kernel_size (its initialiser multiplies it); stride / padding / dilation
+        # go to nn.Conv2d unchanged, so (h, w) pairs are accepted for them
         self._kernel_size = _as_int(kernel_size, "kernel_size")
-        self._stride = _as_int(stride, "stride")
-        self._padding = _as_int(padding, "padding")
-        self._dilation = _as_int(dilation, "dilation")
+        self._stride = ops._pair(stride, "stride")
+        self._padding = ops._pair(padding, "padding")
+        self._dilation = ops._pair(dilation, "dilation")
         self._in_channels = in_channels
         self._nodes = n * segments if self._discontinuous else (n - 1) * segments + 1
         self._channels = self._nodes * in_channels
@@ -101,7 +103,8 @@ class PiecewiseDiscontinuousPolynomialConvolution2d(_PiecewiseConvolution2dBase)
 
 class _PiecewiseConvolution1dBase(nn.Module):
     """1-d variants (reference FunctionalConvolution.py:493-519, :622-650): Expansion1d + nn.Conv1d in
-    the reference, here the fully connected kernels on unfolded rows.  Parameter ``conv.weight
+    the reference, here the convolution kernels with H = Kh = 1 (stride, zero padding and dilation handled
+    by the CUDA library's prep stage).  Parameter ``conv.weight
     [O, C*V, K]`` initialised by the reference's conv_wrapper recipe (uniform in +-wm/(C*V*K*K); the
     reference's 1-d classes do not apply the constant-per-link initialisation of the 2-d ones)."""
     _discontinuous = False
@@ -114,20 +117,18 @@ class _PiecewiseConvolution1dBase(nn.Module):
         name = type(self).__name__
         if groups != 1 or padding_mode != "zeros" or isinstance(padding, str):
             raise ValueError(f"{name}: groups != 1 / non-zero padding modes are not supported by the CUDA path")
-        if _as_int(padding, "padding") != 0:
-            raise ValueError(f"{name}: padding != 0 is not supported yet")
-        if float(length) != 2.0:
-            raise ValueError(f"{name}: only length=2.0 is supported")
         self._n, self._segments, self._length = n, segments, length
         self._kernel_size = _as_int(kernel_size, "kernel_size")
         self._stride, self._dilation = _as_int(stride, "stride"), _as_int(dilation, "dilation")
+        self._padding = _as_int(padding, "padding")
         self._nodes = n * segments if self._discontinuous else (n - 1) * segments + 1
         self._channels = self._nodes * in_channels
         self._out_channels = out_channels
         self.periodicity = periodicity
         k = self._kernel_size
         self.conv = nn.Conv1d(in_channels=self._channels, out_channels=out_channels, kernel_size=k,
-                              stride=self._stride, padding=0, dilation=self._dilation, groups=1, bias=False)
+                              stride=self._stride, padding=self._padding, dilation=self._dilation, groups=1,
+                              bias=False)
         in_features = self._channels * k * k          # the reference's conv_wrapper uses k*k for every rank
         if rescale_output is False:
             self.conv.weight.data.uniform_(-weight_magnitude / in_features, weight_magnitude / in_features)
@@ -144,8 +145,8 @@ class _PiecewiseConvolution1dBase(nn.Module):
                                "only and has no CPU fallback")
         return ops.piecewise_polynomial_conv1d(x, self.conv.weight, self._n, self._segments, self._kernel_size,
                                                length=float(self._length), discontinuous=self._discontinuous,
-                                               periodicity=self.periodicity, stride=self._stride, padding=0,
-                                               dilation=self._dilation, rescale=self._rescale)
+                                               periodicity=self.periodicity, stride=self._stride,
+                                               padding=self._padding, dilation=self._dilation, rescale=self._rescale)
 
 
 class PiecewisePolynomialConvolution1d(_PiecewiseConvolution1dBase):

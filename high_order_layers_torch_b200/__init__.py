@@ -16,10 +16,13 @@ from .layers import (  # noqa: F401
     MaxCenterNormalizationND,
     normalization_layers,
     convolutional_layers,
+    convolutional_transpose_layers,
     fc_layers,
     high_order_convolution_layers,
+    high_order_convolution_transpose_layers,
     high_order_fc_layers,
 )
+from .FunctionalConvolutionTranspose import PiecewisePolynomialConvolutionTranspose2d  # noqa: F401
 from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial  # noqa: F401
 from .FunctionalConvolution import (  # noqa: F401
     PiecewiseDiscontinuousPolynomialConvolution1d,

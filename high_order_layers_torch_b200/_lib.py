@@ -44,6 +44,13 @@ SIGNATURES = {
     "hol_pw_conv2d_backward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                                   _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _sz, _u32,
                                                   _vp]),
+    "hol_pw_conv_workspace_bytes": (_sz, [_i64, _vp, _i32, _i32, _i32, _i32]),
+    "hol_pw_conv_forward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _f32, _i32, _f32,
+                                               _vp, _sz, _vp]),
+    "hol_pw_conv_backward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _f32,
+                                                _i32, _f32, _vp, _sz, _u32, _vp]),
+    "hol_fold_rows_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hol_unfold_rows_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hol_pw_profile_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
                                           _f32, _vp, _sz, _vp, _vp]),
     "hol_row_norm_forward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

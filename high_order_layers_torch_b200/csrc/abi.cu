@@ -251,51 +251,58 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const f
                            (flags & HOL_WS_PREPARED) != 0, (flags & HOL_GY_STATS_VALID) != 0, st);
 }
 
-size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
-                                     int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
-                                     int32_t discontinuous) {
-    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return 0;
-    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
-    if (Ho <= 0 || Wo <= 0) return 0;
-    PwShape s;
-    if (make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
-    PwWorkspace ws;
-    return carve(s, nullptr, ws, Bimg * C * H * W);
+// ---- convolutions: rectangular geometry; the square 2-d entry points forward to it -----------------
+static bool conv_geom(HolConvGeom& g, const int32_t* q) {
+    if (!q) return false;
+    g.C = q[0], g.H = q[1], g.W = q[2], g.Kh = q[3], g.Kw = q[4], g.sh = q[5], g.sw = q[6], g.ph = q[7], g.pw = q[8];
+    g.dh = q[9], g.dw = q[10];
+    if (g.C <= 0 || g.H <= 0 || g.W <= 0 || g.Kh <= 0 || g.Kw <= 0 || g.sh <= 0 || g.sw <= 0 || g.dh <= 0 || g.dw <= 0 ||
+        g.ph < 0 || g.pw < 0)
+        return false;
+    g.Ho = conv_out(g.H, g.Kh, g.sh, g.ph, g.dh);
+    g.Wo = conv_out(g.W, g.Kw, g.sw, g.pw, g.dw);
+    return g.Ho > 0 && g.Wo > 0;
 }
 
-int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
-                              int32_t C, int32_t H, int32_t W, int32_t O, int32_t K, int32_t stride, int32_t padding,
-                              int32_t dilation, int32_t n, int32_t S, float length, int32_t discontinuous,
-                              float periodicity, void* ws_ptr, size_t ws_bytes, void* stream) {
-    if (!x || !w_fc || !nodes_host || !y_rows || !ws_ptr) return HOL_EINVAL;
-    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return HOL_EINVAL;
-    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
-    if (Ho <= 0 || Wo <= 0) return HOL_EINVAL;
+size_t hol_pw_conv_workspace_bytes(int64_t Bimg, const int32_t* geom, int32_t O, int32_t n, int32_t S,
+                                   int32_t discontinuous) {
+    HolConvGeom g;
+    if (Bimg < 0 || !conv_geom(g, geom)) return 0;
     PwShape s;
-    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
-    if (s.B == 0) return HOL_OK;
+    if (make_shape(s, Bimg * g.Ho * g.Wo, g.C * g.Kh * g.Kw, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return 0;
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
+    return carve(s, nullptr, ws, Bimg * g.C * g.H * g.W);
+}
+
+int hol_pw_conv_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
+                            const int32_t* geom, int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
+                            float periodicity, void* ws_ptr, size_t ws_bytes, void* stream) {
+    HolConvGeom g;
+    if (Bimg < 0 || !conv_geom(g, geom)) return HOL_EINVAL;
+    if (Bimg == 0) return HOL_OK;
+    if (!x || !w_fc || !nodes_host || !y_rows || !ws_ptr) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, Bimg * g.Ho * g.Wo, g.C * g.Kh * g.Kw, O, n, S, discontinuous, length, periodicity, nodes_host));
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, Bimg * g.C * g.H * g.W) > ws_bytes) return HOL_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(reset_scalars(s, ws, st));
-    HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+    HOL_TRY(launch_prep_conv(x, s, ws, Bimg, g, st));
     if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
     HOL_TRY(launch_pack(w_fc, s, ws, st));
     return launch_forward(s, ws, y_rows, st);
 }
 
-int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float* w_fc, const float* nodes_host,
-                               float* dx, float* dw_fc, int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O,
-                               int32_t K, int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
-                               float length, int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes,
-                               uint32_t flags, void* stream) {
-    if (Bimg < 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0) return HOL_EINVAL;
-    const int Ho = conv_out(H, K, stride, padding, dilation), Wo = conv_out(W, K, stride, padding, dilation);
-    if (Ho <= 0 || Wo <= 0) return HOL_EINVAL;
+int hol_pw_conv_backward_f32(const float* gy_rows, const float* x, const float* w_fc, const float* nodes_host, float* dx,
+                             float* dw_fc, int64_t Bimg, const int32_t* geom, int32_t O, int32_t n, int32_t S,
+                             float length, int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes,
+                             uint32_t flags, void* stream) {
+    HolConvGeom g;
+    if (Bimg < 0 || !conv_geom(g, geom)) return HOL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (Bimg == 0) {  // empty batch: dX is empty, dW is all zeros
         PwShape s0;
-        HOL_TRY(make_shape(s0, 0, C * K * K, O, n, S, discontinuous, length, periodicity, nullptr));
+        HOL_TRY(make_shape(s0, 0, g.C * g.Kh * g.Kw, O, n, S, discontinuous, length, periodicity, nullptr));
         if (dw_fc) {
             cudaError_t e = cudaMemsetAsync(dw_fc, 0, (size_t)O * s0.I * s0.nb * 4, st);
             if (e != cudaSuccess) return (int)e;
@@ -304,18 +311,46 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
     }
     if (!gy_rows || !x || !w_fc || !nodes_host || !ws_ptr) return HOL_EINVAL;
     PwShape s;
-    HOL_TRY(make_shape(s, Bimg * Ho * Wo, C * K * K, O, n, S, discontinuous, length, periodicity, nodes_host));
+    HOL_TRY(make_shape(s, Bimg * g.Ho * g.Wo, g.C * g.Kh * g.Kw, O, n, S, discontinuous, length, periodicity, nodes_host));
     PwWorkspace ws;
-    if (carve(s, ws_ptr, ws, Bimg * C * H * W) > ws_bytes) return HOL_EWORKSPACE;
+    if (carve(s, ws_ptr, ws, Bimg * g.C * g.H * g.W) > ws_bytes) return HOL_EWORKSPACE;
     if (!(flags & HOL_WS_PREPARED)) {
         HOL_TRY(reset_scalars(s, ws, st));
-        HOL_TRY(launch_prep_conv(x, s, ws, Bimg, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+        HOL_TRY(launch_prep_conv(x, s, ws, Bimg, g, st));
     }
     HOL_TRY(backward_common(s, ws, gy_rows, w_fc, dx ? ws.dx_rows : nullptr, 1, dw_fc,
                             (flags & HOL_WS_PREPARED) != 0 && !s.tc.fwd, (flags & HOL_WS_PREPARED) != 0,
                             (flags & HOL_GY_STATS_VALID) != 0, st));
-    if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, C, H, W, K, stride, padding, dilation, Ho, Wo, st));
+    if (dx) HOL_TRY(launch_col2im(ws.dx_rows, dx, Bimg, s.Bp, g, st));
     return HOL_OK;
+}
+
+#define HOL_SQUARE_GEOM(q) const int32_t q[11] = {C, H, W, K, K, stride, stride, padding, padding, dilation, dilation}
+
+size_t hol_pw_conv2d_workspace_bytes(int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O, int32_t K,
+                                     int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
+                                     int32_t discontinuous) {
+    HOL_SQUARE_GEOM(q);
+    return hol_pw_conv_workspace_bytes(Bimg, q, O, n, S, discontinuous);
+}
+
+int hol_pw_conv2d_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
+                              int32_t C, int32_t H, int32_t W, int32_t O, int32_t K, int32_t stride, int32_t padding,
+                              int32_t dilation, int32_t n, int32_t S, float length, int32_t discontinuous,
+                              float periodicity, void* ws_ptr, size_t ws_bytes, void* stream) {
+    HOL_SQUARE_GEOM(q);
+    return hol_pw_conv_forward_f32(x, w_fc, nodes_host, y_rows, Bimg, q, O, n, S, length, discontinuous, periodicity, ws_ptr,
+                                   ws_bytes, stream);
+}
+
+int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float* w_fc, const float* nodes_host,
+                               float* dx, float* dw_fc, int64_t Bimg, int32_t C, int32_t H, int32_t W, int32_t O,
+                               int32_t K, int32_t stride, int32_t padding, int32_t dilation, int32_t n, int32_t S,
+                               float length, int32_t discontinuous, float periodicity, void* ws_ptr, size_t ws_bytes,
+                               uint32_t flags, void* stream) {
+    HOL_SQUARE_GEOM(q);
+    return hol_pw_conv_backward_f32(gy_rows, x, w_fc, nodes_host, dx, dw_fc, Bimg, q, O, n, S, length, discontinuous,
+                                    periodicity, ws_ptr, ws_bytes, flags, stream);
 }
 
 int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const float* nodes_host, float* y, float* dx,

@@ -7,10 +7,13 @@
 
 int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwShape& s, cudaStream_t st);
 int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st);
-int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, int C, int H, int W, int K,
-                     int stride, int padding, int dilation, int Ho, int Wo, cudaStream_t st);
-int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, int C, int H, int W, int K, int stride,
-                  int padding, int dilation, int Ho, int Wo, cudaStream_t st);
+// convolution geometry (rectangular; 1-d convolutions are H = Kh = 1); Ho / Wo derived by the ABI layer
+struct HolConvGeom {
+    int C, H, W, Kh, Kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+};
+int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, const HolConvGeom& g,
+                     cudaStream_t st);
+int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, const HolConvGeom& g, cudaStream_t st);
 int launch_pack(const float* w, const PwShape& s, const PwWorkspace& ws, cudaStream_t st);
 int launch_bucket_sort(const PwShape& s, const PwWorkspace& ws, cudaStream_t st);
 

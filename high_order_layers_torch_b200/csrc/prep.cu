@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict
 
 // Implicit im2col: row = (b, ho, wo), input i = (c, kh, kw).  Taps that fall into the zero
 // padding are flagged invalid (the reference pads the expanded tensor, so they add nothing).
-struct ConvGeom {
-    int C, H, W, K, stride, padding, dilation, Ho, Wo;
+struct ConvGeom {  // rectangular geometry: 1-d convolutions are H = Kh = 1
+    int C, H, W, Kh, Kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
 };
 
 // Stage 1: the elementwise recipe once per pixel, image layout kept (NCHW).
@@ -184,16 +184,16 @@ __global__ void __launch_bounds__(256) pw_unfold_kernel(const float* __restrict_
     const int64_t t = row / g.Wo;
     const int ho = (int)(t % g.Ho);
     const int64_t b = t / g.Ho;
-    const int h0 = ho * g.stride - g.padding, w0 = wo * g.stride - g.padding;
+    const int h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
     int i = 0;
     for (int ch = 0; ch < g.C; ++ch) {
         const int64_t plane = (b * g.C + ch) * (int64_t)g.H * g.W;
-        for (int kh = 0; kh < g.K; ++kh) {
-            const int h = h0 + kh * g.dilation;
+        for (int kh = 0; kh < g.Kh; ++kh) {
+            const int h = h0 + kh * g.dh;
             const bool hok = live && h >= 0 && h < g.H;
 #pragma unroll 5
-            for (int kw = 0; kw < g.K; ++kw, ++i) {
-                const int w = w0 + kw * g.dilation;
+            for (int kw = 0; kw < g.Kw; ++kw, ++i) {
+                const int w = w0 + kw * g.dw;
                 float xl = 0.0f;
                 uint16_t sg = (uint16_t)HOL_SEG_INVALID;
                 if (hok && w >= 0 && w < g.W) {
@@ -220,21 +220,105 @@ __global__ void __launch_bounds__(256) pw_col2im_kernel(const float* __restrict_
     const int ch = (int)(t % g.C);
     const int64_t b = t / g.C;
     float acc = 0.0f;
-    for (int kh = 0; kh < g.K; ++kh) {
-        const int hn = h + g.padding - kh * g.dilation;
-        if (hn < 0 || hn % g.stride) continue;
-        const int ho = hn / g.stride;
+    for (int kh = 0; kh < g.Kh; ++kh) {
+        const int hn = h + g.ph - kh * g.dh;
+        if (hn < 0 || hn % g.sh) continue;
+        const int ho = hn / g.sh;
         if (ho >= g.Ho) continue;
-        for (int kw = 0; kw < g.K; ++kw) {
-            const int wn = w + g.padding - kw * g.dilation;
-            if (wn < 0 || wn % g.stride) continue;
-            const int wo = wn / g.stride;
+        for (int kw = 0; kw < g.Kw; ++kw) {
+            const int wn = w + g.pw - kw * g.dw;
+            if (wn < 0 || wn % g.sw) continue;
+            const int wo = wn / g.sw;
             if (wo >= g.Wo) continue;
-            const int i = (ch * g.K + kh) * g.K + kw;
+            const int i = (ch * g.Kh + kh) * g.Kw + kw;
             acc += dx_t[(int64_t)i * Bp + ((b * g.Ho + ho) * g.Wo + wo)];
         }
     }
     dx[e] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// conv-transpose (FunctionalConvolutionTranspose.py:75-160): the expansion followed by
+// nn.ConvTranspose2d equals the piecewise layer applied per input pixel (rows = B*H*W, inputs = C,
+// outputs = O*K*K) followed by a fold of the K*K taps onto the output grid
+//   y[b, o, h*s - p + kh*d, w*s - p + kw*d] += z[(b, h, w)][o*K*K + kh*K + kw].
+// fold gathers (one thread per output element, fixed order: no atomics), unfold is its adjoint.
+// ---------------------------------------------------------------------------------------
+struct FoldGeom {
+    int O, H, W, Ho, Wo, K, stride, padding, dilation;
+};
+
+__global__ void __launch_bounds__(256) pw_fold_rows_kernel(const float* __restrict__ z, float* __restrict__ y, int64_t total,
+                                                           FoldGeom g) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int wo = (int)(e % g.Wo);
+    int64_t t = e / g.Wo;
+    const int ho = (int)(t % g.Ho);
+    t /= g.Ho;
+    const int o = (int)(t % g.O);
+    const int64_t b = t / g.O;
+    const int64_t ld = (int64_t)g.O * g.K * g.K;
+    float acc = 0.0f;
+    for (int kh = 0; kh < g.K; ++kh) {
+        const int hn = ho + g.padding - kh * g.dilation;
+        if (hn < 0 || hn % g.stride) continue;
+        const int h = hn / g.stride;
+        if (h >= g.H) continue;
+        for (int kw = 0; kw < g.K; ++kw) {
+            const int wn = wo + g.padding - kw * g.dilation;
+            if (wn < 0 || wn % g.stride) continue;
+            const int w = wn / g.stride;
+            if (w >= g.W) continue;
+            acc += z[((b * g.H + h) * g.W + w) * ld + (o * g.K + kh) * g.K + kw];
+        }
+    }
+    y[e] = acc;
+}
+
+__global__ void __launch_bounds__(256) pw_unfold_rows_kernel(const float* __restrict__ gy, float* __restrict__ gz,
+                                                             int64_t total, FoldGeom g) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [rows][O*K*K]
+    if (e >= total) return;
+    const int kw = (int)(e % g.K);
+    int64_t t = e / g.K;
+    const int kh = (int)(t % g.K);
+    t /= g.K;
+    const int o = (int)(t % g.O);
+    t /= g.O;
+    const int w = (int)(t % g.W);
+    t /= g.W;
+    const int h = (int)(t % g.H);
+    const int64_t b = t / g.H;
+    const int ho = h * g.stride - g.padding + kh * g.dilation, wo = w * g.stride - g.padding + kw * g.dilation;
+    float v = 0.0f;
+    if (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) v = gy[((b * g.O + o) * g.Ho + ho) * (int64_t)g.Wo + wo];
+    gz[e] = v;
+}
+
+extern "C" int hol_fold_rows_f32(const float* z_rows, float* y, int64_t Bimg, int32_t O, int32_t H, int32_t W, int32_t Ho,
+                                 int32_t Wo, int32_t K, int32_t stride, int32_t padding, int32_t dilation, void* stream) {
+    if (Bimg < 0 || O <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0)
+        return HOL_EINVAL;
+    const int64_t total = Bimg * O * Ho * Wo;
+    if (total == 0) return HOL_OK;
+    if (!z_rows || !y) return HOL_EINVAL;
+    FoldGeom g{O, H, W, Ho, Wo, K, stride, padding, dilation};
+    pw_fold_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z_rows, y, total, g);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hol_unfold_rows_f32(const float* gy, float* gz_rows, int64_t Bimg, int32_t O, int32_t H, int32_t W,
+                                   int32_t Ho, int32_t Wo, int32_t K, int32_t stride, int32_t padding, int32_t dilation,
+                                   void* stream) {
+    if (Bimg < 0 || O <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || K <= 0 || stride <= 0 || dilation <= 0 || padding < 0)
+        return HOL_EINVAL;
+    const int64_t total = Bimg * H * W * O * K * K;
+    if (total == 0) return HOL_OK;
+    if (!gy || !gz_rows) return HOL_EINVAL;
+    FoldGeom g{O, H, W, Ho, Wo, K, stride, padding, dilation};
+    pw_unfold_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gy, gz_rows, total, g);
+    return (int)cudaGetLastError();
 }
 
 // w[O][I][nb] -> wk[nOT][I][R][OTP].  Packed row r = (c, a) = (r / RS, r % RS) holds reference
@@ -359,10 +443,14 @@ int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cuda
     return (int)cudaGetLastError();
 }
 
-int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, int C, int H, int W, int K,
-                     int stride, int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
-    ConvGeom g{C, H, W, K, stride, padding, dilation, Ho, Wo};
-    const int64_t count = Bimg * C * H * W;
+static ConvGeom make_geom(const HolConvGeom& c) {
+    return ConvGeom{c.C, c.H, c.W, c.Kh, c.Kw, c.sh, c.sw, c.ph, c.pw, c.dh, c.dw, c.Ho, c.Wo};
+}
+
+int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, int64_t Bimg, const HolConvGeom& cg,
+                     cudaStream_t st) {
+    const ConvGeom g = make_geom(cg);
+    const int64_t count = Bimg * g.C * g.H * g.W;
     if (count > 0) {
         pw_prep_image_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, ws.xl_img, ws.seg_img, count,
                                                                               make_prep_const(s), (unsigned*)ws.tc_scalars);
@@ -373,10 +461,9 @@ int launch_prep_conv(const float* x, const PwShape& s, const PwWorkspace& ws, in
     return (int)cudaGetLastError();
 }
 
-int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, int C, int H, int W, int K, int stride,
-                  int padding, int dilation, int Ho, int Wo, cudaStream_t st) {
-    ConvGeom g{C, H, W, K, stride, padding, dilation, Ho, Wo};
-    const int64_t total = Bimg * C * H * W;
+int launch_col2im(const float* dx_t, float* dx, int64_t Bimg, int64_t Bp, const HolConvGeom& cg, cudaStream_t st) {
+    const ConvGeom g = make_geom(cg);
+    const int64_t total = Bimg * g.C * g.H * g.W;
     if (total == 0) return HOL_OK;
     pw_col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dx_t, dx, total, Bp, g);
     return (int)cudaGetLastError();

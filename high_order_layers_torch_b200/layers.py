@@ -1,7 +1,7 @@
 """Layer registries and factories with the reference's names and error behaviour
 (reference layers.py:258-295, :357-372) restricted to the hot path: the keys ``continuous`` /
 ``discontinuous`` / ``polynomial`` (fully connected) and ``continuous2d`` / ``discontinuous2d``
-(convolution).  Asking for any other key
+(convolution) and ``continuous2d`` (conv-transpose).  Asking for any other key
 raises the same ValueError the reference raises for an unknown layer type."""
 from __future__ import annotations
 
@@ -10,6 +10,7 @@ import torch.nn as nn
 from .FunctionalConvolution import (PiecewiseDiscontinuousPolynomialConvolution1d,
                                     PiecewiseDiscontinuousPolynomialConvolution2d, PiecewisePolynomialConvolution1d,
                                     PiecewisePolynomialConvolution2d)
+from .FunctionalConvolutionTranspose import PiecewisePolynomialConvolutionTranspose2d
 from .PolynomialLayers import PiecewiseDiscontinuousPolynomial, PiecewisePolynomial, Polynomial
 from .utils import (l2_normalization, max_abs_normalization, max_abs_normalization_last, max_abs_normalization_nd,
                     max_center_normalization, max_center_normalization_nd)
@@ -113,6 +114,11 @@ convolutional_layers = {
 }
 
 
+convolutional_transpose_layers = {
+    "continuous2d": PiecewisePolynomialConvolutionTranspose2d,
+}
+
+
 def high_order_fc_layers(layer_type: str, **kwargs):
     if layer_type in fc_layers.keys():
         return fc_layers[layer_type](**kwargs)
@@ -125,3 +131,11 @@ def high_order_convolution_layers(layer_type: str, **kwargs):
         return convolutional_layers[layer_type](**kwargs)
     raise ValueError(
         f"Convolutional layer type {layer_type} not recognized.  Must be one of {list(convolutional_layers.keys())}")
+
+
+def high_order_convolution_transpose_layers(layer_type: str, **kwargs):
+    if layer_type in convolutional_transpose_layers.keys():
+        return convolutional_transpose_layers[layer_type](**kwargs)
+    raise ValueError(
+        f"ConvolutionalTranspose layer type {layer_type} not recognized.  Must be one of "
+        f"{list(convolutional_transpose_layers.keys())}")

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -254,64 +254,80 @@ def piecewise_polynomial(x: Tensor, w: Tensor, n: int, segments: int, length: fl
 
 
 # ------------------------------------------------------------------------------------------
-# unfolded 2-d convolution (rows = B*Ho*Wo, inputs = C*K*K)
+# unfolded convolution (rows = B*Ho*Wo, inputs = C*Kh*Kw); 1-d convolutions are H = Kh = 1
 # ------------------------------------------------------------------------------------------
 def conv_out_size(h: int, k: int, stride: int, padding: int, dilation: int) -> int:
     return (h + 2 * padding - dilation * (k - 1) - 1) // stride + 1
 
 
-def conv_workspace(x: Tensor, w_fc: Tensor, n: int, segments: int, discontinuous: bool, kernel_size: int,
-                   stride: int, padding: int, dilation: int) -> Tensor:
+def _pair(v, name: str) -> Tuple[int, int]:
+    if isinstance(v, (tuple, list)):
+        if len(v) == 1:
+            return int(v[0]), int(v[0])
+        if len(v) != 2:
+            raise ValueError(f"{name}={v}: one value or a pair expected")
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
+
+
+def _geom(C: int, H: int, W: int, kernel, stride, padding, dilation):
+    """{C, H, W, Kh, Kw, sh, sw, ph, pw, dh, dw} for the hol_pw_conv_* entry points + the output size."""
+    (kh, kw), (sh, sw), (ph, pw), (dh, dw) = (_pair(kernel, "kernel_size"), _pair(stride, "stride"),
+                                              _pair(padding, "padding"), _pair(dilation, "dilation"))
+    arr = (ctypes.c_int32 * 11)(C, H, W, kh, kw, sh, sw, ph, pw, dh, dw)
+    return arr, conv_out_size(H, kh, sh, ph, dh), conv_out_size(W, kw, sw, pw, dw)
+
+
+def _conv_workspace_bytes(B, C, H, W, O, kernel, stride, padding, dilation, n, segments, discontinuous) -> int:
+    g, _, _ = _geom(C, H, W, kernel, stride, padding, dilation)
+    nbytes = _lib.load().hol_pw_conv_workspace_bytes(B, ctypes.cast(g, ctypes.c_void_p), O, n, segments, int(discontinuous))
+    if nbytes == 0:
+        _lib.check(-2, "hol_pw_conv_workspace_bytes")
+    return int(nbytes)
+
+
+def conv_workspace(x: Tensor, w_fc: Tensor, n: int, segments: int, discontinuous: bool, kernel_size, stride, padding,
+                   dilation) -> Tensor:
     B, C, H, W = x.shape
     nbytes = _conv_workspace_bytes(B, C, H, W, w_fc.shape[0], kernel_size, stride, padding, dilation, n, segments,
                                    discontinuous)
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
 
 
-def _conv_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments, discontinuous) -> int:
-    nbytes = _lib.load().hol_pw_conv2d_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments,
-                                                       int(discontinuous))
-    if nbytes == 0:
-        _lib.check(-2, "hol_pw_conv2d_workspace_bytes")
-    return int(nbytes)
-
-
 @torch.library.custom_op("hol::pw_conv2d_rows", mutates_args=(), device_types="cuda")
 def pw_conv2d_rows(x: Tensor, w_fc: Tensor, n: int, segments: int, length: float, discontinuous: bool,
-                   periodicity: Optional[float], kernel_size: int, stride: int, padding: int,
-                   dilation: int) -> Tuple[Tensor, Tensor]:
-    """x[B,C,H,W], w_fc[O, C*K*K, nb] -> (y_rows[B*Ho*Wo, O], ws): the workspace of the call, reused by
-    ``hol::pw_conv2d_rows_backward``."""
+                   periodicity: Optional[float], kernel_size: Sequence[int], stride: Sequence[int],
+                   padding: Sequence[int], dilation: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """x[B,C,H,W], w_fc[O, C*Kh*Kw, nb] -> (y_rows[B*Ho*Wo, O], ws): the workspace of the call, reused by
+    ``hol::pw_conv2d_rows_backward``.  kernel_size / stride / padding / dilation are (h, w) pairs."""
     _check_inputs(x, w_fc, "pw_conv2d_rows")
     if x.dim() != 4:
         raise ValueError(f"pw_conv2d_rows: x must be [B, C, H, W], got {tuple(x.shape)}")
     B, C, H, W = x.shape
     O = w_fc.shape[0]
-    K = kernel_size
-    if tuple(w_fc.shape) != (O, C * K * K, _nb(n, segments, discontinuous)):
+    kh, kw = _pair(kernel_size, "kernel_size")
+    if tuple(w_fc.shape) != (O, C * kh * kw, _nb(n, segments, discontinuous)):
         raise ValueError(f"pw_conv2d_rows: weight shape {tuple(w_fc.shape)} does not match the layer")
-    Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
+    g, Ho, Wo = _geom(C, H, W, kernel_size, stride, padding, dilation)
     if Ho <= 0 or Wo <= 0:
         raise ValueError("pw_conv2d_rows: kernel does not fit the input")
     lib = _lib.load()
     xc, wc = x.contiguous(), w_fc.contiguous()
-    ws = torch.empty(_conv_workspace_bytes(B, C, H, W, O, K, stride, padding, dilation, n, segments, discontinuous),
-                     dtype=torch.uint8, device=x.device)
+    ws = torch.empty(_conv_workspace_bytes(B, C, H, W, O, kernel_size, stride, padding, dilation, n, segments,
+                                           discontinuous), dtype=torch.uint8, device=x.device)
     y = torch.empty((B * Ho * Wo, O), dtype=torch.float32, device=x.device)
     nodes = lobatto_nodes(n, length)  # conv builds its basis with the layer's length (LagrangePolynomial.py:242-246)
     with torch.cuda.device(x.device):
-        _lib.check(lib.hol_pw_conv2d_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, C, H, W, O, K, stride,
-                                                 padding, dilation, n, segments, length, int(discontinuous),
-                                                 _per(periodicity), _ptr(ws), ws.numel(), _stream(x)),
-                   "hol_pw_conv2d_forward_f32")
+        _lib.check(lib.hol_pw_conv_forward_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y), B, ctypes.cast(g, ctypes.c_void_p),
+                                               O, n, segments, length, int(discontinuous), _per(periodicity), _ptr(ws),
+                                               ws.numel(), _stream(x)), "hol_pw_conv_forward_f32")
     return y, ws
 
 
 @pw_conv2d_rows.register_fake
 def _(x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, stride, padding, dilation):
     B, C, H, W = x.shape
-    Ho = conv_out_size(H, kernel_size, stride, padding, dilation)
-    Wo = conv_out_size(W, kernel_size, stride, padding, dilation)
+    _, Ho, Wo = _geom(int(C), int(H), int(W), kernel_size, stride, padding, dilation)
     nbytes = _conv_workspace_bytes(int(B), int(C), int(H), int(W), int(w_fc.shape[0]), kernel_size, stride, padding,
                                    dilation, n, segments, discontinuous)
     return (torch.empty((B * Ho * Wo, w_fc.shape[0]), dtype=torch.float32, device=x.device),
@@ -320,9 +336,9 @@ def _(x, w_fc, n, segments, length, discontinuous, periodicity, kernel_size, str
 
 @torch.library.custom_op("hol::pw_conv2d_rows_backward", mutates_args=("ws",), device_types="cuda")
 def pw_conv2d_rows_backward(gy: Tensor, x: Tensor, w_fc: Tensor, ws: Tensor, n: int, segments: int, length: float,
-                            discontinuous: bool, periodicity: Optional[float], kernel_size: int, stride: int,
-                            padding: int, dilation: int, need_dx: bool, need_dw: bool,
-                            ws_prepared: bool) -> Tuple[Tensor, Tensor]:
+                            discontinuous: bool, periodicity: Optional[float], kernel_size: Sequence[int],
+                            stride: Sequence[int], padding: Sequence[int], dilation: Sequence[int], need_dx: bool,
+                            need_dw: bool, ws_prepared: bool) -> Tuple[Tensor, Tensor]:
     _check_inputs(x, w_fc, "pw_conv2d_rows_backward")
     B, C, H, W = x.shape
     O = w_fc.shape[0]
@@ -331,13 +347,14 @@ def pw_conv2d_rows_backward(gy: Tensor, x: Tensor, w_fc: Tensor, ws: Tensor, n: 
     dx = torch.empty_like(xc) if need_dx else torch.empty((0,), dtype=torch.float32, device=x.device)
     dw = torch.empty_like(wc) if need_dw else torch.empty((0,), dtype=torch.float32, device=x.device)
     nodes = lobatto_nodes(n, length)
+    g, _, _ = _geom(C, H, W, kernel_size, stride, padding, dilation)
     with torch.cuda.device(x.device):
-        _lib.check(lib.hol_pw_conv2d_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes),
-                                                  _ptr(dx if need_dx else None), _ptr(dw if need_dw else None), B, C,
-                                                  H, W, O, kernel_size, stride, padding, dilation, n, segments, length,
-                                                  int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
-                                                  _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
-                   "hol_pw_conv2d_backward_f32")
+        _lib.check(lib.hol_pw_conv_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes),
+                                                _ptr(dx if need_dx else None), _ptr(dw if need_dw else None), B,
+                                                ctypes.cast(g, ctypes.c_void_p), O, n, segments, length,
+                                                int(discontinuous), _per(periodicity), _ptr(ws), ws.numel(),
+                                                _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                   "hol_pw_conv_backward_f32")
     return dx, dw
 
 
@@ -371,24 +388,124 @@ def _conv_bwd(ctx, gy, _gws=None):
 pw_conv2d_rows.register_autograd(_conv_bwd, setup_context=_conv_setup)
 
 
-def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
+def piecewise_polynomial_conv2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size,
                                 length: float = 2.0, discontinuous: bool = False,
-                                periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
-                                dilation: int = 1, rescale: float = 1.0) -> Tensor:
-    """conv.weight[O, C*nb, K, K] layout in, NCHW out: the unfolded path of SURVEY 3.3."""
+                                periodicity: Optional[float] = None, stride=1, padding=0,
+                                dilation=1, rescale: float = 1.0) -> Tensor:
+    """conv.weight[O, C*nb, Kh, Kw] layout in, NCHW out: the unfolded path of SURVEY 3.3.  kernel_size,
+    stride, padding and dilation are ints or (h, w) pairs."""
     B, C, H, W = x.shape
     O = weight.shape[0]
-    K = kernel_size
+    kh, kw = _pair(kernel_size, "kernel_size")
     nb = _nb(n, segments, discontinuous)
-    w_fc = weight.view(O, C, nb, K, K).permute(0, 1, 3, 4, 2).reshape(O, C * K * K, nb)
+    w_fc = weight.view(O, C, nb, kh, kw).permute(0, 1, 3, 4, 2).reshape(O, C * kh * kw, nb)
     _check_inputs(x, w_fc, "piecewise_polynomial_conv2d")
-    y_rows = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, K, stride,
-                            padding, dilation)[0]
-    Ho, Wo = conv_out_size(H, K, stride, padding, dilation), conv_out_size(W, K, stride, padding, dilation)
+    ks, st, pd, dl = (list(_pair(v, k)) for v, k in ((kernel_size, "kernel_size"), (stride, "stride"),
+                                                     (padding, "padding"), (dilation, "dilation")))
+    y_rows = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, ks, st, pd, dl)[0]
+    Ho, Wo = conv_out_size(H, kh, st[0], pd[0], dl[0]), conv_out_size(W, kw, st[1], pd[1], dl[1])
     y = y_rows.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
     if rescale != 1.0:
         y = y * rescale
     return y
+
+
+def piecewise_polynomial_conv1d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
+                                length: float = 2.0, discontinuous: bool = False,
+                                periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
+                                dilation: int = 1, rescale: float = 1.0) -> Tensor:
+    """PiecewisePolynomialConvolution1d (reference FunctionalConvolution.py:493-519, :622-650): the 2-d path
+    with H = Kh = 1 -- the prep kernel unfolds the taps itself and flags the zero-padded ones invalid, so
+    padding, stride and dilation are all handled by the CUDA library.  x[B, C, L], conv.weight[O, C*nb, K]."""
+    if x.dim() != 3:
+        raise ValueError(f"piecewise_polynomial_conv1d: x must be [B, C, L], got {tuple(x.shape)}")
+    y = piecewise_polynomial_conv2d(x.unsqueeze(2), weight.unsqueeze(2), n, segments, (1, int(kernel_size)), length,
+                                    discontinuous, periodicity, (1, int(stride)), (0, int(padding)), (1, int(dilation)),
+                                    rescale)
+    return y.squeeze(2)
+
+
+# ------------------------------------------------------------------------------------------
+# conv-transpose: the piecewise layer per input pixel, then a fold of the taps onto the output grid
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("hol::fold_rows", mutates_args=(), device_types="cuda")
+def fold_rows(z_rows: Tensor, B: int, O: int, H: int, W: int, Ho: int, Wo: int, K: int, stride: int, padding: int,
+              dilation: int) -> Tensor:
+    """z_rows[B*H*W, O*K*K] -> y[B, O, Ho, Wo] (hol_fold_rows_f32)."""
+    if z_rows.dtype != torch.float32 or tuple(z_rows.shape) != (B * H * W, O * K * K):
+        raise ValueError(f"fold_rows: float32 [{B * H * W}, {O * K * K}] expected, got {z_rows.dtype} {tuple(z_rows.shape)}")
+    zc = z_rows.contiguous()
+    y = torch.empty((B, O, Ho, Wo), dtype=torch.float32, device=z_rows.device)
+    with torch.cuda.device(z_rows.device):
+        _lib.check(_lib.load().hol_fold_rows_f32(_ptr(zc), _ptr(y), B, O, H, W, Ho, Wo, K, stride, padding, dilation,
+                                                 _stream(z_rows)), "hol_fold_rows_f32")
+    return y
+
+
+@fold_rows.register_fake
+def _(z_rows, B, O, H, W, Ho, Wo, K, stride, padding, dilation):
+    return torch.empty((B, O, Ho, Wo), dtype=torch.float32, device=z_rows.device)
+
+
+@torch.library.custom_op("hol::unfold_rows", mutates_args=(), device_types="cuda")
+def unfold_rows(gy: Tensor, B: int, O: int, H: int, W: int, Ho: int, Wo: int, K: int, stride: int, padding: int,
+                dilation: int) -> Tensor:
+    """Adjoint of fold_rows: gy[B, O, Ho, Wo] -> gz_rows[B*H*W, O*K*K] (hol_unfold_rows_f32)."""
+    gc = gy.contiguous()
+    gz = torch.empty((B * H * W, O * K * K), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        _lib.check(_lib.load().hol_unfold_rows_f32(_ptr(gc), _ptr(gz), B, O, H, W, Ho, Wo, K, stride, padding, dilation,
+                                                   _stream(gy)), "hol_unfold_rows_f32")
+    return gz
+
+
+@unfold_rows.register_fake
+def _(gy, B, O, H, W, Ho, Wo, K, stride, padding, dilation):
+    return torch.empty((B * H * W, O * K * K), dtype=torch.float32, device=gy.device)
+
+
+def _fold_setup(ctx, inputs, output):
+    ctx.args = tuple(inputs[1:])
+
+
+def _fold_bwd(ctx, gy):
+    return (unfold_rows(gy, *ctx.args),) + (None,) * 10
+
+
+def _unfold_setup(ctx, inputs, output):
+    ctx.args = tuple(inputs[1:])
+
+
+def _unfold_bwd(ctx, gz):
+    return (fold_rows(gz, *ctx.args),) + (None,) * 10
+
+
+fold_rows.register_autograd(_fold_bwd, setup_context=_fold_setup)
+unfold_rows.register_autograd(_unfold_bwd, setup_context=_unfold_setup)
+
+
+def piecewise_polynomial_conv_transpose2d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
+                                          length: float = 2.0, discontinuous: bool = False,
+                                          periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
+                                          output_padding: int = 0, dilation: int = 1, rescale: float = 1.0) -> Tensor:
+    """PiecewisePolynomialConvolutionTranspose2d (reference FunctionalConvolutionTranspose.py:75-160):
+    x[B, C, H, W], conv.weight[C*nb, O, K, K] (nn.ConvTranspose2d layout) -> y[B, O, Ho, Wo]."""
+    B, C, H, W = x.shape
+    K = int(kernel_size)
+    nb = _nb(n, segments, discontinuous)
+    O = weight.shape[1]
+    if tuple(weight.shape) != (C * nb, O, K, K):
+        raise ValueError(f"piecewise_polynomial_conv_transpose2d: weight shape {tuple(weight.shape)} does not match "
+                         f"[{C * nb}, out_channels, {K}, {K}]")
+    # per input pixel: inputs = the C channels, outputs = (o, kh, kw)
+    w_fc = weight.view(C, nb, O, K, K).permute(2, 3, 4, 0, 1).reshape(O * K * K, C, nb)
+    _check_inputs(x, w_fc, "piecewise_polynomial_conv_transpose2d")
+    z = pw_conv2d_rows(x, w_fc, n, segments, float(length), bool(discontinuous), periodicity, [1, 1], [1, 1], [0, 0],
+                       [1, 1])[0]
+    Ho = (H - 1) * stride - 2 * padding + dilation * (K - 1) + output_padding + 1
+    Wo = (W - 1) * stride - 2 * padding + dilation * (K - 1) + output_padding + 1
+    y = fold_rows(z, B, O, H, W, Ho, Wo, K, stride, padding, dilation)
+    return y * rescale if rescale != 1.0 else y
 
 
 # ------------------------------------------------------------------------------------------
@@ -450,47 +567,6 @@ row_norm.register_autograd(_row_norm_bwd, setup_context=_row_norm_setup)
 def normalize_rows(x: Tensor, kind: str, eps: float = 1e-6) -> Tensor:
     """Fused per-sample normalisation over dim 1 of a CUDA fp32 [B, W] tensor."""
     return row_norm(x, NORM_KINDS[kind], float(eps))[0]
-
-
-# ------------------------------------------------------------------------------------------
-# 1-d convolution: the fully connected layer on unfolded rows (rows = B*Lo, inputs = C*K)
-# ------------------------------------------------------------------------------------------
-def conv1d_rows(x: Tensor, kernel_size: int, stride: int, dilation: int) -> Tensor:
-    """x[B, C, L] -> im2col rows [B*Lo, C*K], column c*K + k = x[b, c, lo*stride + k*dilation]."""
-    B, C, L = x.shape
-    Lo = conv_out_size(L, kernel_size, stride, 0, dilation)
-    if Lo <= 0:
-        raise ValueError("conv1d: kernel does not fit the input")
-    taps = (torch.arange(Lo, device=x.device).unsqueeze(1) * stride
-            + torch.arange(kernel_size, device=x.device).unsqueeze(0) * dilation)            # [Lo, K]
-    return x[:, :, taps].permute(0, 2, 1, 3).reshape(B * Lo, C * kernel_size)
-
-
-def conv1d_weight_as_fc(weight: Tensor, in_channels: int, nb: int) -> Tensor:
-    """conv.weight[O, C*nb, K] (expanded channel c*nb + v) -> w_fc[O, C*K, nb]."""
-    O, _, K = weight.shape
-    return weight.view(O, in_channels, nb, K).permute(0, 1, 3, 2).reshape(O, in_channels * K, nb)
-
-
-def piecewise_polynomial_conv1d(x: Tensor, weight: Tensor, n: int, segments: int, kernel_size: int,
-                                length: float = 2.0, discontinuous: bool = False,
-                                periodicity: Optional[float] = None, stride: int = 1, padding: int = 0,
-                                dilation: int = 1, rescale: float = 1.0) -> Tensor:
-    """PiecewisePolynomialConvolution1d (reference FunctionalConvolution.py:493-519, :622-650) as the
-    fully connected kernels on unfolded rows.  The unfold is a torch gather (autograd folds dX back);
-    zero padding would need the invalid-tap flag of the 2-d path and is not supported yet."""
-    if padding != 0:
-        raise ValueError("piecewise_polynomial_conv1d: padding != 0 is not supported yet")
-    if float(length) != 2.0:
-        raise ValueError("piecewise_polynomial_conv1d: only length=2.0 is supported")
-    B, C, L = x.shape
-    O = weight.shape[0]
-    nb = _nb(n, segments, discontinuous)
-    rows = conv1d_rows(x, kernel_size, stride, dilation)
-    w_fc = conv1d_weight_as_fc(weight, C, nb)
-    y_rows = piecewise_polynomial(rows, w_fc, n, segments, 2.0, discontinuous, periodicity)
-    y = y_rows.view(B, -1, O).permute(0, 2, 1)
-    return y * rescale if rescale != 1.0 else y
 
 
 def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, discontinuous: bool, want_dx: bool = True,

@@ -133,6 +133,32 @@ int hol_pw_conv2d_backward_f32(const float* gy_rows, const float* x, const float
                                float periodicity, void* ws, size_t ws_bytes, uint32_t flags,
                                void* stream);
 
+/* ---- rectangular / 1-d geometry (FunctionalConvolution.py:53-103 conv_wrapper kwargs; the 1-d layers
+ * :493-519, :622-650 are H = Kh = 1) -----------------------------------------------------------------
+ * geom = {C, H, W, Kh, Kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w} (HOST pointer, 11 values).
+ * I = C*Kh*Kw with column c*Kh*Kw + kh*Kw + kw; everything else as the square entry points above, which
+ * forward to these. */
+size_t hol_pw_conv_workspace_bytes(int64_t Bimg, const int32_t* geom, int32_t O, int32_t n, int32_t S,
+                                   int32_t discontinuous);
+int hol_pw_conv_forward_f32(const float* x, const float* w_fc, const float* nodes_host, float* y_rows, int64_t Bimg,
+                            const int32_t* geom, int32_t O, int32_t n, int32_t S, float length,
+                            int32_t discontinuous, float periodicity, void* ws, size_t ws_bytes, void* stream);
+int hol_pw_conv_backward_f32(const float* gy_rows, const float* x, const float* w_fc, const float* nodes_host,
+                             float* dx, float* dw_fc, int64_t Bimg, const int32_t* geom, int32_t O, int32_t n,
+                             int32_t S, float length, int32_t discontinuous, float periodicity, void* ws,
+                             size_t ws_bytes, uint32_t flags, void* stream);
+
+/* ---- conv-transpose (FunctionalConvolutionTranspose.py:75-160) --------------------------------------
+ * Expansion + nn.ConvTranspose2d == the piecewise layer per input pixel (hol_pw_conv_forward_f32 with
+ * a 1x1 kernel: rows = Bimg*H*W, I = C, O' = O*K*K, w_fc[O*K*K, C, nb]) followed by a fold of the K*K
+ * taps onto the output grid: y[b, o, h*s - p + kh*d, w*s - p + kw*d] += z[(b,h,w)][o*K*K + kh*K + kw].
+ * fold writes y[Bimg, O, Ho, Wo] (every element, gathered in a fixed order); unfold is its adjoint and
+ * writes gz_rows[Bimg*H*W, O*K*K] from gy[Bimg, O, Ho, Wo]. */
+int hol_fold_rows_f32(const float* z_rows, float* y, int64_t Bimg, int32_t O, int32_t H, int32_t W, int32_t Ho,
+                      int32_t Wo, int32_t K, int32_t stride, int32_t padding, int32_t dilation, void* stream);
+int hol_unfold_rows_f32(const float* gy, float* gz_rows, int64_t Bimg, int32_t O, int32_t H, int32_t W, int32_t Ho,
+                        int32_t Wo, int32_t K, int32_t stride, int32_t padding, int32_t dilation, void* stream);
+
 /* DIAGNOSTIC entry (the only one that synchronises): runs forward + backward once on `stream`
  * with CUDA events between the kernels and returns their durations in milliseconds in
  * ms_out_host[9] = {prep, pack, forward, dx, bucket_sort, dw, gemm_fwd, gemm_dx, gemm_dw}: the

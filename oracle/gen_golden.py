@@ -457,6 +457,86 @@ def main():
     c1["cases"] = np.array(c1_cases)
     np.savez_compressed(os.path.join(args.out, "conv1d.npz"), **c1)
 
+    # -------------------------------------------- round 2 (own RNG: the files above stay bit-identical)
+    # padded 1-d convolutions, paired 2-d geometry, conv-transpose (FunctionalConvolutionTranspose.py:75-160)
+    import high_order_layers_torch.FunctionalConvolutionTranspose as fct
+    rng2 = np.random.default_rng(20260101)
+    v2 = {}
+    names = []
+    for kind, cls in kinds1.items():
+        for (n, S, C, O, K, L, B, stride, pad, dil, resc) in [(3, 4, 2, 3, 3, 11, 2, 1, 1, 1, False),
+                                                              (2, 5, 3, 2, 4, 17, 2, 2, 3, 1, True),
+                                                              (4, 2, 1, 2, 3, 9, 3, 1, 2, 2, False)]:
+            layer = cls(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K, stride=stride, padding=pad,
+                        dilation=dil, rescale_output=resc)
+            with torch.no_grad():
+                layer.conv.weight.copy_(torch.from_numpy(
+                    rng2.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)))
+            x = rng2.uniform(-1.2, 1.2, size=(B, C, L)).astype(np.float32)
+            xt = torch.from_numpy(x.copy()).requires_grad_(True)
+            y = layer(xt)
+            gy = rng2.standard_normal(size=tuple(y.shape)).astype(np.float32)
+            y.backward(torch.from_numpy(gy))
+            name = f"conv1d_{kind}_n{n}_S{S}_K{K}_p{pad}"
+            v2[name + "_x"], v2[name + "_w"], v2[name + "_gy"] = x, layer.conv.weight.detach().numpy().copy(), gy
+            v2[name + "_y"] = y.detach().numpy().copy()
+            v2[name + "_dx"] = np.zeros_like(x) if xt.grad is None else xt.grad.numpy().copy()
+            v2[name + "_dw"] = layer.conv.weight.grad.numpy().copy()
+            v2[name + "_meta"] = np.array([n, S, C, O, K, L, B, stride, pad, dil, int(resc), int(kind == "disc")], dtype=np.int64)
+            names.append(name)
+    v2["conv1d_cases"] = np.array(names)
+    names = []
+    for (n, S, C, O, K, H, W, B, stride, pad, dil) in [(3, 4, 2, 3, 3, 9, 7, 2, (2, 1), (1, 2), (1, 1)),
+                                                     (2, 3, 1, 2, 2, 6, 8, 1, (1, 2), (0, 1), (2, 1))]:
+        layer = R.fcv.PiecewisePolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K,
+                                                       stride=stride, padding=pad, dilation=dil)
+        with torch.no_grad():
+            layer.conv.weight.copy_(torch.from_numpy(
+                rng2.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)))
+        x = rng2.uniform(-1.2, 1.2, size=(B, C, H, W)).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        y = layer(xt)
+        gy = rng2.standard_normal(size=tuple(y.shape)).astype(np.float32)
+        y.backward(torch.from_numpy(gy))
+        name = f"conv2d_n{n}_S{S}_K{K}_s{stride[0]}{stride[1]}"
+        v2[name + "_x"], v2[name + "_w"], v2[name + "_gy"] = x, layer.conv.weight.detach().numpy().copy(), gy
+        v2[name + "_y"], v2[name + "_dx"] = y.detach().numpy().copy(), xt.grad.numpy().copy()
+        v2[name + "_dw"] = layer.conv.weight.grad.numpy().copy()
+        v2[name + "_meta"] = np.array([n, S, C, O, K, H, W, B, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1]],
+                                      dtype=np.int64)
+        names.append(name)
+    v2["conv2d_cases"] = np.array(names)
+    names = []
+    for (n, S, C, O, K, H, W, B, stride, pad, opad, dil, resc, per) in [
+            (3, 4, 2, 3, 3, 5, 6, 2, 1, 0, 0, 1, False, None), (2, 3, 3, 2, 4, 4, 4, 2, 2, 1, 1, 1, True, None),
+            (4, 2, 1, 2, 3, 6, 5, 1, 2, 0, 0, 2, False, 2.0), (1, 3, 2, 2, 2, 3, 3, 2, 1, 0, 0, 1, False, None)]:
+        layer = fct.PiecewisePolynomialConvolutionTranspose2d(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K,
+                                                              stride=stride, padding=pad, output_padding=opad, dilation=dil,
+                                                              rescale_output=resc, periodicity=per)
+        with torch.no_grad():
+            layer.conv.weight.copy_(torch.from_numpy(
+                rng2.uniform(-1, 1, size=tuple(layer.conv.weight.shape)).astype(np.float32)))
+        x = rng2.uniform(-1.2, 1.2, size=(B, C, H, W)).astype(np.float32)
+        if per is not None:
+            x = rng2.uniform(-5, 5, size=(B, C, H, W)).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        y = layer(xt)
+        gy = rng2.standard_normal(size=tuple(y.shape)).astype(np.float32)
+        y.backward(torch.from_numpy(gy))
+        name = f"convT_n{n}_S{S}_K{K}_s{stride}"
+        v2[name + "_x"], v2[name + "_w"], v2[name + "_gy"] = x, layer.conv.weight.detach().numpy().copy(), gy
+        v2[name + "_y"] = y.detach().numpy().copy()
+        v2[name + "_dx"] = np.zeros_like(x) if xt.grad is None else xt.grad.numpy().copy()
+        v2[name + "_dw"] = layer.conv.weight.grad.numpy().copy()
+        v2[name + "_meta"] = np.array([n, S, C, O, K, H, W, B, stride, pad, opad, dil, int(resc)], dtype=np.int64)
+        v2[name + "_fmeta"] = np.array([np.nan if per is None else per], dtype=np.float64)
+        names.append(name)
+    v2["convT_cases"] = np.array(names)
+    torch.manual_seed(1234)
+    v2["init_convT_w"] = fct.PiecewisePolynomialConvolutionTranspose2d(
+        n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3).conv.weight.detach().numpy().copy()
+    np.savez_compressed(os.path.join(args.out, "variants2.npz"), **v2)
+
     total = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out))
     print(f"wrote {len(os.listdir(args.out))} files, {total/1e3:.1f} kB, to {os.path.abspath(args.out)}")
 

@@ -365,24 +365,70 @@ def expand2d(x, n: int, segments: int, length: float = 2.0, discontinuous: bool 
     return out.reshape(B, C * V, H, W)
 
 
+def _hw(v):
+    return (int(v[0]), int(v[1])) if isinstance(v, (tuple, list)) else (int(v), int(v))
+
+
 def conv2d_nchw(x, weight, stride=1, padding=0, dilation=1, dtype=np.float64) -> np.ndarray:
-    """Plain cross-correlation (what nn.Conv2d computes), zero padding, no bias, groups=1."""
+    """Plain cross-correlation (what nn.Conv2d computes), zero padding, no bias, groups=1.
+    stride / padding / dilation: ints or (h, w) pairs."""
     x = np.asarray(x).astype(dtype)
     weight = np.asarray(weight).astype(dtype)
     B, C, H, W = x.shape
     O, C2, KH, KW = weight.shape
     assert C == C2
-    if padding:
-        x = np.pad(x, ((0, 0), (0, 0), (padding, padding), (padding, padding)))
-    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
-    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    (sh, sw), (ph, pw), (dh, dw) = _hw(stride), _hw(padding), _hw(dilation)
+    if ph or pw:
+        x = np.pad(x, ((0, 0), (0, 0), (ph, ph), (pw, pw)))
+    Ho = (H + 2 * ph - dh * (KH - 1) - 1) // sh + 1
+    Wo = (W + 2 * pw - dw * (KW - 1) - 1) // sw + 1
     y = np.zeros((B, O, Ho, Wo), dtype=dtype)
     for kh in range(KH):
         for kw in range(KW):
-            patch = x[:, :, kh * dilation: kh * dilation + stride * (Ho - 1) + 1: stride,
-                      kw * dilation: kw * dilation + stride * (Wo - 1) + 1: stride]
+            patch = x[:, :, kh * dh: kh * dh + sh * (Ho - 1) + 1: sh, kw * dw: kw * dw + sw * (Wo - 1) + 1: sw]
             y += np.einsum("bchw,oc->bohw", patch, weight[:, :, kh, kw])
     return y
+
+
+def conv_transpose2d_nchw(x, weight, stride=1, padding=0, output_padding=0, dilation=1, dtype=np.float64) -> np.ndarray:
+    """What nn.ConvTranspose2d computes (no bias, groups=1): weight [C, O, K, K],
+    y[b, o, h*s - p + kh*d, w*s - p + kw*d] += x[b, c, h, w] * weight[c, o, kh, kw]."""
+    x = np.asarray(x).astype(dtype)
+    weight = np.asarray(weight).astype(dtype)
+    B, C, H, W = x.shape
+    C2, O, KH, KW = weight.shape
+    assert C == C2
+    Ho = (H - 1) * stride - 2 * padding + dilation * (KH - 1) + output_padding + 1
+    Wo = (W - 1) * stride - 2 * padding + dilation * (KW - 1) + output_padding + 1
+    full = np.zeros((B, O, Ho + 2 * padding, Wo + 2 * padding), dtype=dtype)
+    for kh in range(KH):
+        for kw in range(KW):
+            contrib = np.einsum("bchw,co->bohw", x, weight[:, :, kh, kw])
+            full[:, :, kh * dilation: kh * dilation + stride * (H - 1) + 1: stride,
+                 kw * dilation: kw * dilation + stride * (W - 1) + 1: stride] += contrib
+    return full[:, :, padding: padding + Ho, padding: padding + Wo]
+
+
+def pw_conv_transpose2d_forward(x, weight, n: int, segments: int, length: float = 2.0, periodicity: float | None = None,
+                                stride=1, padding=0, output_padding=0, dilation=1, rescale: float = 1.0, nodes=None,
+                                dtype=np.float64) -> np.ndarray:
+    """PiecewisePolynomialConvolutionTranspose.forward (FunctionalConvolutionTranspose.py:127-134)."""
+    x = np.asarray(x, dtype=F32)
+    if periodicity is not None:
+        x, _ = make_periodic_f32(x, periodicity)
+    ex = expand2d(x, n, segments, length, False, nodes, dtype)
+    return conv_transpose2d_nchw(ex, weight, stride, padding, output_padding, dilation, dtype) * dtype(rescale)
+
+
+def pw_conv1d_forward(x, weight, n: int, segments: int, length: float = 2.0, discontinuous: bool = False,
+                      periodicity: float | None = None, stride=1, padding=0, dilation=1, rescale: float = 1.0,
+                      nodes=None, dtype=np.float64) -> np.ndarray:
+    """PiecewisePolynomialConvolution1d / Discontinuous1d (FunctionalConvolution.py:493-519, :622-650):
+    Expansion1d + nn.Conv1d == the 2-d path with H = Kh = 1.  x [B, C, L], weight [O, C*V, K]."""
+    x = np.asarray(x, dtype=F32)
+    y = pw_conv2d_forward(x[:, :, None, :], np.asarray(weight)[:, :, None, :], n, segments, length, discontinuous,
+                          periodicity, (1, stride), (0, padding), (1, dilation), rescale, nodes, dtype)
+    return y[:, :, 0, :]
 
 
 def pw_conv2d_forward(x, weight, n: int, segments: int, length: float = 2.0,

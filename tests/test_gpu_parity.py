@@ -805,10 +805,14 @@ def test_opcheck_all_ops():
     opcheck(torch.ops.hol.pw_segment_index.default, (x, 4, 2.0, 2.0))
     xi = t(rng.uniform(-1, 1, size=(2, 3, 8, 8)).astype(np.float32))
     wf = t(rng.uniform(-1, 1, size=(4, 27, 9)).astype(np.float32))
-    ca = (3, 4, 2.0, False, None, 3, 1, 0, 1)
+    ca = (3, 4, 2.0, False, None, [3, 3], [1, 1], [0, 0], [1, 1])
     opcheck(torch.ops.hol.pw_conv2d_rows.default, (xi.clone().requires_grad_(True), wf.clone().requires_grad_(True)) + ca,
             test_utils=basic)
     wsc = ops.conv_workspace(xi, wf, 3, 4, False, 3, 1, 0, 1)
+    zr = t(rng.standard_normal(size=(2 * 4 * 5, 3 * 9)).astype(np.float32))
+    opcheck(torch.ops.hol.fold_rows.default, (zr.clone().requires_grad_(True), 2, 3, 4, 5, 9, 11, 3, 2, 0, 1))
+    gyf = t(rng.standard_normal(size=(2, 3, 9, 11)).astype(np.float32))
+    opcheck(torch.ops.hol.unfold_rows.default, (gyf.clone().requires_grad_(True), 2, 3, 4, 5, 9, 11, 3, 2, 0, 1))
     gr = t(rng.standard_normal(size=(2 * 6 * 6, 4)).astype(np.float32))
     opcheck(torch.ops.hol.pw_conv2d_rows_backward.default, (gr, xi, wf, wsc) + ca + (True, True, False), test_utils=basic)
     xn = t(rng.uniform(-2, 2, size=(9, 33)).astype(np.float32))
@@ -851,3 +855,61 @@ def test_gradient_sink_writes_dw_into_the_flat_buffer():
     flat.finish()
     for p, g in zip(net.parameters(), want):
         assert p.grad.data_ptr() >= flat.flat.data_ptr() and torch.equal(p.grad, g)
+
+
+def test_round2_variants_golden():
+    """SURVEY 8f-3, second batch (fixture variants2.npz from the unmodified reference): 1-d convolutions
+    with zero padding / stride / dilation handled by the CUDA library's prep stage (no torch unfold),
+    2-d convolutions with (h, w) stride / padding / dilation pairs, and the conv-transpose layer."""
+    g = load_golden("variants2.npz")
+    for name in g["conv1d_cases"]:
+        name = str(name)
+        n, S, C, O, K, L, B, stride, pad, dil, resc, disc = (int(v) for v in g[name + "_meta"])
+        cls = hol.PiecewiseDiscontinuousPolynomialConvolution1d if disc else hol.PiecewisePolynomialConvolution1d
+        layer = cls(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K, stride=stride, padding=pad,
+                    dilation=dil, rescale_output=bool(resc), device=DEV)
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        assert tuple(y.shape) == g[name + "_y"].shape, name
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+    for name in g["conv2d_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, s0, s1, p0, p1, d0, d1 = (int(v) for v in g[name + "_meta"])
+        layer = hol.PiecewisePolynomialConvolution2d(n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K,
+                                                     device=DEV, stride=(s0, s1), padding=(p0, p1), dilation=(d0, d1))
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        assert tuple(y.shape) == g[name + "_y"].shape, name
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+    for name in g["convT_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, stride, pad, opad, dil, resc = (int(v) for v in g[name + "_meta"])
+        per = float(g[name + "_fmeta"][0])
+        per = None if np.isnan(per) else per
+        layer = hol.high_order_convolution_transpose_layers(
+            "continuous2d", n=n, segments=S, in_channels=C, out_channels=O, kernel_size=K, stride=stride, padding=pad,
+            output_padding=opad, dilation=dil, rescale_output=bool(resc), periodicity=per, device=DEV)
+        assert layer.conv.weight.shape == g[name + "_w"].shape
+        with torch.no_grad():
+            layer.conv.weight.copy_(t(g[name + "_w"]))
+        xt = t(g[name + "_x"]).requires_grad_(True)
+        y = layer(xt)
+        assert tuple(y.shape) == g[name + "_y"].shape, name
+        y.backward(t(g[name + "_gy"]))
+        assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL, name
+        assert rel_err(layer.conv.weight.grad.cpu().numpy(), g[name + "_dw"]) < TOL, name
+        if n > 1:
+            assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
+        else:
+            assert not xt.grad.any()

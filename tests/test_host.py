@@ -141,7 +141,7 @@ def test_fake_tensor_shapes():
     assert y.shape == (7, 3) and y.dtype == torch.float32
     xi = torch.empty(2, 3, 8, 8, device="meta")
     wf = torch.empty(4, 27, 9, device="meta")
-    yr, ws = ops.pw_conv2d_rows(xi, wf, 3, 4, 2.0, False, None, 3, 1, 0, 1)
+    yr, ws = ops.pw_conv2d_rows(xi, wf, 3, 4, 2.0, False, None, [3, 3], [1, 1], [0, 0], [1, 1])
     assert yr.shape == (2 * 6 * 6, 4) and ws.dtype == torch.uint8
     assert ws.numel() == _lib.load().hol_pw_conv2d_workspace_bytes(2, 3, 8, 8, 4, 3, 1, 0, 1, 3, 4, 0)
     # autograd through the fake ops (shape propagation of the gradients)
@@ -149,6 +149,19 @@ def test_fake_tensor_shapes():
     wm = torch.empty(3, 5, 9, device="meta", requires_grad=True)
     ym = ops.piecewise_polynomial(xm, wm, 3, 4, 2.0, False, None)
     assert ym.requires_grad
+
+
+def test_conv_transpose_host_side():
+    g = load_golden("variants2.npz")
+    torch.manual_seed(1234)
+    ct = hol.high_order_convolution_transpose_layers("continuous2d", n=3, segments=4, in_channels=2, out_channels=3,
+                                                     kernel_size=3)
+    assert ct.conv.weight.shape == (18, 3, 3, 3)
+    assert np.array_equal(ct.conv.weight.detach().numpy(), g["init_convT_w"])
+    with pytest.raises(ValueError, match="not recognized"):
+        hol.high_order_convolution_transpose_layers("fourier2d", n=3, in_channels=2, out_channels=2, kernel_size=3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ct(torch.zeros(1, 2, 4, 4))
 
 
 def test_variant_layers_host_side():
@@ -240,28 +253,49 @@ def test_sparse_lion_matches_reference_fixture_cpu():
 
 
 def test_conv1d_unfold_mapping_and_init_match_reference():
-    """the 1-d convolution as the fully connected layer on unfolded rows: the unfold and
-    the conv.weight -> w_fc mapping are checked on CPU with the oracle standing in for the CUDA op
-    (fixture conv1d.npz from FunctionalConvolution.py:493-650), plus the initial weights for a seed."""
+    """the 1-d convolution is the 2-d path with H = Kh = 1: the weight mapping conv.weight
+    [O, C*V, K] -> w_fc [O, C*K, V] and the tap order c*K + k are checked on CPU with the oracle standing
+    in for the CUDA op (fixtures from FunctionalConvolution.py:493-650, incl. zero padding), plus the
+    initial weights for a seed."""
     from oracle import pw_oracle as orc
+    for fname, key, padded in (("conv1d.npz", "cases", False), ("variants2.npz", "conv1d_cases", True)):
+        g = load_golden(fname)
+        for name in g[key]:
+            name = str(name)
+            meta = [int(v) for v in g[name + "_meta"]]
+            if padded:
+                n, S, C, O, K, L, B, stride, pad, dil, resc, disc = meta
+            else:
+                (n, S, C, O, K, L, B, stride, dil, resc, disc), pad = meta, 0
+            nb = n * S if disc else (n - 1) * S + 1
+            x = g[name + "_x"]
+            xp = np.pad(x, ((0, 0), (0, 0), (pad, pad)))
+            Lo = (L + 2 * pad - dil * (K - 1) - 1) // stride + 1
+            taps = np.arange(Lo)[:, None] * stride + np.arange(K)[None, :] * dil                  # [Lo, K]
+            rows = xp[:, :, taps].transpose(0, 2, 1, 3).reshape(B * Lo, C * K)                     # column c*K + k
+            valid = ((taps >= pad) & (taps < pad + L))                                             # zero-padded taps add nothing
+            w_fc = torch.from_numpy(g[name + "_w"]).unsqueeze(2).view(O, C, nb, 1, K).permute(0, 1, 3, 4, 2) \
+                .reshape(O, C * K, nb).numpy()
+            nodes = ops.lobatto_nodes(n).numpy()
+            # the oracle has no invalid-tap flag: evaluate tap by tap and mask
+            y_rows = np.zeros((B * Lo, O))
+            for k in range(K):
+                cols = [c * K + k for c in range(C)]
+                part = orc.pw_forward(rows[:, cols], w_fc[:, cols], n, S, 2.0, bool(disc), None, nodes=nodes)
+                y_rows += part * np.tile(valid[:, k], B)[:, None]
+            y = y_rows.reshape(B, Lo, O).transpose(0, 2, 1) * (1.0 / (C * K * K) if resc else 1.0)
+            ref = g[name + "_y"]
+            assert y.shape == ref.shape, name
+            assert np.abs(y - ref).max() <= 2e-6 * max(np.abs(ref).max(), 1e-30), name
     g = load_golden("conv1d.npz")
-    for name in g["cases"]:
-        name = str(name)
-        n, S, C, O, K, L, B, stride, dil, resc, disc = (int(v) for v in g[name + "_meta"])
-        nb = n * S if disc else (n - 1) * S + 1
-        rows = ops.conv1d_rows(torch.from_numpy(g[name + "_x"]), K, stride, dil).numpy()
-        w_fc = ops.conv1d_weight_as_fc(torch.from_numpy(g[name + "_w"]), C, nb).numpy()
-        y_rows = orc.pw_forward(rows, w_fc, n, S, 2.0, bool(disc), None, nodes=ops.lobatto_nodes(n).numpy())
-        y = y_rows.reshape(B, -1, O).transpose(0, 2, 1) * (1.0 / (C * K * K) if resc else 1.0)
-        ref = g[name + "_y"]
-        assert y.shape == ref.shape, name
-        assert np.abs(y - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), name
     torch.manual_seed(1234)
     layer = hol.high_order_convolution_layers("continuous1d", n=3, segments=4, in_channels=2, out_channels=3,
                                               kernel_size=3)
     assert np.array_equal(layer.conv.weight.detach().numpy(), g["init_cont_w"])
+    padded = hol.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3, padding=1)
+    assert padded.conv.padding == (1,)
     with pytest.raises(ValueError):
-        hol.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3, padding=1)
+        hol.PiecewisePolynomialConvolution1d(n=3, segments=4, in_channels=2, out_channels=3, kernel_size=3, groups=2)
 
 
 def test_planner_sweep_is_consistent():

@@ -228,3 +228,30 @@ def test_dx_is_invariant_under_a_constant_per_link():
             # 5x the weight range moves dX by ~1e-7 relative -- the size of the artefact the centring drops
             assert np.abs(dx1 - dx0).max() < 1e-6 * np.abs(dx0).max(), (disc, n, S)
             assert np.array_equal(dw0, dw1)   # dW does not depend on w at all
+
+
+def test_round2_variants_against_reference_fixtures():
+    """variants2.npz (padded 1-d convolutions, paired 2-d geometry, conv-transpose): the oracle's
+    restatements reproduce the reference's outputs."""
+    g = load_golden("variants2.npz")
+    nodes = load_golden("nodes.npz")
+    for name in g["conv1d_cases"]:
+        name = str(name)
+        n, S, C, O, K, L, B, stride, pad, dil, resc, disc = (int(v) for v in g[name + "_meta"])
+        y = orc.pw_conv1d_forward(g[name + "_x"], g[name + "_w"], n, S, 2.0, bool(disc), None, stride, pad, dil,
+                                  1.0 / (C * K * K) if resc else 1.0, nodes=nodes[f"X_{n}"])
+        assert y.shape == g[name + "_y"].shape and rel_err(y, g[name + "_y"]) < 2e-6, name
+    for name in g["conv2d_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, s0, s1, p0, p1, d0, d1 = (int(v) for v in g[name + "_meta"])
+        y = orc.pw_conv2d_forward(g[name + "_x"], g[name + "_w"], n, S, 2.0, False, None, (s0, s1), (p0, p1), (d0, d1),
+                                  nodes=nodes[f"X_{n}"])
+        assert y.shape == g[name + "_y"].shape and rel_err(y, g[name + "_y"]) < 2e-6, name
+    for name in g["convT_cases"]:
+        name = str(name)
+        n, S, C, O, K, H, W, B, stride, pad, opad, dil, resc = (int(v) for v in g[name + "_meta"])
+        per = float(g[name + "_fmeta"][0])
+        per = None if np.isnan(per) else per
+        y = orc.pw_conv_transpose2d_forward(g[name + "_x"], g[name + "_w"], n, S, 2.0, per, stride, pad, opad, dil,
+                                            1.0 / (C * K * K) if resc else 1.0, nodes=nodes[f"X_{n}"])
+        assert y.shape == g[name + "_y"].shape and rel_err(y, g[name + "_y"]) < 2e-6, name
