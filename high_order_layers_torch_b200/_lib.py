@@ -19,6 +19,7 @@ HOL_GY_STATS_VALID = 2
 HOL_PLAN_DISABLE_TENSOR_CORES = 1
 HOL_PLAN_DISABLE_DENSE_DW = 2
 HOL_PLAN_NO_SHARED_PHI = 4
+HOL_PLAN_NO_CLUSTER = 16
 HOL_PLAN_FLUSH_SHIFT = 8
 
 _c_f32p = ctypes.c_void_p

@@ -17,6 +17,7 @@
 #define HOL_OVR_DISABLE_DWD HOL_PLAN_DISABLE_DENSE_DW
 #define HOL_OVR_NO_SHARE_PHI HOL_PLAN_NO_SHARED_PHI
 #define HOL_OVR_FLUSH_SHIFT HOL_PLAN_FLUSH_SHIFT
+#define HOL_OVR_NO_CLUSTER HOL_PLAN_NO_CLUSTER
 
 #define HOL_WARPS_SORT 8
 #define HOL_SORT_CHUNK 8192  // samples per bucket-sort CTA / dW split unit

@@ -175,9 +175,54 @@ void tc_prof_end(TcProf* prof, float* ms3) {
     prof->count = 0;
 }
 
+template <int EPI, int N, int AMODE, int CL>
+static int launch_gemm_cl(TcGemmParams p, int64_t mtiles, int ntiles_n, TcProf* prof, size_t smem, cudaStream_t st) {
+    static std::atomic<uint64_t> attr_done{0};
+    p.ntile_n = ntiles_n;
+    p.ntile_m = (mtiles + CL - 1) / CL;  // the rasterisation walks m-tiles or pairs of m-tiles
+    p.mt_last = mtiles - 1;
+    p.ntiles = p.ntile_m * ntiles_n;
+    p.nitems = p.ntiles * p.ksplit;
+    p.group_m = ntiles_n >= 12 ? 12 : (148 / CL + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
+    if (p.group_m > p.ntile_m) p.group_m = (int)p.ntile_m;
+    if (p.group_m < 1) p.group_m = 1;
+    auto kern = pw_tc_gemm_kernel<EPI, N, AMODE, CL>;
+    cudaError_t e = hol_ensure_max_smem(kern, attr_done);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t slots = sm_count() / CL;  // persistent: one CTA per SM, CL CTAs per work item
+    const unsigned grid = (unsigned)((p.nitems < slots ? p.nitems : slots) * CL);
+    const bool rec = prof && prof->count < 48;
+    if (rec) {
+        cudaEventCreate(&prof->ev[prof->count][0]);
+        cudaEventCreate(&prof->ev[prof->count][1]);
+        prof->kind[prof->count] = EPI;
+        cudaEventRecord(prof->ev[prof->count][0], st);
+    }
+    if (CL == 1) {
+        kern<<<grid, TC_THREADS, smem, st>>>(p);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = CL;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, p);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (rec) cudaEventRecord(prof->ev[prof->count++][1], st);
+    return (int)cudaGetLastError();
+}
+
 template <int EPI, int N, int AMODE>
 static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, int ksplit, TcProf* prof, cudaStream_t st) {
-    static std::atomic<uint64_t> attr_done{0};
     if (p.a_nkc == 0) p.a_nkc = p.nkc;
     const int stage = 2 * TC_A_IMG + 2 * p.BN * TC_BK * 2;
     int nst = (HOL_SMEM_BUDGET - 1024) / stage;
@@ -190,31 +235,15 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, int ksplit,
     // oracle with same-sign operands (the worst case, tools/check_flush_error.py): y / dX / dW relative
     // error 1.4e-6 / 1.7e-6 / 5e-7 at 2 chunks, 1.3e-6 / 2.3e-6 / 9e-7 at 4, while draining half as often
     // takes the dX GEMM of C2 from 15.7 to 13.6 ms.
-    p.ntile_n = ntiles_n;
-    p.ntile_m = mtiles;
-    p.ntiles = mtiles * ntiles_n;
     p.ksplit = ksplit < 1 ? 1 : ksplit;
     p.kc_per_split = (p.nkc + p.ksplit - 1) / p.ksplit;
     p.ksplit = (p.nkc + p.kc_per_split - 1) / p.kc_per_split;  // no empty work items
-    p.nitems = p.ntiles * p.ksplit;
-    p.group_m = ntiles_n >= 12 ? 12 : (148 + ntiles_n - 1) / ntiles_n;  // ~square block of co-running tiles
-    if (p.group_m > mtiles) p.group_m = (int)mtiles;
-    if (p.group_m < 1) p.group_m = 1;
-    auto kern = pw_tc_gemm_kernel<EPI, N, AMODE>;
-    cudaError_t e = hol_ensure_max_smem(kern, attr_done);
-    if (e != cudaSuccess) return (int)e;
-    const int64_t sms = sm_count();
-    const unsigned grid = (unsigned)(p.nitems < sms ? p.nitems : sms);  // persistent: one CTA per SM
-    const bool rec = prof && prof->count < 48;
-    if (rec) {
-        cudaEventCreate(&prof->ev[prof->count][0]);
-        cudaEventCreate(&prof->ev[prof->count][1]);
-        prof->kind[prof->count] = EPI;
-        cudaEventRecord(prof->ev[prof->count][0], st);
-    }
-    kern<<<grid, TC_THREADS, smem, st>>>(p);
-    if (rec) cudaEventRecord(prof->ev[prof->count++][1], st);
-    return (int)cudaGetLastError();
+    // Pairs of m-tiles as two-CTA clusters that multicast the B tile to each other (tc_kernel.cuh) whenever
+    // there are enough pairs to fill the machine; small problems keep single CTAs.
+    const int64_t pair_items = ((mtiles + 1) / 2) * ntiles_n * p.ksplit;
+    const bool pairs = mtiles >= 2 && pair_items >= 32 && !(hol_plan_overrides() & HOL_OVR_NO_CLUSTER);
+    return pairs ? launch_gemm_cl<EPI, N, AMODE, 2>(p, mtiles, ntiles_n, prof, smem, st)
+                 : launch_gemm_cl<EPI, N, AMODE, 1>(p, mtiles, ntiles_n, prof, smem, st);
 }
 
 // kernels of ours per call (bench.py's gpu_launches): kind 0 forward, 1 dX, 2 dW, 3 the shared

@@ -64,6 +64,33 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in `mask` of the cluster; each
+// destination CTA's mbarrier (same offset) receives complete_tx for the bytes that landed in it
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 struct TcGemmParams {
     const unsigned char* a_tiles;  // [m-tile][k-chunk][hi|lo] images of 128 rows
     const unsigned char* b_tiles;  // [n-tile][k-chunk][hi|lo] images of BN rows
@@ -74,7 +101,9 @@ struct TcGemmParams {
     int64_t row0, rows_valid, Bp;  // EPI_Y/DX: batch rows of this launch; EPI_DW: row0 > 0 => accumulate into out
     int64_t ntiles;                // m-tiles * n-tiles
     int64_t nitems;                // ntiles * ksplit
-    int64_t ntile_m;
+    int64_t ntile_m;               // m-tiles (CL = 1) or pairs of m-tiles (CL = 2) the rasterisation walks
+    int64_t mt_last;               // last valid m-tile (a pair may end on a tile that does not exist: loads are
+                                   // clamped to this tile and its epilogue stores nothing)
     int64_t part_stride;           // EPI_DW, ksplit > 1: floats between the partial results of two k-splits
     int ntile_n, group_m;          // rasterisation: groups of group_m m-tiles, m fastest inside a group
     int ksplit, kc_per_split;      // the k-chunks of a tile are split over ksplit work items
@@ -97,7 +126,7 @@ __device__ __forceinline__ void tile_coords(const TcGemmParams& p, int64_t tile,
     mt = first_m + local % gsize;
     nt = (int)(local / gsize);
 }
-// work item -> (m-tile, n-tile, k-chunk range)
+// work item -> (m-tile or m-tile pair, n-tile, k-chunk range)
 __device__ __forceinline__ void item_coords(const TcGemmParams& p, int64_t item, int64_t& mt, int& nt, int& ks, int& kc_lo,
                                             int& kc_hi) {
     ks = (int)(item % p.ksplit);
@@ -147,10 +176,17 @@ __device__ __forceinline__ void dx_pick(const float (&racc)[TC_MAXHALF], int bas
 //            samples (half a batch tile), gathered by the producer warp with 16-byte cp.async copies
 //            into the canonical MN-major no-swizzle layout
 //            [image][column group of 8][64 samples][8 x fp16]  (SBO = 1024 B, LBO = 128 B)
+// CL = 2: the kernel runs as clusters of two CTAs that own two NEIGHBOURING m-tiles of the same n-tile.
+// Both need the same B tile: each CTA fetches one of its two fp16 images (hi / lo) and multicasts it
+// into both shared memories, so a k-chunk costs every CTA 32 KB (A) + 32 KB (half of B) of L2 reads
+// instead of 32 + 64 -- these GEMMs run at the L2 -> SM bandwidth cap (~42 B/clk/SM: 96 KB per 1536-cycle
+// MMA chunk is more than the cap delivers), so the bytes per chunk are what sets their speed.  A stage
+// may only be refilled when BOTH CTAs' MMAs are done with it (the peer writes into it), hence the
+// `empty` barriers count two commits, multicast by each MMA warp to both CTAs.
 enum { A_TILES = 0, A_PHI_MN = 2 };
 #define TC_THREADS 384
 
-template <int EPI, int N, int AMODE>
+template <int EPI, int N, int AMODE, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int BN = p.BN;
@@ -165,6 +201,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;  // this CTA's m-tile inside the pair
+    const int64_t cid = blockIdx.x / CL, ncl = gridDim.x / CL;  // cluster id / number of clusters
     const int nst = p.nst;
     const int FG = p.flush_chunks;
     uint32_t tmem_cols = 32;
@@ -175,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             // A_PHI_MN: the bulk copy of B (expect_tx arrival of lane 0) + one asynchronous arrival per
             // producer lane when its cp.async copies of the stage have landed
             mbar_init(&full[s], AMODE == A_PHI_MN ? 33 : 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);  // one tcgen05.commit per CTA of the cluster
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -191,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -209,10 +248,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
         // (cp.async.mbarrier.arrive.noinc), so the warp runs ahead over the whole ring instead of
         // waiting for every stage to land before issuing the next one.
         int it = 0;
-        for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        for (int64_t item = cid; item < p.nitems; item += ncl) {
             int nt, ks, kc_lo, kc_hi;
             int64_t mt;
             item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
+            mt = min(mt * CL + (int64_t)crank, p.mt_last);  // this CTA's m-tile (clamped: a pair may end on a missing tile)
             const unsigned char* a_mt = p.a_tiles + (2 * mt) * (int64_t)(2 * TC_A_IMG) + lane * 16;
             const int64_t a_bt = (int64_t)p.a_nkc * (2 * TC_A_IMG);  // bytes per batch tile
             const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
@@ -222,7 +262,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                 unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
                 if (lane == 0) {
                     mbar_expect_tx(&full[st], (uint32_t)(2 * B_IMG));
-                    bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)sc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
+                    if (CL == 2)  // this CTA's image of the B tile (hi: rank 0, lo: rank 1) goes to both CTAs
+                        bulk_g2s_multicast(dst + 2 * TC_A_IMG + crank * B_IMG, b_src + (int64_t)sc * (2 * B_IMG) + crank * B_IMG,
+                                           (uint32_t)B_IMG, &full[st], (uint16_t)3);
+                    else
+                        bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)sc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
                 }
                 // samples 64*(sc & 1) .. +63 of batch tile sc >> 1
                 const unsigned char* src = a_mt + (int64_t)(sc >> 1) * a_bt + (sc & 1) * 1024;
@@ -239,13 +283,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");  // nothing in flight when the CTA exits
+        if (CL == 2)  // tail: every commit the peer's MMA warp multicasts to this CTA's barriers has landed
+            for (int k = 0; k < nst; ++k, ++it) mbar_wait(&empty[it % nst], (uint32_t)(((it / nst) & 1) ^ 1));
     } else if (warp == 0) {
         if (elect_one()) {
             int it = 0;
-            for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            for (int64_t item = cid; item < p.nitems; item += ncl) {
                 int nt, ks, kc_lo, kc_hi;
                 int64_t mt;
                 item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
+                mt = min(mt * CL + (int64_t)crank, p.mt_last);
                 const unsigned char* a_src = p.a_tiles + (mt * p.a_nkc) * (int64_t)(2 * TC_A_IMG);
                 const unsigned char* b_src = p.b_tiles + ((int64_t)nt * p.nkc) * (int64_t)(2 * B_IMG);
                 for (int kc = kc_lo; kc < kc_hi; ++kc, ++it) {
@@ -254,9 +301,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                     unsigned char* dst = stages + (size_t)st * STAGE_BYTES;
                     mbar_expect_tx(&full[st], (uint32_t)STAGE_BYTES);
                     bulk_g2s(dst, a_src + (int64_t)kc * (2 * TC_A_IMG), 2 * TC_A_IMG, &full[st]);
-                    bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
+                    if (CL == 2)
+                        bulk_g2s_multicast(dst + 2 * TC_A_IMG + crank * B_IMG, b_src + (int64_t)kc * (2 * B_IMG) + crank * B_IMG,
+                                           (uint32_t)B_IMG, &full[st], (uint16_t)3);
+                    else
+                        bulk_g2s(dst + 2 * TC_A_IMG, b_src + (int64_t)kc * (2 * B_IMG), (uint32_t)(2 * B_IMG), &full[st]);
                 }
             }
+            if (CL == 2)  // tail: every commit the peer's MMA warp multicasts to this CTA's barriers has landed
+                for (int k = 0; k < nst; ++k, ++it) mbar_wait(&empty[it % nst], (uint32_t)(((it / nst) & 1) ^ 1));
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -268,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             const uint32_t LBO_A = AMODE == A_PHI_MN ? 128u : TC_BM * 16, SBO_A = AMODE == A_PHI_MN ? 1024u : 128u;
             const uint32_t LBO_B = (uint32_t)BN * 16, SBO = 128;
             int it = 0, g = 0;
-            for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            for (int64_t item = cid; item < p.nitems; item += ncl) {
                 const int ks = (int)(item % p.ksplit);
                 const int kc_lo = ks * p.kc_per_split, kc_hi = min(p.nkc, kc_lo + p.kc_per_split);
                 for (int kc = kc_lo; kc < kc_hi; ++kc, ++it) {
@@ -296,7 +349,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                         umma_f16(td, a_hi, b_lo, idesc, 1u);
                         umma_f16(td, a_lo, b_hi, idesc, 1u);
                     }
-                    umma_commit(&empty[st]);  // arrives when the MMAs above have finished reading this stage
+                    // arrives when the MMAs above have finished reading this stage -- on the peer's barrier too:
+                    // the peer's producer writes its B image into this CTA's stage
+                    if (CL == 2) umma_commit_multicast(&empty[st], (uint16_t)3);
+                    else umma_commit(&empty[st]);
                     if ((rel % FG) == FG - 1 || kc == kc_hi - 1) {
                         umma_commit(&tmem_full[acc]);
                         ++g;
@@ -321,10 +377,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
         else
             inv = 1.0f / (pow2_scale_for(__uint_as_float(p.sc->max_gy)) * pow2_scale_for(__uint_as_float(p.sc->max_w)));
 
-        for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        for (int64_t item = cid; item < p.nitems; item += ncl) {
             int nt, ks, kc_lo, kc_hi;
             int64_t mt;
             item_coords(p, item, mt, nt, ks, kc_lo, kc_hi);
+            mt = mt * CL + (int64_t)crank;
+            const bool tile_valid = mt <= p.mt_last;  // the second tile of the last pair may not exist
             const int ngroups = (kc_hi - kc_lo + FG - 1) / FG;
             float racc[TC_MAXHALF];
 #pragma unroll
@@ -342,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                 for (int ii = 0; ii < PF; ++ii) {
                     pf_sg[ii] = HOL_SEG_INVALID;
                     pf_xl[ii] = 0.0f;
-                    if (b < p.Bp && i0 + ii < p.I) {
+                    if (tile_valid && b < p.Bp && i0 + ii < p.I) {
                         pf_sg[ii] = p.seg_t[(int64_t)(i0 + ii) * p.Bp + b];
                         pf_xl[ii] = p.xl_t[(int64_t)(i0 + ii) * p.Bp + b];
                     }
@@ -381,7 +439,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             const int64_t row = mt * TC_BM + rl;  // row inside this launch
             const int colbase = nt * BN + h * HALF;
 
-            if (EPI == EPI_Y) {
+            if (!tile_valid) {
+                // nothing to store
+            } else if (EPI == EPI_Y) {
                 if (row < p.rows_valid) {
                     float* yrow = p.out + (p.row0 + row) * (int64_t)p.ld + colbase;
                     const bool vec = (p.ld & 3) == 0 && (HALF & 3) == 0;
@@ -468,6 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");

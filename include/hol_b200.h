@@ -75,6 +75,7 @@ const char* hol_error_string(int code);
 #define HOL_PLAN_DISABLE_TENSOR_CORES 1u /* gather kernels everywhere                                */
 #define HOL_PLAN_DISABLE_DENSE_DW 2u     /* bucketed dW instead of the dense-register dW              */
 #define HOL_PLAN_NO_SHARED_PHI 4u        /* chunked Phi / Phi^T tiles instead of the shared Phi tiles */
+#define HOL_PLAN_NO_CLUSTER 16u          /* single-CTA GEMM tiles instead of two-CTA multicast clusters */
 #define HOL_PLAN_FLUSH_SHIFT 8           /* bits 8..11: k-chunks per TMEM drain (0 = default 4)       */
 uint32_t hol_set_plan_overrides(uint32_t mask);
 
