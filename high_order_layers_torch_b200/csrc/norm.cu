@@ -45,22 +45,31 @@ __global__ void __launch_bounds__(256) pw_row_norm_fwd_kernel(const float* __res
         if (lane == 0) stats[row] = make_float4(den, nrm, 0.0f, 0.0f);
         return;
     }
+    // torch.max / torch.min propagate NaN: a NaN anywhere in the row makes the whole row NaN (and takes the
+    // arg-max), so NaN is treated as larger than everything; the stored indices always lie inside the row
+    // (an all-NaN row -- the normal state after a divergence -- must not send the backward out of bounds).
     float vmax = -INFINITY, vmin = -INFINITY;  // vmin tracks -x
-    int imax = 0x7fffffff, imin = 0x7fffffff;
+    int imax = W, imin = W;
+    bool nan_seen = false;
     for (int c = lane; c < W; c += 32) {
         const float v = xr[c];
         const float a = (KIND == HOL_NORM_MAX_ABS) ? fabsf(v) : v;
-        if (a > vmax || c < imax && a == vmax) vmax = a, imax = c;
-        if (KIND == HOL_NORM_MAX_CENTER && (-v > vmin || c < imin && -v == vmin)) vmin = -v, imin = c;
+        if (v != v) nan_seen = true;
+        if (a > vmax || c < imax && a == vmax || imax == W) vmax = a, imax = c;
+        if (KIND == HOL_NORM_MAX_CENTER && (-v > vmin || c < imin && -v == vmin || imin == W)) vmin = -v, imin = c;
     }
+    nan_seen = __any_sync(0xffffffffu, nan_seen);
     warp_argmax(vmax, imax);
+    if (imax >= W) imax = 0;
+    if (nan_seen) vmax = NAN;
     if (KIND == HOL_NORM_MAX_ABS) {
         const float den = __fadd_rn(vmax, eps);
         for (int c = lane; c < W; c += 32) yr[c] = __fdiv_rn(xr[c], den);
         if (lane == 0) stats[row] = make_float4(den, 0.0f, __int_as_float(imax), 0.0f);
     } else {
         warp_argmax(vmin, imin);
-        const float mn = -vmin;
+        if (imin >= W) imin = 0;
+        const float mn = nan_seen ? NAN : -vmin;
         const float mid = __fmul_rn(0.5f, __fadd_rn(vmax, mn));
         const float den = __fadd_rn(__fsub_rn(vmax, mid), eps);
         for (int c = lane; c < W; c += 32) yr[c] = __fdiv_rn(__fsub_rn(xr[c], mid), den);
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(256) pw_row_norm_bwd_kernel(const float* __res
     sgx = warp_sum(sgx);
     const float inv = 1.0f / den;
     if (KIND == HOL_NORM_MAX_ABS) {
-        const int im = __float_as_int(st.z);
+        const int im = min(max(__float_as_int(st.z), 0), W - 1);
         const float xm = xr[im];
         const float sgn = xm > 0.0f ? 1.0f : (xm < 0.0f ? -1.0f : 0.0f);
         const float corr = -sgx * inv * inv * sgn;
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(256) pw_row_norm_bwd_kernel(const float* __res
     } else if (KIND == HOL_NORM_MAX_CENTER) {
         // y = (x - mid) / d, d = mag + eps:  dL/dmid = -sum(g)/d,  dL/dd = -sum(g (x - mid))/d^2;
         // d mid / d x_max = d mid / d x_min = 1/2,  d mag / d x_max = 1/2,  d mag / d x_min = -1/2
-        const int ia = __float_as_int(st.z), ib = __float_as_int(st.w);
+        const int ia = min(max(__float_as_int(st.z), 0), W - 1), ib = min(max(__float_as_int(st.w), 0), W - 1);
         const float dmid = -sg * inv, dd = -sgx * inv * inv;
         const float ca = 0.5f * (dmid + dd), cb = 0.5f * (dmid - dd);
         for (int c = lane; c < W; c += 32) dr[c] = gr[c] * inv + (c == ia ? ca : 0.0f) + (c == ib ? cb : 0.0f);

@@ -85,8 +85,12 @@ __device__ __forceinline__ void prep_stats(float amax, unsigned nout, unsigned* 
         nout += __shfl_xor_sync(0xffffffffu, nout, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (amax > 0.0f) atomicMax(stats + 0, __float_as_uint(amax));  // TcScalars::max_xl
-        if (nout) atomicAdd(stats + 3, nout);                           // TcScalars::n_outliers
+        // Every warp of the grid would otherwise hit ONE address (half a million atomics at config 2:
+        // 0.5 ms of L2 serialisation).  The running maximum settles after the first few CTAs, so look
+        // before touching it: an atomic is only issued by a warp that actually raises the value.
+        const unsigned bits = __float_as_uint(amax);
+        if (amax > 0.0f && bits > *reinterpret_cast<volatile unsigned*>(stats + 0)) atomicMax(stats + 0, bits);  // TcScalars::max_xl
+        if (nout) atomicAdd(stats + 3, nout);                                                                      // TcScalars::n_outliers
     }
 }
 __device__ __forceinline__ void prep_track(float xl, uint32_t sg, float& amax, unsigned& nout) {

@@ -2,8 +2,8 @@
 weights whose gradient is non-zero -- for the piecewise layers that is the n weights of the one
 segment each sample activated per link; every other entry of dW is exactly zero.
 
-CUDA fp32 parameters take one fused kernel per parameter (csrc/optim.cu) through
-the ``hol::sparse_lion_step`` op; other tensors use the equivalent torch expression.  As in the
+Every parameter takes one fused kernel (csrc/optim.cu) through the
+``hol::sparse_lion_step`` op; like the layers there is no CPU / torch fallback.  As in the
 reference, ``weight_decay`` has no effect: its decay line multiplies the copy that advanced
 indexing returns (sparse_lion.py:19), so no weight is ever decayed.
 """
@@ -31,15 +31,6 @@ def sparse_lion_step(p: Tensor, grad: Tensor, exp_avg: Tensor, lr: float, wd: fl
                                                 _stream(p)), "hol_sparse_lion_step_f32")
 
 
-def _update_torch(p: Tensor, grad: Tensor, exp_avg: Tensor, lr: float, beta1: float, beta2: float) -> None:
-    touched = grad != 0.0
-    g = grad[touched]
-    m = exp_avg[touched]
-    step = (m * beta1).add(g, alpha=1 - beta1).sign_()
-    p[touched] = p[touched].add_(step, alpha=-lr)
-    exp_avg[touched] = m.mul(beta2).add_(g, alpha=1 - beta2)
-
-
 class SparseLion(Optimizer):
     def __init__(self, params, lr: float = 1e-4, betas: Tuple[float, float] = (0.9, 0.99), weight_decay: float = 0.0,
                  use_triton: bool = False):
@@ -63,8 +54,8 @@ class SparseLion(Optimizer):
                 if len(state) == 0:
                     state["exp_avg"] = torch.zeros_like(p)
                 exp_avg = state["exp_avg"]
-                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous():
-                    sparse_lion_step(p, p.grad, exp_avg, lr, wd, beta1, beta2)
-                else:
-                    _update_torch(p, p.grad, exp_avg, lr, beta1, beta2)
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("SparseLion: parameters must be contiguous float32 CUDA tensors (this build runs "
+                                       "on CUDA (sm_100a) only and has no CPU fallback)")
+                sparse_lion_step(p, p.grad, exp_avg, lr, wd, beta1, beta2)
         return loss

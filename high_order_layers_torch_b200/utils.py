@@ -1,8 +1,9 @@
 """Small elementwise helpers kept for API compatibility (reference utils.py:8-79).
 
 The per-sample normalisations HighOrderMLP puts between layers run as one fused CUDA kernel each
-way for CUDA fp32 [B, W] inputs (csrc/norm.cu); inside the layers the periodic fold
-is fused into the prep kernel (csrc/prep.cu).
+way (csrc/norm.cu) -- CUDA fp32 only, no torch fallback; inside the layers the periodic
+fold is fused into the prep kernel (csrc/prep.cu).  ``make_periodic`` is the host-side helper the
+inspection methods (``which_segment`` on CPU tensors) use.
 """
 from __future__ import annotations
 
@@ -10,8 +11,17 @@ import torch
 from torch import Tensor
 
 
-def _fused(x: Tensor, dim: int) -> bool:
-    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and dim in (1, -1)
+def _rows(x: Tensor, dim: int, what: str) -> Tensor:
+    """The fused kernels take CUDA fp32 [B, W] tensors normalised over dim 1; like the layers there is no
+    CPU / torch fallback (north_star): anything else raises."""
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: input is on {x.device}; this build runs on CUDA (sm_100a) only and has no CPU fallback")
+    if x.dtype != torch.float32:
+        raise TypeError(f"{what}: float32 input required, got {x.dtype}")
+    if x.dim() != 2 or dim not in (1, -1):
+        raise ValueError(f"{what}: a [batch, width] tensor normalised over dim 1 is required, got {tuple(x.shape)}, dim={dim} "
+                         "(use the *_nd / *_last variants for other ranks)")
+    return x
 
 
 def max_abs(x: Tensor, dim: int = 1) -> Tensor:
@@ -19,31 +29,22 @@ def max_abs(x: Tensor, dim: int = 1) -> Tensor:
 
 
 def max_abs_normalization(x: Tensor, eps: float = 1e-6, dim: int = 1) -> Tensor:
-    """x / (max|x| + eps) per sample -- reference utils.py:12-13.  CUDA fp32 [B, W] inputs take the
-    fused kernel pair (csrc/norm.cu); anything else the reference's torch expression."""
-    if _fused(x, dim):
-        from .ops import normalize_rows
-        return normalize_rows(x, "max_abs", eps)
-    return x / (max_abs(x, dim=dim) + eps)
+    """x / (max|x| + eps) per sample -- reference utils.py:12-13, as one fused kernel each way (csrc/norm.cu)."""
+    from .ops import normalize_rows
+    return normalize_rows(_rows(x, dim, "max_abs_normalization"), "max_abs", eps)
 
 
 def max_abs_normalization_last(x: Tensor, eps: float = 1e-6) -> Tensor:
-    """reference utils.py:16-17"""
-    if x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2:
-        from .ops import normalize_rows
-        return normalize_rows(x.reshape(-1, x.shape[-1]), "max_abs", eps).reshape(x.shape)
-    return x / (max_abs(x, dim=x.dim() - 1) + eps)
+    """reference utils.py:16-17: normalised over the last dimension"""
+    from .ops import normalize_rows
+    flat = x.reshape(-1, x.shape[-1])
+    return normalize_rows(_rows(flat, 1, "max_abs_normalization_last"), "max_abs", eps).reshape(x.shape)
 
 
 def max_center_normalization(x: Tensor, eps: float = 1e-6, dim: int = 1) -> Tensor:
     """(x - midrange) / (max - midrange + eps) per sample -- reference utils.py:20-28."""
-    if _fused(x, dim):
-        from .ops import normalize_rows
-        return normalize_rows(x, "max_center", eps)
-    max_x = torch.max(x, dim=dim, keepdim=True)[0]
-    min_x = torch.min(x, dim=dim, keepdim=True)[0]
-    midrange = 0.5 * (max_x + min_x)
-    return (x - midrange) / (max_x - midrange + eps)
+    from .ops import normalize_rows
+    return normalize_rows(_rows(x, dim, "max_center_normalization"), "max_center", eps)
 
 
 def max_center_normalization_nd(x: Tensor, eps: float = 1e-6) -> Tensor:
@@ -53,10 +54,8 @@ def max_center_normalization_nd(x: Tensor, eps: float = 1e-6) -> Tensor:
 
 def l2_normalization(x: Tensor, eps: float = 1e-6) -> Tensor:
     """x / (||x||_2 + eps) per sample -- reference utils.py:57-58."""
-    if _fused(x, 1):
-        from .ops import normalize_rows
-        return normalize_rows(x, "l2", eps)
-    return x / (x.norm(2, 1, keepdim=True) + eps)
+    from .ops import normalize_rows
+    return normalize_rows(_rows(x, 1, "l2_normalization"), "l2", eps)
 
 
 def max_abs_normalization_nd(x: Tensor, eps: float = 1e-6) -> Tensor:

@@ -913,3 +913,23 @@ def test_round2_variants_golden():
             assert rel_err(xt.grad.cpu().numpy(), g[name + "_dx"]) < TOL, name
         else:
             assert not xt.grad.any()
+
+
+def test_row_norms_nan_rows_match_torch():
+    """A NaN anywhere in a row makes the whole normalised row NaN (torch.max propagates NaN) and an
+    all-NaN row -- the normal state after a divergence -- must not send the backward out of bounds."""
+    from high_order_layers_torch_b200 import utils as U
+    x = torch.rand(6, 37, device=DEV) * 2 - 1
+    x[1, 5] = float("nan")
+    x[3, :] = float("nan")
+    for fn, expr in ((U.max_abs_normalization, lambda v: v / (v.abs().max(1, keepdim=True)[0] + 1e-6)),
+                     (U.max_center_normalization, None)):
+        xt = x.clone().requires_grad_(True)
+        y = fn(xt)
+        y.sum().backward()
+        torch.cuda.synchronize()
+        assert torch.isnan(y[1]).all() and torch.isnan(y[3]).all()
+        ok = torch.tensor([0, 2, 4, 5], device=DEV)
+        assert torch.isfinite(y[ok]).all() and torch.isfinite(xt.grad[ok]).all()
+        if expr is not None:
+            assert torch.equal(y[ok], expr(x[ok]))

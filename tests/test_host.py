@@ -246,10 +246,21 @@ def _run_sparse_lion(device):
     assert np.array_equal(par.detach().cpu().numpy()[untouched], g["p0"][untouched])   # never decayed, never moved
 
 
-def test_sparse_lion_matches_reference_fixture_cpu():
-    """four steps of SparseLion against the reference's (sparse_lion.py:13-92),
-    including its no-op weight decay."""
-    _run_sparse_lion("cpu")
+def test_no_torch_fallbacks_in_optimizer_and_normalisations():
+    """north_star: no CPU fallback anywhere -- SparseLion and the normalisation helpers refuse CPU tensors
+    like the layers do (the fixture comparison of SparseLion runs on the GPU: test_sparse_lion_fused_kernel)."""
+    from high_order_layers_torch_b200 import utils as U
+    from high_order_layers_torch_b200.sparse_optimizers import SparseLion
+    par = torch.nn.Parameter(torch.ones(3, 4))
+    par.grad = torch.ones(3, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SparseLion([par], lr=1e-2).step()
+    for fn in (U.max_abs_normalization, U.max_center_normalization, U.l2_normalization, U.max_abs_normalization_nd,
+               U.max_abs_normalization_last, U.max_center_normalization_nd):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn(torch.ones(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        hol.MaxAbsNormalization()(torch.ones(2, 3))
 
 
 def test_conv1d_unfold_mapping_and_init_match_reference():
