@@ -193,7 +193,7 @@ def build_workload(torch, cfg, device, rank, args):
             layer.w.uniform_(-1, 1)
         x = make_inputs(torch, (B, I), gen, device).requires_grad_(True)
         gy = torch.randn(B, O, generator=gen, device=device)
-        flat = FlatGradients(layer.parameters())
+        flat = FlatGradients(layer.parameters(), collective=args.collective)
 
         def step():
             flat.begin()
@@ -234,7 +234,7 @@ def build_workload(torch, cfg, device, rank, args):
         target = (torch.randint(0, wd[-1], (B,), generator=gen, device=device) if classify
                   else torch.randn(B, wd[-1], generator=gen, device=device))
         lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
-        flat = FlatGradients(net.parameters())
+        flat = FlatGradients(net.parameters(), collective=args.collective)
 
         def step():
             flat.begin()
@@ -291,7 +291,7 @@ def build_workload(torch, cfg, device, rank, args):
             net.conv2.conv.weight.uniform_(-0.2, 0.2)
         x = make_inputs(torch, (B, 3, 32, 32), gen, device)
         target = torch.randint(0, 100, (B,), generator=gen, device=device)
-        flat = FlatGradients(net.parameters())
+        flat = FlatGradients(net.parameters(), collective=args.collective)
 
         def step():
             flat.begin()
@@ -469,8 +469,9 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         "unit": "samples/s", "cuda_graph": graphed, "gpu_launches_per_step": wl["launches"],
         "l2": "inputs larger than L2 (no flush needed)" if wl["bytes"] > 3 * 126e6
               else "working set fits L2; no flush between steps",
-        "clocks": clocks,
+        "clocks": clocks, "collective": wl["flat"].collective if world > 1 else "none",
     }
+    wl["flat"].check()
     if with_e2e:
         res["e2e"] = {"value": wl["samples"] * world / (e2e_ms / e2e_steps / 1e3), "unit": "samples/s",
                       "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
@@ -566,9 +567,10 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": head["workload"], "per_gpu_batch": head["per_gpu_batch"],
                        "global_batch": head["global_batch"], "parallelism": f"dp{world}", "l2": head["l2"],
-                       "allreduce": "per-layer fp32 NCCL all-reduce (avg) of dW on a side stream, issued right after the "
-                                    "layer's dW kernels and overlapped with the rest of the backward"
-                       if world > 1 else "none", "cuda_graph": head["cuda_graph"]},
+                       "allreduce": ("per-layer fp32 mean all-reduce of dW on a side stream, issued right after the layer's "
+                                     "dW kernels and overlapped with the rest of the backward; " +
+                                     ("own peer-memory kernels over NVLink (csrc/p2p.cu)" if head["collective"] == "p2p"
+                                      else "NCCL")) if world > 1 else "none", "cuda_graph": head["cuda_graph"]},
             "e2e": head.get("e2e"),
             "gpu_launches": head["gpu_launches_per_step"] * steps,
             "gpu_launches_per_step": head["gpu_launches_per_step"],
@@ -1020,6 +1022,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's torch-CUDA leg")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="dW all-reduce: our peer-memory kernels over NVLink (p2p; auto = p2p when available) or NCCL")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the step in a CUDA graph (auto: MLP / conv workloads only)")
     args = ap.parse_args()

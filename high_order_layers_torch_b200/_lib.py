@@ -52,6 +52,8 @@ SIGNATURES = {
                                                 _i32, _f32, _vp, _sz, _u32, _vp]),
     "hol_fold_rows_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hol_unfold_rows_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hol_p2p_flags_bytes": (_sz, []),
+    "hol_p2p_allreduce_f32": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, _f32, _vp]),
     "hol_pw_profile_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
                                           _f32, _vp, _sz, _vp, _vp]),
     "hol_row_norm_forward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

@@ -12,9 +12,16 @@ gradient, started as soon as that layer's dW kernel has been queued.
 * Every other parameter (conv weights reached through a permuted view, ``nn.Linear``) accumulates
   through autograd as usual and is reduced by ``finish()`` in as few collectives as its slices allow.
 
-A step is ``begin()`` -> forward -> backward -> ``finish()``.  Works with any torch.distributed
-backend (``gloo`` in the CPU tests, ``nccl`` on the GPUs); with a single process the collectives are
-skipped and only the direct dW write remains.  The whole step, collectives included, can be
+The exchange itself runs on our own kernels over NVLink peer memory where it can (csrc/p2p.cu): on
+CUDA with the ``nccl`` backend the flat buffer is allocated in symmetric memory (torch's
+``_symmetric_memory`` hands out the mapping: plumbing), every rank reads its peers' gradients with
+plain loads over NVLink / NVSwitch, adds them in rank order and stores the result into all
+buffers -- deterministic, graph-capturable, and latency-wise ~3x cheaper than NCCL's all-reduce at
+the 5 MB size that sits exposed at the end of an MLP's backward.  ``collective="nccl"`` (or a backend
+without peer memory: ``gloo`` in the CPU tests) uses ``dist.all_reduce`` instead.
+
+A step is ``begin()`` -> forward -> backward -> ``finish()``.  With a single process the collectives
+are skipped and only the direct dW write remains.  The whole step, collectives included, can be
 captured in a CUDA graph: the side stream forks from and joins the capturing stream through events.
 """
 from __future__ import annotations
@@ -34,7 +41,7 @@ def shard_range(total: int, rank: int, world: int):
 
 class FlatGradients:
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 average: bool = True, direct: bool = True, overlap: bool = True):
+                 average: bool = True, direct: bool = True, overlap: bool = True, collective: str = "auto"):
         seen = set()
         self.params: List[torch.nn.Parameter] = []
         for p in params:  # HighOrderMLP registers its first/last layer twice: deduplicate
@@ -48,7 +55,26 @@ class FlatGradients:
         self.average = average
         self.direct = direct
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        self.collective = "nccl"
+        self._p2p = None
+        self.flat = None
+        # "auto": peer memory up to 1 GiB of gradients (every rank takes the same decision from the same sizes);
+        # beyond that NCCL's bandwidth-optimal algorithms are the better tool and the mapping is left alone
+        if (collective == "p2p" or (collective == "auto" and self.numel * 4 <= (1 << 30))) and dev.type == "cuda" \
+                and dt == torch.float32 and self._world() > 1 and dist.get_backend(group) == "nccl":
+            try:
+                self._setup_p2p(dev)
+                self.collective = "p2p"
+            except Exception as e:  # no peer mapping on this system: the library collective still works
+                if collective == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"FlatGradients: symmetric memory unavailable ({type(e).__name__}: {str(e)[:120]}); "
+                              "using dist.all_reduce")
+                self._p2p = None
+                self.flat = None
+        if self.flat is None:
+            self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
         self._range: Dict[int, Tuple[int, int]] = {}
         off = 0
         for p in self.params:
@@ -62,6 +88,31 @@ class FlatGradients:
         self._direct_ids: set = set()  # parameters whose layers wrote into the sink in the last step
 
     # -- plumbing -------------------------------------------------------------------------
+    def _setup_p2p(self, dev) -> None:
+        """Flat buffer + flag block in symmetric memory, peer pointer tables for csrc/p2p.cu."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        lib = _lib.load()
+        group = self.group if self.group is not None else dist.group.WORLD
+        flat = symm_mem.empty(self.numel, dtype=torch.float32, device=dev)
+        flat.zero_()
+        words = (lib.hol_p2p_flags_bytes() + 3) // 4
+        flags = symm_mem.empty(words, dtype=torch.int32, device=dev)
+        flags.zero_()
+        torch.cuda.synchronize(dev)
+        h_buf = symm_mem.rendezvous(flat, group)
+        h_flg = symm_mem.rendezvous(flags, group)
+        dist.barrier(group)  # every rank's flag block is zeroed before anyone signals into it
+        self.flat = flat
+        self._p2p = dict(lib=lib, flags=flags, handles=(h_buf, h_flg), bufs_dev=int(h_buf.buffer_ptrs_dev),
+                         flags_dev=int(h_flg.buffer_ptrs_dev), rank=int(h_buf.rank), world=int(h_buf.world_size))
+
+    def check(self) -> None:
+        """Raise if a peer-memory exchange gave up waiting for a rank (csrc/p2p.cu); synchronises."""
+        if self._p2p is not None and int(self._p2p["flags"][33].item()) != 0:
+            raise RuntimeError("FlatGradients: a rank did not arrive at a peer-memory all-reduce (timeout)")
+
     def _world(self) -> int:
         if not dist.is_available() or not dist.is_initialized():
             return 1
@@ -95,6 +146,17 @@ class FlatGradients:
     def _reduce(self, lo: int, hi: int) -> None:
         world = self._world()
         if world == 1:
+            return
+        if self._p2p is not None:
+            import ctypes
+
+            from . import _lib
+            q = self._p2p
+            with torch.cuda.device(self.flat.device):
+                _lib.check(q["lib"].hol_p2p_allreduce_f32(
+                    ctypes.c_void_p(q["bufs_dev"]), ctypes.c_void_p(q["flags_dev"]), q["rank"], q["world"], lo, hi - lo,
+                    (1.0 / world) if self.average else 1.0,
+                    ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)), "hol_p2p_allreduce_f32")
             return
         buf = self.flat[lo:hi]
         backend = dist.get_backend(self.group)

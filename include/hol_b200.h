@@ -203,6 +203,19 @@ int hol_row_norm_backward_f32(int32_t kind, const float* gy, const float* x, con
 int hol_sparse_lion_step_f32(float* p, const float* grad, float* exp_avg, int64_t count, float lr,
                              float wd, float beta1, float beta2, void* stream);
 
+/* ---- data-parallel exchange step over NVLink peer memory ---------------------------------
+ * Sum (scale = 1) or mean (scale = 1/world) all-reduce of `count` floats at `offset` of the flat gradient
+ * buffer, by our own kernels: every rank's buffer lives in symmetric memory (one allocation per rank,
+ * mapped into every process of the node).  bufs_dev / flags_dev are DEVICE arrays of `world` device
+ * pointers -- rank p's buffer and rank p's zero-initialised flag block of hol_p2p_flags_bytes() bytes --
+ * in the same order on every rank.  Every rank of the group must make the same calls in the same order.
+ * Deterministic (rank-order sum), graph-capturable (device-side epochs), never blocks the host; a peer
+ * that never arrives makes the flag waits give up after ~4 s and sets the error word
+ * (uint32 index 33: 16 + 16 flag words, epoch, error) of the caller's flag block. */
+size_t hol_p2p_flags_bytes(void);
+int hol_p2p_allreduce_f32(void* const* bufs_dev, void* const* flags_dev, int32_t rank, int32_t world, int64_t offset,
+                          int64_t count, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
