@@ -219,9 +219,21 @@ class FlatGradients:
         """End of the backward: reduce what autograd accumulated and join the side stream."""
         self._alias()
         rest = [i for i in self._range if i not in self._done]
-        if self._world() > 1:
-            for lo, hi in self._ranges(rest):
-                self._reduce(lo, hi)          # on the current stream: nothing is left to overlap with
+        if self._world() > 1 and rest:
+            # Nothing is left to overlap with, but the exchanges of a step stay on ONE stream: the peer-memory
+            # kernels share a flag block and a device-side epoch, so two of them must never run concurrently
+            # (every rank has to walk the same sequence of barriers).
+            if self._side is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._side_used = True
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(ev)
+                    for lo, hi in self._ranges(rest):
+                        self._reduce(lo, hi)
+            else:
+                for lo, hi in self._ranges(rest):
+                    self._reduce(lo, hi)
         if self._side is not None and self._side_used:
             # join the side stream (it forked from this one through an event, so the join is also valid
             # inside a CUDA graph capture; an unused side stream must NOT be touched during a capture)

@@ -46,6 +46,8 @@ flat.check()
 # graph capture + replay, timing against NCCL at the first-layer size (5.2 MB)
 n = 128 * 784 * 13
 buf_nccl = torch.randn(n, device=dev)
+torch.cuda.synchronize()
+dist.barrier()
 def p2p_step():
     flat._reduce(0, n)
 g = torch.cuda.CUDAGraph()
