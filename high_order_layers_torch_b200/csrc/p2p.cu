@@ -10,8 +10,9 @@
 //                all N buffers.  Only rank r ever touches part r of any buffer, so nothing races.
 //   barrier-out  every rank's stores have landed; the slice is complete everywhere.
 // Traffic per rank: (N-1)/N of the slice in, the same out -- 9 MB for the 5.2 MB first-layer gradient of
-// the MLP at N = 8, ~13 us at 700 GB/s per direction, where NCCL's latency-bound all-reduce of that size
-// took ~70 us and sat exposed at the end of the backward (the first layer's dW is computed last).
+// the MLP at N = 8, ~13 us at 700 GB/s per direction; at that size the exchange is latency-bound (two
+// flag round trips over NVLink + three launches): measured 31 / 42 us at 2 / 4 GPUs against 38 / 42 us for
+// NCCL's all-reduce, and inside the config-3 step 0.796 ms at 8 GPUs against 0.818 ms with NCCL.
 // Three tiny launches on the caller's stream (stream order is the grid-wide sync between the phases);
 // the flags carry a device-side epoch, so the sequence can be captured in a CUDA graph and replayed.
 // A rank that never shows up must not hang the others forever: the flag waits give up after ~4 s and
@@ -73,15 +74,22 @@ __global__ void __launch_bounds__(256) pw_p2p_reduce_kernel(float* const* bufs, 
     const int64_t v_lo = lo + head < hi ? lo + head : hi;
     const int64_t nvec = (hi - v_lo) / 4;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    // All `world` peer loads of an element are issued before the first add (a load over NVLink takes ~2 us;
+    // a load-add chain over the peers would serialise them).  The sum itself still runs in rank order.
     for (int64_t k = tid; k < nvec; k += nthr) {
         const int64_t e = v_lo + 4 * k;
-        float4 s = __ldcg(reinterpret_cast<const float4*>(bufs[0] + e));
-        for (int p = 1; p < world; ++p) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(bufs[p] + e));
-            s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
-        }
+        float4 v[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if (p < world) v[p] = __ldcg(reinterpret_cast<const float4*>(bufs[p] + e));
+        float4 s = v[0];
+#pragma unroll
+        for (int p = 1; p < 16; ++p)
+            if (p < world) s.x += v[p].x, s.y += v[p].y, s.z += v[p].z, s.w += v[p].w;
         s.x *= scale, s.y *= scale, s.z *= scale, s.w *= scale;
-        for (int p = 0; p < world; ++p) *reinterpret_cast<float4*>(bufs[p] + e) = s;
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if (p < world) *reinterpret_cast<float4*>(bufs[p] + e) = s;
     }
     // ragged ends
     const int64_t tail0 = v_lo + 4 * nvec;
