@@ -112,6 +112,7 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     int parts = bucketed ? s.ksplit : s.dwd.ksplit;
     if (s.tc.dw) parts = s.tc.dw_ksplit;  // tensor-core dW: batch split over several CTAs per tile
     ws.dw_part = parts > 1 ? (float*)take((size_t)parts * s.O * s.I * s.nb * sizeof(float)) : nullptr;
+    ws.y_part = (s.tc.fwd && s.tc.fwd_ksplit > 1) ? (float*)take((size_t)s.tc.fwd_ksplit * s.B * s.O * sizeof(float)) : nullptr;
     ws.dx_rows = conv ? (float*)take((size_t)s.I * s.Bp * sizeof(float)) : nullptr;
     ws.xl_img = conv ? (float*)take((size_t)conv_pixels * sizeof(float)) : nullptr;
     ws.seg_img = conv ? (uint16_t*)take((size_t)conv_pixels * sizeof(uint16_t)) : nullptr;
@@ -415,7 +416,7 @@ int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
     return (s.tc.fwd ? 1 : 0) | (s.tc.dx ? 2 : 0) | (s.tc.dw ? 4 : 0) | (s.dwd.enabled ? 8 : 0) |
            ((s.tc.enabled && s.tc.share_phi) ? 16 : 0) | (s.rot ? 32 : 0) |
-           ((s.tc.dw ? (s.tc.dw_ksplit & 255) : 0) << 8);
+           ((s.tc.dw ? (s.tc.dw_ksplit & 255) : 0) << 8) | ((s.tc.fwd ? (s.tc.fwd_ksplit & 255) : 0) << 16);
 }
 
 int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous,

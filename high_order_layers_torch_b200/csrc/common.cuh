@@ -42,6 +42,7 @@ struct TcPlan {
     int BNx, nNTx, noc;       // dX: N tile over the dense columns (multiple of 2*Kin), its count, 64-wide output chunks
     int nMTw;                 // dW: 128-row M tiles over the dense columns
     int dw_ksplit;            // dW: the batch (K) is split over this many CTAs per tile (partials -> dw_part)
+    int fwd_ksplit;           // forward: the dense columns (K) are split likewise when the batch gives few tiles (partials -> y_part)
     int flush_chunks;         // k-chunks accumulated in TMEM between drains
     int64_t rows_per_launch;  // batch rows expanded + multiplied per launch (bounds the Phi tiles)
     size_t a_bytes, b_bytes;  // Phi tile / W tile storage
@@ -90,6 +91,7 @@ struct PwWorkspace {
     uint32_t* order;  // [I][Bp]  sample ids sorted by segment (stable)
     uint32_t* offs;   // [I][nchunks][Seff+1] bucket offsets into order
     float* dw_part;   // [ksplit][O][I][nb] partial weight gradients (ksplit > 1 only)
+    float* y_part;    // [fwd_ksplit][B][O] partial outputs of a forward split over K (tensor-core path)
     float* dx_rows;   // conv only: [rows][I] unfolded input gradient
     float* xl_img;    // conv only: [Bimg][C][H][W] local coordinate per pixel (before the unfold)
     uint16_t* seg_img;  // conv only: segment + flags per pixel

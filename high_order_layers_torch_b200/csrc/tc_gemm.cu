@@ -121,6 +121,17 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
         if (ks > 16) ks = 16;
         if (ks >= 2) t.dw_ksplit = (int)ks;
     }
+    // forward: no reduction dimension to spare SMs with either -- when the batch gives fewer tiles than ~half
+    // the SMs (config 3: 64 tiles of 196 k-chunks) the k-chunks are split over 2-4 work items per tile; every
+    // CTA is bound by its own shared-memory / L2 port, so the extra CTAs add bandwidth, not just issue slots
+    t.fwd_ksplit = 1;
+    if (t.fwd && rows >= s.Bp) {
+        const int64_t tiles = mtiles_all * t.nNT;
+        int64_t ks = sm_count() / tiles;
+        if (ks > t.nkc / 16) ks = t.nkc / 16;  // at least 16 k-chunks per split
+        if (ks > 4) ks = 4;
+        if (ks >= 2) t.fwd_ksplit = (int)ks;
+    }
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
     size_t a = t.share_phi ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
@@ -250,7 +261,7 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, int ksplit,
 // max|gy| pass of a backward with any tensor-core part (prep not included)
 int tc_launch_count(const PwShape& s, const TcPlan& t, int kind, bool prepared) {
     const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
-    if (kind == 0) return 2 + nl * 2 + 1;                          // wstats, pack_w, (expand, gemm) per batch chunk, fix_y
+    if (kind == 0) return 2 + nl * 2 + (t.fwd_ksplit > 1 ? 1 : 0) + 1;  // wstats, pack_w, (expand, gemm), [reduce], fix_y
     if (kind == 1) return (prepared ? 0 : 1) + 1 + nl * 2 + 1;     // [wstats], pack_wt, (pack_gy, gemm), fix_dx
     if (kind == 3) return 1;
     if (t.share_phi) return (prepared && t.fwd ? 0 : 1) + 2 + (t.dw_ksplit > 1 ? 1 : 0) + 1;  // [expand], pack_gyt, gemm, [reduce], fix_dw
@@ -342,7 +353,9 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         if (rc != HOL_OK) return rc;
         TcGemmParams p;
         fill_common(p, s, ws, t);
-        p.out = y;
+        const bool split = t.fwd_ksplit > 1;  // only planned when one launch covers the batch
+        p.out = split ? ws.y_part : y;
+        p.part_stride = s.B * (int64_t)s.O;
         p.row0 = row0;
         p.rows_valid = s.B - row0 < rows ? s.B - row0 : rows;
         p.BN = t.BN;
@@ -351,8 +364,13 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         p.nkc = t.nkc;
         p.a_nkc = ekc;
         p.a_tiles = phi;
-        rc = launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, 1, (TcProf*)ws.prof, st);
+        rc = launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, t.fwd_ksplit, (TcProf*)ws.prof, st);
         if (rc != HOL_OK) return rc;
+        if (split) {
+            const int kcs = (t.nkc + t.fwd_ksplit - 1) / t.fwd_ksplit;
+            rc = launch_dw_reduce(ws.y_part, y, s.B * (int64_t)s.O, (t.nkc + kcs - 1) / kcs, st);
+            if (rc != HOL_OK) return rc;
+        }
     }
     FixParams f;
     fill_fix(f, s, ws, w, nullptr, y, 0);

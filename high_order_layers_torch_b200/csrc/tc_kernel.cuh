@@ -104,7 +104,7 @@ struct TcGemmParams {
     int64_t ntile_m;               // m-tiles (CL = 1) or pairs of m-tiles (CL = 2) the rasterisation walks
     int64_t mt_last;               // last valid m-tile (a pair may end on a tile that does not exist: loads are
                                    // clamped to this tile and its epilogue stores nothing)
-    int64_t part_stride;           // EPI_DW, ksplit > 1: floats between the partial results of two k-splits
+    int64_t part_stride;           // ksplit > 1 (EPI_DW, EPI_Y): floats between the partial results of two k-splits
     int ntile_n, group_m;          // rasterisation: groups of group_m m-tiles, m fastest inside a group
     int ksplit, kc_per_split;      // the k-chunks of a tile are split over ksplit work items
     int BN, n_valid, ld, nkc, nst, n_basis, flush_chunks;
@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                 // nothing to store
             } else if (EPI == EPI_Y) {
                 if (row < p.rows_valid) {
-                    float* yrow = p.out + (p.row0 + row) * (int64_t)p.ld + colbase;
+                    // (a forward split over K writes this split's partial result: summed by pw_dw_reduce_kernel)
+                    float* yrow = p.out + (int64_t)ks * p.part_stride + (p.row0 + row) * (int64_t)p.ld + colbase;
                     const bool vec = (p.ld & 3) == 0 && (HALF & 3) == 0;
 #pragma unroll
                     for (int e = 0; e < TC_MAXHALF; e += 4) {

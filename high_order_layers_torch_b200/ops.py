@@ -582,7 +582,8 @@ def plan_flags(B: int, I: int, O: int, n: int, segments: int, discontinuous: boo
     if f < 0:
         raise ValueError("plan_flags: shape outside the envelope")
     return {"tc_forward": bool(f & 1), "tc_dx": bool(f & 2), "tc_dw": bool(f & 4), "dense_dw": bool(f & 8),
-            "shared_phi": bool(f & 16), "rotated_gather": bool(f & 32), "tc_dw_ksplit": (f >> 8) & 255}
+            "shared_phi": bool(f & 16), "rotated_gather": bool(f & 32), "tc_dw_ksplit": (f >> 8) & 255,
+            "tc_fwd_ksplit": (f >> 16) & 255}
 
 
 def uses_tensor_cores(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> bool:

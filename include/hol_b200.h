@@ -178,8 +178,8 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
 
 /* Which kernels the planner picks for a layer shape (diagnostic, used by bench.py): bit 0 / 1 / 2 =
  * forward / dX / dW on the tcgen05 path, bit 3 = dense-register dW (narrow layers), bit 4 = the
- * forward's Phi tiles are shared with dW, bit 5 = lane-rotated gather kernels (S > 8), bits 8..15 =
- * k-split of the tensor-core dW GEMM; -1 = bad shape. */
+ * forward's Phi tiles are shared with dW, bit 5 = lane-rotated gather kernels (S > 8), bits 8..15 /
+ * 16..23 = k-split of the tensor-core dW / forward GEMM; -1 = bad shape. */
 int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int32_t discontinuous);
 
 /* ---- per-sample normalisations between layers ------------------------------

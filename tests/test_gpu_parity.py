@@ -636,7 +636,8 @@ def test_tensor_core_dw_split_over_the_batch(contraction_path):
     w = rng.uniform(-1, 1, size=(O, I, orc.weights_per_link(n, S, False))).astype(np.float32)
     gy = rng.standard_normal(size=(B, O)).astype(np.float32)
     if contraction_path == "tensor-core":
-        assert ops.plan_flags(B, I, O, n, S, False)["tc_dw_ksplit"] > 1
+        plan = ops.plan_flags(B, I, O, n, S, False)
+        assert plan["tc_dw_ksplit"] > 1 and plan["tc_fwd_ksplit"] > 1   # 64 forward tiles: split over K as well
     y, dx, dw = run_fc(x, w, gy, n, S, False)
     y2, dx2, dw2 = run_fc(x, w, gy, n, S, False)
     assert np.array_equal(dw, dw2) and np.array_equal(dx, dx2) and np.array_equal(y, y2)   # bit-reproducible
