@@ -61,6 +61,24 @@ static int tc_bn_for(int O, int64_t mtiles, bool may_shrink) {
     return bn;
 }
 
+// Split of the reduction dimension over several work items per tile: the persistent grid runs
+// `slots` work items at a time (pairs of tiles when there are at least two m-tiles), so the time is
+// ~ceil(items / slots) waves of 1/ks of the k-chunks each; a small charge per split stands for the
+// partial results' reduction pass.  E.g. 98 dW tiles (49 pairs on 74 slots): ks = 3 -> 2 waves of 1/3.
+static int pick_ksplit(int64_t mtiles, int64_t ntiles, int64_t kchunks, int min_chunks, int max_ks) {
+    const int64_t units = (mtiles >= 2 ? (mtiles + 1) / 2 : mtiles) * ntiles;
+    const int64_t slots = mtiles >= 2 ? sm_count() / 2 : sm_count();
+    if (units >= 2 * slots) return 1;  // several waves anyway: the tail is not worth partial buffers of the full result
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ks = 1; ks <= max_ks; ++ks) {
+        if (ks > 1 && kchunks / ks < min_chunks) break;
+        const double cost = (double)((units * ks + slots - 1) / slots) / ks + 0.02 * (ks - 1);
+        if (cost < best_cost - 1e-9) best_cost = cost, best = ks;
+    }
+    return best;
+}
+
 bool tc_plan(const PwShape& s, TcPlan& t) {
     memset(&t, 0, sizeof(t));
     const uint32_t ovr = hol_plan_overrides();
@@ -113,25 +131,13 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     rows = (rows + TC_BM - 1) / TC_BM * TC_BM;
     t.rows_per_launch = rows;
     t.dw_ksplit = 1;
-    if (t.share_phi && t.dw) {
-        const int64_t tiles = (int64_t)(t.nkc_pad / 2) * t.nNTw;
-        const int64_t nbc = (s.Bp + TC_BK - 1) / TC_BK;  // 64-sample stages
-        int64_t ks = sm_count() / tiles;
-        if (ks > nbc / 8) ks = nbc / 8;  // at least 8 stages per split
-        if (ks > 16) ks = 16;
-        if (ks >= 2) t.dw_ksplit = (int)ks;
-    }
+    if (t.share_phi && t.dw)  // 64-sample stages, at least 8 per split
+        t.dw_ksplit = pick_ksplit(t.nkc_pad / 2, t.nNTw, (s.Bp + TC_BK - 1) / TC_BK, 8, 16);
     // forward: no reduction dimension to spare SMs with either -- when the batch gives fewer tiles than ~half
     // the SMs (config 3: 64 tiles of 196 k-chunks) the k-chunks are split over 2-4 work items per tile; every
     // CTA is bound by its own shared-memory / L2 port, so the extra CTAs add bandwidth, not just issue slots
     t.fwd_ksplit = 1;
-    if (t.fwd && rows >= s.Bp) {
-        const int64_t tiles = mtiles_all * t.nNT;
-        int64_t ks = sm_count() / tiles;
-        if (ks > t.nkc / 16) ks = t.nkc / 16;  // at least 16 k-chunks per split
-        if (ks > 4) ks = 4;
-        if (ks >= 2) t.fwd_ksplit = (int)ks;
-    }
+    if (t.fwd && rows >= s.Bp) t.fwd_ksplit = pick_ksplit(mtiles_all, t.nNT, t.nkc, 16, 4);
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
     size_t a = t.share_phi ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
