@@ -597,13 +597,15 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of the same command; keyed by (config, dominant pass).  None where no
-# capture exists.  r1c values (profiles/r1c_tc_ncu_full_summary.md) until the r2 capture replaces them.
+# capture exists.
 NCU_TRAFFIC = {
-    ("c2", "forward"): 22.096271e9 + 0.278053e9,
-    ("c2", "dx"): 7.899103e9 + 0.397953e9,
-    ("c2", "dw"): 13.179519e9 + 0.167509e9,
+    ("c2", "forward"): 20.051057e9 + 0.258172e9,
+    ("c2", "dw"): 19.402402e9 + 0.167457e9,
+    ("c2", "dx"): 4.371290e9 + 0.272215e9,
+    ("c3", "forward"): 417.521e6 + 3.513e6,   # layer 1 (784 -> 128), the layer the roofline block profiles
+    ("c3", "dw"): 419.554e6 + 11.534e6,
 }
-NCU_TRAFFIC_SOURCE = "profiles/r1c_tc_ncu_full_summary.md (ncu --set full, same command)"
+NCU_TRAFFIC_SOURCE = "profiles/r2_c2_ncu_full_summary.md / r2_c3_ncu_full_summary.md (ncu --set full, same command)"
 
 
 def load_peaks():
