@@ -146,6 +146,8 @@ FC_ORACLE_CASES = [
     ("disc", 2, 8, 5, 31, 2100, 2.0),        # widest narrow layer, periodic fold
     ("cont", 1, 8, 7, 12, 4096, None),
     ("disc", 4, 1, 3, 1, 2500, None),
+    ("cont", 4, 4, 128, 10, 8192, None),     # config-3 classifier head at the bench batch: four lanes per sample (fwd.cu IS = 4)
+    ("disc", 3, 5, 37, 16, 1000, None),      # the same variant with a ragged last input chunk
 ]
 
 
