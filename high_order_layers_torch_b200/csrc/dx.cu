@@ -26,11 +26,8 @@ struct DxParams {
 // column chunks of a tile in the rotated order ((qb + (l%8)/4) % (OT/16), (t + l%8) % 4), so the 8
 // lanes of a quarter warp always read 8 different bank groups whatever their segments are (see
 // fwd.cu); the matching gy chunk is loaded in the same order.
-// BTMAX = 512 (with IT = 2): layers whose packed rows are so large that only two inputs fit a stage
-// anyway (S >= 32 at 64-wide tiles): twice the samples per CTA halve the L2 -> shared-memory weight
-// traffic per (sample, input), which is what those shapes are bound by next to the shared-memory wall.
-template <int N, int OT, int IT, bool ROT, int BTMAX = 256>
-__global__ void __launch_bounds__(BTMAX, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __grid_constant__ DxParams p) {
+template <int N, int OT, int IT, bool ROT>
+__global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __grid_constant__ DxParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -200,18 +197,6 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
     } else {
         BT = 256;
         if ((s.Bp / BT) * ((s.I + it_eff - 1) / it_eff) < 2 * 148) BT = 128;
-    }
-    if constexpr (ROT && IT > 2) {
-        // few inputs per stage and plenty of CTAs: the 512-sample variant
-        if (it_eff <= 2 && s.Bp % 512 == 0 && (s.Bp / 512) * ((s.I + it_eff - 1) / it_eff) >= 4 * 148) {
-            auto kern2 = pw_dx_kernel<N, OT, 2, ROT, 512>;
-            static std::atomic<uint64_t> attr_done2{0};
-            cudaError_t e2 = hol_ensure_max_smem(kern2, attr_done2);
-            if (e2 != cudaSuccess) return (int)e2;
-            dim3 grid2((unsigned)(s.Bp / 512), (unsigned)((s.I + it_eff - 1) / it_eff));
-            kern2<<<grid2, 512, smem, st>>>(p);
-            return (int)cudaGetLastError();
-        }
     }
     auto kern = pw_dx_kernel<N, OT, IT, ROT>;
     static std::atomic<uint64_t> attr_done{0};
