@@ -135,14 +135,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def count_launches(layers, first_needs_dx=True, conv=False):
-    """Kernels of csrc/ launched per step for a stack of layers [(B, I, O, n, S, disc), ...]."""
+def count_launches(layers, first_needs_dx=True, conv=False, fused_norm=False):
+    """Kernels of csrc/ launched per step for a stack of layers [(B, I, O, n, S, disc), ...];
+    `fused_norm`: every layer but the last runs with its normalisation folded in (HighOrderMLP)."""
     from high_order_layers_torch_b200 import ops
     total = 0
     for k, (B, I, O, n, S, disc) in enumerate(layers):
         want_dx = first_needs_dx or k > 0
-        total += ops.launch_count(0, B, I, O, n, S, disc)
-        total += ops.launch_count(1, B, I, O, n, S, disc, want_dx=want_dx, want_dw=True, prepared=True)
+        fn = fused_norm and k + 1 < len(layers)
+        total += ops.launch_count(0, B, I, O, n, S, disc, fused_norm=fn)
+        total += ops.launch_count(1, B, I, O, n, S, disc, want_dx=want_dx, want_dw=True, prepared=True, fused_norm=fn)
         if conv:
             total += 1  # the conv prep is two kernels (per-pixel prep, unfold)
         if conv and want_dx:
@@ -259,9 +261,9 @@ def build_workload(torch, cfg, device, rank, args):
         wl.update(model=net, flat=flat, step=step, e2e_compute=e2e_compute, samples=B,
                   host=dict(x=x.cpu().pin_memory(), t=target.cpu().pin_memory()),
                   h2d=x.numel() * 4 + target.numel() * target.element_size(), d2h=4, bytes=by, flops=fl,
-                  # + one fused normalisation kernel each way between consecutive layers (csrc/norm.cu)
-                  launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False)
-                  + 2 * (len(dims) - 1),
+                  # the normalisation between consecutive layers rides in the layer calls (hol_pw_forward_norm_f32)
+                  launches=count_launches([(B, i_, o_, n, S, False) for i_, o_ in dims], first_needs_dx=False,
+                                          fused_norm=True),
                   layers=[(B, i_, o_, n, S, False) for i_, o_ in dims], x=x, first_needs_dx=False)
         return wl
 

@@ -93,6 +93,14 @@ class _PiecewiseBase(nn.Module):
         return ops.piecewise_polynomial(x, self.w, self._n, self._segments, float(self._length),
                                         self._discontinuous, self.periodicity)
 
+    def forward_normalized(self, x: Tensor, norm: str, eps: float = 1e-6) -> Tensor:
+        """norm(self(x)) for the per-sample normalisations (max_abs / max_center / l2) as one layer call:
+        HighOrderMLP uses it for a layer followed by its normalisation module."""
+        if not x.is_cuda or x.dim() != 2:
+            return ops.normalize_rows(self.forward(x), norm, eps)  # forward raises the layer's own errors
+        return ops.piecewise_polynomial_normalized(x, self.w, self._n, self._segments, norm, eps, float(self._length),
+                                                   self._discontinuous, self.periodicity)
+
     def extra_repr(self) -> str:
         return (f"n={self._n}, in_features={self.in_features}, out_features={self.out_features}, "
                 f"segments={self._segments}, length={self._length}, periodicity={self.periodicity}")

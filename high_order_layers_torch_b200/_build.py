@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 LIB_NAME = "libhol_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
 SOURCES = ["prep.cu", "abi.cu", "fwd.cu", "dx.cu", "dw.cu", "dwd.cu", "norm.cu", "optim.cu", "p2p.cu", "tc_gemm.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh", "tc_build.cuh", "tc_kernel.cuh", "tc_fixup.cuh", os.path.join(ROOT, "include", "hol_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh", "tc_build.cuh", "tc_kernel.cuh", "tc_fixup.cuh", "norm_rows.cuh", os.path.join(ROOT, "include", "hol_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

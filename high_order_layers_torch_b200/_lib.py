@@ -15,6 +15,7 @@ HOL_MAX_N = 10
 HOL_MAX_SEGMENTS = 4096
 HOL_WS_PREPARED = 1
 HOL_GY_STATS_VALID = 2
+HOL_COUNT_FUSED_NORM = 4
 # hol_set_plan_overrides bits (diagnostic: tests / A-B runs force a kernel family)
 HOL_PLAN_DISABLE_TENSOR_CORES = 1
 HOL_PLAN_DISABLE_DENSE_DW = 2
@@ -37,6 +38,10 @@ SIGNATURES = {
     "hol_pw_segment_index_i64": (ctypes.c_int, [_vp, _vp, _i64, _i32, _f32, _f32, _vp]),
     "hol_pw_forward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _f32,
                                           _vp, _sz, _vp]),
+    "hol_pw_forward_norm_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i64, _i32, _i32, _i32, _i32, _f32,
+                                               _i32, _f32, _vp, _sz, _vp]),
+    "hol_pw_norm_backward_f32": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _sz,
+                                                _vp]),
     "hol_pw_backward_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32,
                                            _f32, _vp, _sz, _u32, _vp]),
     "hol_pw_conv2d_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),

@@ -209,9 +209,9 @@ int hol_pw_segment_index_i64(const float* x, int64_t* seg, int64_t count, int32_
     return launch_segment_index(x, seg, count, s, (cudaStream_t)stream);
 }
 
-int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, float* y, int64_t B, int32_t I,
-                       int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous, float periodicity,
-                       void* ws_ptr, size_t ws_bytes, void* stream) {
+static int forward_fc(const float* x, const float* w, const float* nodes_host, float* y, const PwNormArgs& norm, int64_t B,
+                      int32_t I, int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous, float periodicity,
+                      void* ws_ptr, size_t ws_bytes, void* stream) {
     if (!x || !w || !nodes_host || !y || !ws_ptr) return B == 0 ? HOL_OK : HOL_EINVAL;
     PwShape s;
     HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, length, periodicity, nodes_host));
@@ -221,9 +221,51 @@ int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, 
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(reset_scalars(s, ws, st));
     HOL_TRY(launch_prep_fc(x, s, ws, st));
-    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w, y, st);
+    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w, y, norm, st);
     HOL_TRY(launch_pack(w, s, ws, st));
-    return launch_forward(s, ws, y, st);
+    HOL_TRY(launch_forward(s, ws, y, st));
+    // gather path: the normalisation runs as its own kernel right behind the forward, inside the same call
+    if (norm.kind >= 0) return launch_row_norm_forward(norm.kind, y, norm.y_norm, norm.stats, B, O, norm.eps, st);
+    return HOL_OK;
+}
+
+int hol_pw_forward_f32(const float* x, const float* w, const float* nodes_host, float* y, int64_t B, int32_t I,
+                       int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous, float periodicity,
+                       void* ws_ptr, size_t ws_bytes, void* stream) {
+    const PwNormArgs none{-1, 0.0f, nullptr, nullptr};
+    return forward_fc(x, w, nodes_host, y, none, B, I, O, n, S, length, discontinuous, periodicity, ws_ptr, ws_bytes, stream);
+}
+
+int hol_pw_forward_norm_f32(const float* x, const float* w, const float* nodes_host, float* y_raw, float* y_norm,
+                            float* stats, int32_t norm_kind, float eps, int64_t B, int32_t I, int32_t O, int32_t n,
+                            int32_t S, float length, int32_t discontinuous, float periodicity, void* ws_ptr,
+                            size_t ws_bytes, void* stream) {
+    if (norm_kind < 0 || norm_kind > 2) return HOL_EINVAL;
+    if (B > 0 && (!y_norm || !stats)) return HOL_EINVAL;
+    const PwNormArgs norm{norm_kind, eps, y_norm, stats};
+    return forward_fc(x, w, nodes_host, y_raw, norm, B, I, O, n, S, length, discontinuous, periodicity, ws_ptr, ws_bytes,
+                      stream);
+}
+
+int hol_pw_norm_backward_f32(int32_t norm_kind, const float* gy_norm, const float* y_raw, const float* stats,
+                             float* gy_raw, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
+                             int32_t discontinuous, void* ws_ptr, size_t ws_bytes, void* stream) {
+    if (norm_kind < 0 || norm_kind > 2 || B < 0) return HOL_EINVAL;
+    if (B == 0) return HOL_OK;
+    if (!gy_norm || !y_raw || !stats || !gy_raw || !ws_ptr) return HOL_EINVAL;
+    PwShape s;
+    HOL_TRY(make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr));
+    PwWorkspace ws;
+    if (carve(s, ws_ptr, ws, -1) > ws_bytes) return HOL_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the same sweep takes max|gy_raw| for the tensor-core backward passes of the layer (HOL_GY_STATS_VALID)
+    unsigned* absmax = nullptr;
+    if (s.tc.enabled && (s.tc.dx || s.tc.dw)) {
+        absmax = reinterpret_cast<unsigned*>(ws.tc_scalars) + 2;  // TcScalars::max_gy
+        cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return launch_row_norm_backward(norm_kind, gy_norm, y_raw, stats, gy_raw, B, O, absmax, st);
 }
 
 int hol_pw_backward_f32(const float* gy, const float* x, const float* w, const float* nodes_host, float* dx, float* dw,
@@ -289,7 +331,7 @@ int hol_pw_conv_forward_f32(const float* x, const float* w_fc, const float* node
     cudaStream_t st = (cudaStream_t)stream;
     HOL_TRY(reset_scalars(s, ws, st));
     HOL_TRY(launch_prep_conv(x, s, ws, Bimg, g, st));
-    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, st);
+    if (s.tc.fwd) return launch_forward_tc(s, ws, s.tc, w_fc, y_rows, PwNormArgs{-1, 0.0f, nullptr, nullptr}, st);
     HOL_TRY(launch_pack(w_fc, s, ws, st));
     return launch_forward(s, ws, y_rows, st);
 }
@@ -378,7 +420,9 @@ int hol_pw_profile_f32(const float* gy, const float* x, const float* w, const fl
     mark(1);
     if (rc == HOL_OK && !(s.tc.fwd && (s.tc.dx || n == 1))) rc = launch_pack(w, s, ws, st);
     mark(2);
-    if (rc == HOL_OK) rc = s.tc.fwd ? launch_forward_tc(s, ws, s.tc, w, y, st) : launch_forward(s, ws, y, st);
+    if (rc == HOL_OK)
+        rc = s.tc.fwd ? launch_forward_tc(s, ws, s.tc, w, y, PwNormArgs{-1, 0.0f, nullptr, nullptr}, st)
+                      : launch_forward(s, ws, y, st);
     mark(3);
     if (rc == HOL_OK && ((s.tc.dx && n > 1) || s.tc.dw)) rc = launch_tc_gy_absmax(s, ws, gy, st);
     if (rc == HOL_OK) {
@@ -424,8 +468,11 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     PwShape s;
     if (make_shape(s, B, I, O, n, S, discontinuous, 2.0f, NAN, nullptr) != HOL_OK) return -1;
     const bool prepared = (flags & HOL_WS_PREPARED) != 0;
-    if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0, false) : 2);  // prep + (pack, forward)
+    const bool fused_norm = (flags & HOL_COUNT_FUSED_NORM) != 0;
+    // prep + (pack, forward [, normalisation kernel]); on the tensor-core path the normalisation rides in the finalize pass
+    if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0, false) : 2 + (fused_norm ? 1 : 0));
     int c = prepared ? 0 : 1;  // prep
+    if (fused_norm) c += 1;    // normalisation backward (takes max|gy| along the way: HOL_GY_STATS_VALID)
     const bool tc_dx = want_dx && n > 1 && s.tc.dx, tc_dw = want_dw && s.tc.dw;
     if ((tc_dx || tc_dw) && !(flags & HOL_GY_STATS_VALID)) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
     if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2);

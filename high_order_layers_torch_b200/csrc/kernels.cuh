@@ -31,7 +31,15 @@ int launch_backward_dw_dense(const PwShape& s, const PwWorkspace& ws, const floa
 
 // tensor-core passes (tc_gemm.cu)
 bool tc_plan(const PwShape& s, TcPlan& t);
-int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st);
+// a per-sample normalisation folded into a layer's passes (kind < 0: none)
+struct PwNormArgs {
+    int kind;
+    float eps;
+    float* y_norm;  // [B][O]
+    float* stats;   // [B][4]
+};
+int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y,
+                      const PwNormArgs& norm, cudaStream_t st);
 // max |gy| -> TcScalars::max_gy; once per backward call before the dW / dX passes below
 int launch_tc_gy_absmax(const PwShape& s, const PwWorkspace& ws, const float* gy, cudaStream_t st);
 // phi_valid: ws.tc_phi still holds the forward's Phi tiles (shared-Phi path)
@@ -40,6 +48,11 @@ int launch_backward_dw_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
 // wstats_valid: max |w| and the link means in the workspace are the forward's
 int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, const float* gy,
                           float* dx, int transposed, bool wstats_valid, cudaStream_t st);
+
+// per-sample normalisations (norm.cu); absmax != nullptr: the backward also takes max |dx| (a layer's gy statistics)
+int launch_row_norm_forward(int kind, const float* x, float* y, float* stats, int64_t B, int W, float eps, cudaStream_t st);
+int launch_row_norm_backward(int kind, const float* gy, const float* x, const float* stats, float* dx, int64_t B, int W,
+                             unsigned* absmax, cudaStream_t st);
 
 // per-GEMM event pairs collected while hol_pw_profile_f32 runs (PwWorkspace::prof)
 struct TcProf {

@@ -10,6 +10,7 @@
 // walks its outliers in a fixed order, so the results stay bit-reproducible.  With no outlier in the
 // batch (TcScalars::n_outliers == 0, the normal case) each kernel returns at once.
 #pragma once
+#include "norm_rows.cuh"
 #include "tc_common.cuh"
 
 // run-time-n versions of lagrange_basis / lagrange_basis_derivative (common.cuh)
@@ -121,5 +122,69 @@ __global__ void __launch_bounds__(256) pw_tc_fix_dw_kernel(const __grid_constant
                 for (int j = 0; j < p.n; ++j) dl[j] = fmaf(phi[j], g, dl[j]);
             }
         }
+    }
+}
+
+// Last kernel of a tensor-core forward: ONE pass per output row (one warp per row) that
+//   (1) sums the partial results of a forward split over K (ks > 1; fixed order),
+//   (2) adds the fp32 contributions of the row's outlier elements (skipped when the batch has none),
+//   (3) applies the per-sample normalisation that follows the layer in the network, if any
+//       (max_abs / max_center / l2 as the forward's epilogue): the raw row goes to y_raw
+//       (the normalisation's backward needs it), the normalised row to y_norm, its statistics to stats.
+// It replaces the separate reduction, fix-up and normalisation launches (three passes over [B, O]).
+struct FinalizeParams {
+    FixParams fix;        // fix.out = y_raw [B][O]
+    const float* parts;   // [ks][B][O] partial results, or nullptr: y_raw already holds the GEMM's result
+    float* y_norm;        // nullptr: no normalisation
+    float4* stats;
+    int ks, norm_kind;
+    float eps;
+};
+
+__global__ void __launch_bounds__(256) pw_tc_finalize_kernel(const __grid_constant__ FinalizeParams q) {
+    const FixParams& p = q.fix;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= p.B) return;
+    float* yr = p.out + b * p.O;
+    if (q.parts) {
+        const int64_t stride = p.B * (int64_t)p.O;
+        for (int o = lane; o < p.O; o += 32) {
+            float acc = 0.0f;
+            for (int k = 0; k < q.ks; ++k) acc += q.parts[(int64_t)k * stride + b * p.O + o];
+            yr[o] = acc;
+        }
+    }
+    if (p.sc->n_outliers != 0) {
+        // lanes scan the row's inputs 32 at a time; an outlier is then handled by the whole warp over the outputs
+        for (int i0 = 0; i0 < p.I; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t sg = (i < p.I) ? p.seg_t[(int64_t)i * p.Bp + b] : 0u;
+            unsigned mask = __ballot_sync(0xffffffffu, (sg & HOL_SEG_OUTLIER) != 0);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int ii = i0 + l;
+                const uint32_t sgl = __shfl_sync(0xffffffffu, sg, l);
+                const float xl = p.xl_t[(int64_t)ii * p.Bp + b];
+                float phi[HOL_MAX_N];
+                fix_basis(xl, p.tab, p.n, phi, false);
+                const int col = (int)(sgl & HOL_SEG_MASK) * p.stride;
+                __syncwarp();
+                for (int o = lane; o < p.O; o += 32) {
+                    const float* wl = p.w + ((int64_t)o * p.I + ii) * p.nb + col;
+                    float acc = 0.0f;
+                    for (int j = 0; j < p.n; ++j) acc = fmaf(phi[j], wl[j], acc);
+                    yr[o] += acc;
+                }
+            }
+        }
+    }
+    if (q.y_norm) {
+        __syncwarp();  // the row was written by this warp's lanes: visible to all of them from here on
+        float* nr = q.y_norm + b * p.O;
+        if (q.norm_kind == HOL_NORM_MAX_ABS) norm_row_forward<HOL_NORM_MAX_ABS>(yr, nr, q.stats + b, p.O, q.eps, lane);
+        else if (q.norm_kind == HOL_NORM_MAX_CENTER) norm_row_forward<HOL_NORM_MAX_CENTER>(yr, nr, q.stats + b, p.O, q.eps, lane);
+        else norm_row_forward<HOL_NORM_L2>(yr, nr, q.stats + b, p.O, q.eps, lane);
     }
 }

@@ -267,7 +267,7 @@ static int launch_gemm(TcGemmParams p, int64_t mtiles, int ntiles_n, int ksplit,
 // max|gy| pass of a backward with any tensor-core part (prep not included)
 int tc_launch_count(const PwShape& s, const TcPlan& t, int kind, bool prepared) {
     const int nl = (int)((s.Bp + t.rows_per_launch - 1) / t.rows_per_launch);
-    if (kind == 0) return 2 + nl * 2 + (t.fwd_ksplit > 1 ? 1 : 0) + 1;  // wstats, pack_w, (expand, gemm), [reduce], fix_y
+    if (kind == 0) return 2 + nl * 2 + 1;                          // wstats, pack_w, (expand, gemm) per batch chunk, finalize
     if (kind == 1) return (prepared ? 0 : 1) + 1 + nl * 2 + 1;     // [wstats], pack_wt, (pack_gy, gemm), fix_dx
     if (kind == 3) return 1;
     if (t.share_phi) return (prepared && t.fwd ? 0 : 1) + 2 + (t.dw_ksplit > 1 ? 1 : 0) + 1;  // [expand], pack_gyt, gemm, [reduce], fix_dw
@@ -341,7 +341,10 @@ static int launch_expand(const PwShape& s, const PwWorkspace& ws, const TcPlan& 
     return rc;
 }
 
-int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y, cudaStream_t st) {
+// norm.kind >= 0: the per-sample normalisation that follows the layer is applied by the forward's last
+// kernel (y = raw output, norm.y_norm / norm.stats = normalised output and its statistics)
+int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, const float* w, float* y,
+                      const PwNormArgs& norm, cudaStream_t st) {
     TcScalars* sc = (TcScalars*)ws.tc_scalars;
     int rc = launch_tc_wstats(s, ws, w, st);
     if (rc != HOL_OK) return rc;
@@ -372,15 +375,20 @@ int launch_forward_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan& t, 
         p.a_tiles = phi;
         rc = launch_gemm<EPI_Y, 0, A_TILES>(p, rows / TC_BM, t.nNT, t.fwd_ksplit, (TcProf*)ws.prof, st);
         if (rc != HOL_OK) return rc;
-        if (split) {
-            const int kcs = (t.nkc + t.fwd_ksplit - 1) / t.fwd_ksplit;
-            rc = launch_dw_reduce(ws.y_part, y, s.B * (int64_t)s.O, (t.nkc + kcs - 1) / kcs, st);
-            if (rc != HOL_OK) return rc;
-        }
     }
-    FixParams f;
-    fill_fix(f, s, ws, w, nullptr, y, 0);
-    pw_tc_fix_rows_kernel<false><<<(unsigned)((s.B + 255) / 256), 256, 0, st>>>(f);
+    // one pass over the rows: sum of the k-split partials, outlier contributions, optional normalisation
+    FinalizeParams q;
+    fill_fix(q.fix, s, ws, w, nullptr, y, 0);
+    q.parts = t.fwd_ksplit > 1 ? ws.y_part : nullptr;
+    {
+        const int kcs = (t.nkc + t.fwd_ksplit - 1) / t.fwd_ksplit;
+        q.ks = (t.nkc + kcs - 1) / kcs;
+    }
+    q.y_norm = norm.kind >= 0 ? norm.y_norm : nullptr;
+    q.stats = reinterpret_cast<float4*>(norm.stats);
+    q.norm_kind = norm.kind;
+    q.eps = norm.eps;
+    pw_tc_finalize_kernel<<<(unsigned)((s.B + 7) / 8), 256, 0, st>>>(q);
     return (int)cudaGetLastError();
 }
 

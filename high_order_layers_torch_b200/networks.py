@@ -6,7 +6,25 @@ from typing import Any, Callable, Optional
 import torch.nn as nn
 from torch import Tensor
 
-from .layers import SumLayer, high_order_fc_layers
+from .layers import L2Normalization, MaxAbsNormalization, MaxCenterNormalization, SumLayer, high_order_fc_layers
+from .PolynomialLayers import _PiecewiseBase
+
+
+def _fusable_norm(layer, norm):
+    """(kind, eps) when `norm` is one of the per-sample normalisations the layer kernels can apply themselves
+    and neither module carries hooks that would have to see the intermediate tensor; else None."""
+    if not isinstance(layer, _PiecewiseBase) or not hasattr(layer, "forward_normalized"):
+        return None
+    for m in (layer, norm):
+        if m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks:
+            return None
+    if type(norm) is MaxAbsNormalization and norm._dim in (1, -1):
+        return "max_abs", norm._eps
+    if type(norm) is MaxCenterNormalization:
+        return "max_center", norm._eps
+    if type(norm) is L2Normalization:
+        return "l2", norm._eps
+    return None
 
 
 class HighOrderMLP(nn.Module):
@@ -58,6 +76,21 @@ class HighOrderMLP(nn.Module):
                                                  initialization=initialization, **common)
         stack.append(self.output_layer)
         self.model = nn.Sequential(*stack)
+        self.fuse_normalization = True  # False: run every module of `model` on its own (same results)
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.model(x)
+        """``self.model(x)``, except that a layer directly followed by its per-sample normalisation runs as
+        one fused call (``forward_normalized``: the forward's last kernel also normalises, the
+        normalisation's backward also takes the statistic the layer's backward needs) -- same values."""
+        mods = list(self.model)
+        k = 0
+        while k < len(mods):
+            fused = _fusable_norm(mods[k], mods[k + 1]) if (self.fuse_normalization and k + 1 < len(mods)
+                                                            and x.is_cuda and x.dim() == 2) else None
+            if fused is not None:
+                x = mods[k].forward_normalized(x, *fused)
+                k += 2
+            else:
+                x = mods[k](x)
+                k += 1
+        return x

@@ -176,7 +176,8 @@ def _(gy, x, w, ws, n, segments, length, discontinuous, periodicity, need_dx, ne
 
 @torch.library.custom_op("hol::pw_backward_dw_into", mutates_args=("ws", "dw_out"), device_types="cuda")
 def pw_backward_dw_into(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, dw_out: Tensor, n: int, segments: int,
-                        length: float, discontinuous: bool, periodicity: Optional[float], ws_prepared: bool) -> None:
+                        length: float, discontinuous: bool, periodicity: Optional[float], ws_prepared: bool,
+                        gy_stats_valid: bool = False) -> None:
     """dW only, written (not accumulated) into `dw_out` -- a caller-owned contiguous fp32 tensor of
     w's shape, e.g. the parameter's slice of a flat data-parallel gradient buffer (parallel.py)."""
     _check_inputs(x, w, "pw_backward_dw_into")
@@ -190,12 +191,13 @@ def pw_backward_dw_into(gy: Tensor, x: Tensor, w: Tensor, ws: Tensor, dw_out: Te
     with torch.cuda.device(x.device):
         _lib.check(lib.hol_pw_backward_f32(_ptr(gyc), _ptr(xc), _ptr(wc), _ptr(nodes), _ptr(None), _ptr(dw_out), B, I, O,
                                            n, segments, length, int(discontinuous), _per(periodicity), _ptr(ws),
-                                           ws.numel(), _lib.HOL_WS_PREPARED if ws_prepared else 0, _stream(x)),
+                                           ws.numel(), (_lib.HOL_WS_PREPARED if ws_prepared else 0)
+                                           | (_lib.HOL_GY_STATS_VALID if gy_stats_valid else 0), _stream(x)),
                    "hol_pw_backward_f32")
 
 
 @pw_backward_dw_into.register_fake
-def _(gy, x, w, ws, dw_out, n, segments, length, discontinuous, periodicity, ws_prepared):
+def _(gy, x, w, ws, dw_out, n, segments, length, discontinuous, periodicity, ws_prepared, gy_stats_valid=False):
     return None
 
 
@@ -222,22 +224,28 @@ def _pw_bwd(ctx, gy, _gws=None):
     """Backward of hol::pw_forward.  dW first (csrc/abi.cu): when the weight has a gradient sink the
     slice's all-reduce is issued between the dW and the dX launches and overlaps the latter."""
     x, w = ctx.saved_tensors
+    if gy is None:  # y did not take part in the loss
+        return (None,) * 7
+    dx, dw = _layer_backward(ctx, gy, x, w, False)
+    return dx, dw, None, None, None, None, None
+
+
+def _layer_backward(ctx, gy, x, w, gy_stats_valid: bool):
+    """dW, then dX, of one layer from the forward's workspace; `gy_stats_valid`: max|gy| is already there."""
     ws = ctx.ws
     need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     dx = dw = None
-    if gy is None:  # y did not take part in the loss
-        return (None,) * 7
     sink, out = _grad_sink(ctx.w_ref) if need_dw else (None, None)
     if sink is not None:
-        pw_backward_dw_into(gy, x, w, ws, out, *ctx.args, True)
+        pw_backward_dw_into(gy, x, w, ws, out, *ctx.args, True, gy_stats_valid)
         sink.ready(ctx.w_ref)
         if need_dx:
             dx = pw_backward(gy, x, w, ws, *ctx.args, True, False, True, True)[0]
     elif need_dx or need_dw:
-        rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True)
+        rdx, rdw = pw_backward(gy, x, w, ws, *ctx.args, need_dx, need_dw, True, gy_stats_valid)
         dx = rdx if need_dx else None
         dw = rdw if need_dw else None
-    return dx, dw, None, None, None, None, None
+    return dx, dw
 
 
 pw_forward.register_autograd(_pw_bwd, setup_context=_pw_setup)
@@ -251,6 +259,110 @@ def piecewise_polynomial(x: Tensor, w: Tensor, n: int, segments: int, length: fl
     if not x.is_meta:
         _check_inputs(x, w, "piecewise_polynomial")
     return pw_forward(x, w, n, segments, float(length), bool(discontinuous), periodicity)[0]
+
+
+# ------------------------------------------------------------------------------------------
+# a layer with the per-sample normalisation that follows it in the network
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("hol::pw_forward_norm", mutates_args=(), device_types="cuda")
+def pw_forward_norm(x: Tensor, w: Tensor, n: int, segments: int, length: float, discontinuous: bool,
+                    periodicity: Optional[float], norm_kind: int, eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (y_norm[B, O], y_raw[B, O], stats[B, 4], ws): the layer and the normalisation HighOrderMLP puts
+    behind it (reference networks.py:235-270) in one call -- on the tensor-core path the forward's last
+    kernel writes both rows (hol_pw_forward_norm_f32)."""
+    _check_inputs(x, w, "pw_forward_norm")
+    if x.dim() != 2:
+        raise ValueError(f"pw_forward_norm: x must be [batch, in_features], got {tuple(x.shape)}")
+    B, I = x.shape
+    O = w.shape[0]
+    if tuple(w.shape) != (O, I, _nb(n, segments, discontinuous)):
+        raise ValueError(f"pw_forward_norm: weight shape {tuple(w.shape)} does not match "
+                         f"[out, {I}, {_nb(n, segments, discontinuous)}]")
+    lib = _lib.load()
+    xc, wc = x.contiguous(), w.contiguous()
+    y_raw = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    y_norm = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    stats = torch.empty((B, 4), dtype=torch.float32, device=x.device)
+    ws = torch.empty(_fc_workspace_bytes(B, I, O, n, segments, discontinuous), dtype=torch.uint8, device=x.device)
+    nodes = lobatto_nodes(n, 2.0)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hol_pw_forward_norm_f32(_ptr(xc), _ptr(wc), _ptr(nodes), _ptr(y_raw), _ptr(y_norm), _ptr(stats),
+                                               norm_kind, eps, B, I, O, n, segments, length, int(discontinuous),
+                                               _per(periodicity), _ptr(ws), ws.numel(), _stream(x)),
+                   "hol_pw_forward_norm_f32")
+    return y_norm, y_raw, stats, ws
+
+
+@pw_forward_norm.register_fake
+def _(x, w, n, segments, length, discontinuous, periodicity, norm_kind, eps):
+    B, I = x.shape
+    O = w.shape[0]
+    nbytes = _fc_workspace_bytes(int(B), int(I), int(O), n, segments, discontinuous)
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=x.device)
+    return f(B, O), f(B, O), f(B, 4), torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+
+
+@torch.library.custom_op("hol::pw_norm_backward", mutates_args=("ws",), device_types="cuda")
+def pw_norm_backward(gy_norm: Tensor, y_raw: Tensor, stats: Tensor, ws: Tensor, norm_kind: int, in_features: int,
+                     n: int, segments: int, discontinuous: bool) -> Tensor:
+    """Gradient w.r.t. the layer's raw output from the gradient w.r.t. the normalised one; the same sweep
+    leaves max|gy_raw| in the layer's workspace for its tensor-core backward passes (hol_pw_norm_backward_f32)."""
+    lib = _lib.load()
+    g = gy_norm.contiguous()
+    B, O = y_raw.shape
+    out = torch.empty_like(y_raw)
+    with torch.cuda.device(y_raw.device):
+        _lib.check(lib.hol_pw_norm_backward_f32(norm_kind, _ptr(g), _ptr(y_raw), _ptr(stats), _ptr(out), B, in_features, O,
+                                                n, segments, int(discontinuous), _ptr(ws), ws.numel(), _stream(y_raw)),
+                   "hol_pw_norm_backward_f32")
+    return out
+
+
+@pw_norm_backward.register_fake
+def _(gy_norm, y_raw, stats, ws, norm_kind, in_features, n, segments, discontinuous):
+    return torch.empty_like(y_raw)
+
+
+def _pwn_setup(ctx, inputs, output):
+    x, w, n, segments, length, discontinuous, periodicity, norm_kind, _eps = inputs
+    ctx.save_for_backward(x, w, output[1], output[2])
+    ctx.ws = output[3]
+    ctx.set_materialize_grads(False)
+    ctx.w_ref = w
+    ctx.args = (n, segments, length, discontinuous, periodicity)
+    ctx.norm_kind = norm_kind
+
+
+def _pwn_bwd(ctx, g_norm, g_raw=None, _gstats=None, _gws=None):
+    x, w, y_raw, stats = ctx.saved_tensors
+    if g_norm is None and g_raw is None:
+        return (None,) * 9
+    n, segments, _length, discontinuous, _per_ = ctx.args
+    stats_valid = False
+    gy = g_raw
+    if g_norm is not None:
+        gy = pw_norm_backward(g_norm, y_raw, stats, ctx.ws, ctx.norm_kind, x.shape[1], n, segments, discontinuous)
+        stats_valid = g_raw is None
+        if g_raw is not None:  # the raw output was used as well: its gradient adds, the statistic is stale
+            gy = gy + g_raw
+    dx, dw = _layer_backward(ctx, gy, x, w, stats_valid)
+    return dx, dw, None, None, None, None, None, None, None
+
+
+pw_forward_norm.register_autograd(_pwn_bwd, setup_context=_pwn_setup)
+
+NORM_KINDS = {"max_abs": 0, "max_center": 1, "l2": 2}
+
+
+def piecewise_polynomial_normalized(x: Tensor, w: Tensor, n: int, segments: int, norm: str, eps: float = 1e-6,
+                                    length: float = 2.0, discontinuous: bool = False,
+                                    periodicity: Optional[float] = None) -> Tensor:
+    """normalisation(Piecewise(n, segments)(x)) for norm in {"max_abs", "max_center", "l2"} as ONE layer call
+    each way: bit-identical to ``normalize_rows(piecewise_polynomial(...), norm, eps)``."""
+    if not x.is_meta:
+        _check_inputs(x, w, "piecewise_polynomial_normalized")
+    return pw_forward_norm(x, w, n, segments, float(length), bool(discontinuous), periodicity, NORM_KINDS[norm],
+                           float(eps))[0]
 
 
 # ------------------------------------------------------------------------------------------
@@ -511,9 +623,6 @@ def piecewise_polynomial_conv_transpose2d(x: Tensor, weight: Tensor, n: int, seg
 # ------------------------------------------------------------------------------------------
 # per-sample normalisations between layers: one fused kernel each way
 # ------------------------------------------------------------------------------------------
-NORM_KINDS = {"max_abs": 0, "max_center": 1, "l2": 2}
-
-
 @torch.library.custom_op("hol::row_norm", mutates_args=(), device_types="cuda")
 def row_norm(x: Tensor, kind: int, eps: float) -> Tuple[Tensor, Tensor]:
     """x[B, W] -> (y[B, W], stats[B, 4]); kind 0 max_abs, 1 max_center, 2 l2 (reference utils.py:8-58)."""
@@ -570,10 +679,13 @@ def normalize_rows(x: Tensor, kind: str, eps: float = 1e-6) -> Tensor:
 
 
 def launch_count(kind: int, B: int, I: int, O: int, n: int, segments: int, discontinuous: bool, want_dx: bool = True,
-                 want_dw: bool = True, prepared: bool = True) -> int:
-    """Kernels of this library launched by one forward (kind 0) / backward (kind 1) call of a layer."""
+                 want_dw: bool = True, prepared: bool = True, fused_norm: bool = False) -> int:
+    """Kernels of this library launched by one forward (kind 0) / backward (kind 1) call of a layer;
+    `fused_norm`: the layer runs with the normalisation folded in (pw_forward_norm and its backward)."""
+    flags = (_lib.HOL_WS_PREPARED if prepared else 0) | (_lib.HOL_COUNT_FUSED_NORM | _lib.HOL_GY_STATS_VALID
+                                                        if fused_norm else 0)
     return _lib.load().hol_pw_launch_count(kind, B, I, O, n, segments, int(discontinuous), int(want_dx), int(want_dw),
-                                           _lib.HOL_WS_PREPARED if prepared else 0)
+                                           flags)
 
 
 def plan_flags(B: int, I: int, O: int, n: int, segments: int, discontinuous: bool) -> dict:

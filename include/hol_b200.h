@@ -54,6 +54,10 @@ extern "C" {
 #define HOL_MAX_N 10
 #define HOL_MAX_SEGMENTS 4096
 
+#define HOL_NORM_MAX_ABS 0     /* per-sample normalisation kinds (utils.py:8-58) */
+#define HOL_NORM_MAX_CENTER 1
+#define HOL_NORM_L2 2
+
 #define HOL_OK 0
 #define HOL_EINVAL (-1)        /* bad argument (null pointer, non-positive size, ...)      */
 #define HOL_EUNSUPPORTED (-2)  /* valid request outside the compiled envelope (n, S, smem) */
@@ -62,6 +66,7 @@ extern "C" {
 /* flags for hol_pw_backward_f32 */
 #define HOL_WS_PREPARED 1u     /* `ws` still holds the forward's prepared state for the very
                                   same (x, w, shape): skip the prep + pack stages           */
+#define HOL_COUNT_FUSED_NORM 4u /* hol_pw_launch_count only: the layer runs with a folded normalisation */
 #define HOL_GY_STATS_VALID 2u  /* `ws` still holds max|gy| of this very gy, left by a previous
                                   backward call of the same step (a backward split into a dw
                                   call and a dx call takes the statistics once)              */
@@ -106,6 +111,23 @@ int hol_pw_backward_f32(const float* gy, const float* x, const float* w,
                         int32_t O, int32_t n, int32_t S, float length, int32_t discontinuous,
                         float periodicity, void* ws, size_t ws_bytes, uint32_t flags,
                         void* stream);
+
+/* ---- a layer with the per-sample normalisation that follows it --------------------------
+ * HighOrderMLP puts max_abs / max_center / l2 normalisation behind every layer but the last
+ * (networks.py:235-270, layers.py:43-145).  Forward: as hol_pw_forward_f32, and the forward's LAST kernel
+ * (the pass that sums the k-split partial results and adds outlier contributions on the tensor-core
+ * path) also writes the normalised rows y_norm[B, O] and their statistics stats[B][4]; y_raw keeps the
+ * layer's own output (the normalisation's backward needs it).  norm_kind: HOL_NORM_*.
+ * Backward: hol_pw_norm_backward_f32 turns the gradient w.r.t. y_norm into gy_raw[B, O] and, in the same
+ * sweep, takes the max|gy_raw| statistic of the layer's tensor-core passes into `ws`; follow it with
+ * hol_pw_backward_f32(gy_raw, ..., flags = HOL_WS_PREPARED | HOL_GY_STATS_VALID). */
+int hol_pw_forward_norm_f32(const float* x, const float* w, const float* nodes_host, float* y_raw, float* y_norm,
+                            float* stats, int32_t norm_kind, float eps, int64_t B, int32_t I, int32_t O,
+                            int32_t n, int32_t S, float length, int32_t discontinuous, float periodicity,
+                            void* ws, size_t ws_bytes, void* stream);
+int hol_pw_norm_backward_f32(int32_t norm_kind, const float* gy_norm, const float* y_raw, const float* stats,
+                             float* gy_raw, int64_t B, int32_t I, int32_t O, int32_t n, int32_t S,
+                             int32_t discontinuous, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- unfolded PiecewisePolynomialConvolution2d (FunctionalConvolution.py:441-447) -------
  * The convolution is the layer above applied to im2col rows: rows = Bimg*Ho*Wo,
@@ -188,9 +210,6 @@ int hol_pw_plan_flags(int64_t B, int32_t I, int32_t O, int32_t n, int32_t S, int
  * and l2_normalization (utils.py:57-58, layers.py:132-141) over dim 1 of x[B, W].
  * kind: 0 max_abs, 1 max_center, 2 l2.  stats[B][4] (fp32) is written by the forward and read by
  * the backward (denominator, centre / norm, arg-max / arg-min as int bits). */
-#define HOL_NORM_MAX_ABS 0
-#define HOL_NORM_MAX_CENTER 1
-#define HOL_NORM_L2 2
 int hol_row_norm_forward_f32(int32_t kind, const float* x, float* y, float* stats, int64_t B,
                              int32_t W, float eps, void* stream);
 int hol_row_norm_backward_f32(int32_t kind, const float* gy, const float* x, const float* stats,

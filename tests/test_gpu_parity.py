@@ -823,6 +823,11 @@ def test_opcheck_all_ops():
         opcheck(torch.ops.hol.row_norm.default, (xn.clone().requires_grad_(True), kind, 1e-6))
         y, st = ops.row_norm(xn, kind, 1e-6)
         opcheck(torch.ops.hol.row_norm_backward.default, (torch.ones_like(xn), xn, st, kind))
+    for kind in (0, 1, 2):
+        opcheck(torch.ops.hol.pw_forward_norm.default,
+                (x.clone().requires_grad_(True), w.clone().requires_grad_(True)) + fa + (kind, 1e-6), test_utils=basic)
+        yn, yr, st, wsn = ops.pw_forward_norm(x, w, *fa, kind, 1e-6)
+        opcheck(torch.ops.hol.pw_norm_backward.default, (gy, yr, st, wsn, kind, 6, 3, 4, False), test_utils=basic)
     p_ = t(rng.uniform(-1, 1, size=(50,)).astype(np.float32))
     opcheck(torch.ops.hol.sparse_lion_step.default, (p_.clone(), torch.ones_like(p_), torch.zeros_like(p_), 1e-3, 0.0, 0.9, 0.99))
 
@@ -936,3 +941,87 @@ def test_row_norms_nan_rows_match_torch():
         assert torch.isfinite(y[ok]).all() and torch.isfinite(xt.grad[ok]).all()
         if expr is not None:
             assert torch.equal(y[ok], expr(x[ok]))
+
+
+def _same(a, b):
+    return torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0))
+
+
+@pytest.mark.parametrize("B,I,O,n,S,disc", [(1024, 128, 128, 4, 4, False),    # tensor-core layer, forward split over K
+                                            (2048, 784, 128, 4, 4, False),    # first layer of config 3 (on a slice)
+                                            (700, 96, 200, 5, 8, True),       # ragged batch, discontinuous, two N tiles
+                                            (333, 24, 10, 3, 4, False),       # narrow output layer: gather kernels
+                                            (64, 5, 3, 2, 2, True)])
+@pytest.mark.parametrize("norm", ["max_abs", "max_center", "l2"])
+def test_layer_with_folded_normalisation_is_bit_identical_to_the_two_calls(B, I, O, n, S, disc, norm):
+    """SURVEY 8f-1: hol::pw_forward_norm (layer + the per-sample normalisation behind it as one call, the
+    normalisation's backward taking the layer's max|gy| statistic along the way) against
+    normalize_rows(piecewise_polynomial(...)): outputs and both gradients identical bit for bit, with and
+    without outlier inputs, and when the batch also uses the raw output."""
+    rng = np.random.default_rng(B + I + O)
+    nb = orc.weights_per_link(n, S, disc)
+    xh = rng.uniform(-1.1, 1.1, size=(B, I)).astype(np.float32)
+    xh[3, 1] = 40.0  # an outlier on the tensor-core path: goes through the fp32 contributions of the same pass
+    wh = rng.uniform(-1, 1, size=(O, I, nb)).astype(np.float32)
+    gyh = rng.standard_normal(size=(B, O)).astype(np.float32)
+    for use_raw in (False, True):
+        res = []
+        for fused in (False, True):
+            x = t(xh).requires_grad_(True)
+            w = t(wh).requires_grad_(True)
+            if fused:
+                yn, yr, _, _ = ops.pw_forward_norm(x, w, n, S, 2.0, disc, None, ops.NORM_KINDS[norm], 1e-6)
+            else:
+                yr = ops.piecewise_polynomial(x, w, n, S, 2.0, disc, None)
+                yn = ops.normalize_rows(yr, norm, 1e-6)
+            loss = (yn * t(gyh)).sum() + ((yr * yr).sum() * 0.01 if use_raw else 0.0)
+            loss.backward()
+            res.append((yn.detach(), yr.detach(), x.grad, w.grad))
+        for a, b, name in zip(res[0], res[1], ("y_norm", "y_raw", "dx", "dw")):
+            assert _same(a, b), (name, use_raw, float((a - b).abs().max()))
+    # and against the oracle: its layer output through its restatement of the normalisation (utils.py:8-58)
+    y_or = orc.pw_forward(xh, wh, n, S, 2.0, disc)
+    want = {"max_abs": orc.max_abs_normalization, "max_center": orc.max_center_normalization,
+            "l2": orc.l2_normalization}[norm](y_or)
+    assert rel_err(res[1][0].cpu().numpy(), want) < 5e-5  # the outlier's |t|^(n-1) growth costs fp32 digits in its row
+
+
+def test_mlp_runs_layers_with_folded_normalisation_and_matches_module_by_module():
+    """HighOrderMLP.forward folds each normalisation module into the layer before it; with
+    fuse_normalization = False every module of `model` runs on its own.  Same outputs and gradients
+    bit for bit, also through the data-parallel gradient sink; the library's launch count drops by the
+    gy-statistics pass of every normalised tensor-core layer."""
+    from high_order_layers_torch_b200.parallel import FlatGradients
+    for norm_cls in (hol.MaxAbsNormalization, hol.MaxCenterNormalization, hol.L2Normalization):
+        torch.manual_seed(1)
+        net = hol.HighOrderMLP(layer_type="continuous", n=4, in_width=200, out_width=10, hidden_layers=1, hidden_width=128,
+                               in_segments=4, hidden_segments=4, out_segments=4, normalization=norm_cls, device=DEV)
+        x = torch.rand(1024, 200, device=DEV) * 2 - 1
+        tgt = torch.randint(0, 10, (1024,), device=DEV)
+        out = {}
+        for fuse in (False, True):
+            net.fuse_normalization = fuse
+            net.zero_grad(set_to_none=True)
+            y = net(x)
+            torch.nn.functional.cross_entropy(y, tgt).backward()
+            out[fuse] = [y.detach()] + [p.grad.clone() for p in net.parameters()]
+        for a, b in zip(out[False], out[True]):
+            assert _same(a, b)
+        net.zero_grad(set_to_none=True)
+        flat = FlatGradients(net.parameters())
+        flat.begin()
+        torch.nn.functional.cross_entropy(net(x), tgt).backward()
+        flat.finish()
+        for p, g in zip(net.parameters(), out[True][1:]):
+            assert torch.equal(p.grad, g)
+    # a hook on the normalisation module must see the intermediate tensor: the pair is then not folded
+    seen = []
+    h = net.model[1].register_forward_hook(lambda m, i, o: seen.append(i[0].shape))
+    net(x)
+    h.remove()
+    assert seen == [torch.Size([1024, 128])]
+    shape = (8192, 128, 128, 4, 4, False)
+    if ops.plan_flags(*shape)["tc_dw"]:
+        plain = ops.launch_count(0, *shape) + ops.launch_count(1, *shape)
+        folded = ops.launch_count(0, *shape, fused_norm=True) + ops.launch_count(1, *shape, fused_norm=True)
+        assert folded == plain  # forward: same kernels; backward: the gy-statistics pass becomes the normalisation's
