@@ -157,7 +157,7 @@ def tc_gemm_flops(kind, B, I, O, n, S, disc):
     with the tile padding of csrc/tc_gemm.cu (tc_plan)."""
     up = lambda a, b: (a + b - 1) // b * b
     nb = nb_of(n, S, disc)
-    kin = up(nb, 8)
+    kin = up(nb, 8) if kind == "dx" else nb  # Phi / W / dW pack the inputs back to back; dX pads them to 8 columns
     K = I * kin
     bn = 256 if O > 128 else (128 if O > 64 else 64)
     Bp = up(B, 512) if B > 256 else up(B, 32)

@@ -35,11 +35,13 @@ struct TcPlan {
                               // (MN-major A operand), so Phi^T is never built
     int nkc_pad;              // share_phi: k-chunks per batch tile in the Phi storage (nkc rounded up to even)
     size_t phi_bytes;         // share_phi: Phi storage for the whole batch
-    int Kin;                  // dense columns per input: weights per link padded to 8
+    int Kin;                  // dense columns per input in Phi / W / dW: exactly the weights per link (inputs are packed
+                              // back to back, tiles may straddle them)
+    int Kinx;                 // ... in the dX GEMM's N dimension: padded to 8 (its epilogue keeps whole inputs per thread)
     int BN, nNT;              // forward: output tile width and count
     int BNw, nNTw;            // dW: output tile width and count
     int nkc;                  // 64-wide K chunks
-    int BNx, nNTx, noc;       // dX: N tile over the dense columns (multiple of 2*Kin), its count, 64-wide output chunks
+    int BNx, nNTx, noc;       // dX: N tile over the dense columns (multiple of 2*Kinx), its count, 64-wide output chunks
     int nMTw;                 // dW: 128-row M tiles over the dense columns
     int dw_ksplit;            // dW: the batch (K) is split over this many CTAs per tile (partials -> dw_part)
     int fwd_ksplit;           // forward: the dense columns (K) are split likewise when the batch gives few tiles (partials -> y_part)

@@ -48,16 +48,22 @@ __device__ __forceinline__ void fwd_one(float xl, uint32_t sg, const float* slab
     }
 }
 
-template <int N, int OT, bool ROT>
+// IS > 1 (narrow layers: a single tile of <= 16 outputs and too few samples to fill the GPU with one
+// thread per sample): IS consecutive lanes share a sample, take the input groups of a chunk round
+// robin and combine their partial sums with a butterfly at the end -- IS times the threads, 1/IS of
+// the serial chain per thread (the 128 -> 10 classifier head of config 3 ran 40 us on 64 CTAs of 128
+// threads, pure latency).
+template <int N, int OT, bool ROT, int IS = 1>
 __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
     constexpr int OTP = ROT ? OT : OT + 4;
-    const int rot = threadIdx.x & 7;
     constexpr int G = 4;
     const int tid = threadIdx.x;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int q = IS > 1 ? tid % IS : 0;                 // which share of the input groups
+    const int rot = (tid / IS) & 7;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + tid) / IS;
     const int ot = blockIdx.y;
     const int in_floats = p.R * OTP;
     const float* wk_ot = p.wk + (int64_t)ot * p.I * in_floats;
@@ -85,64 +91,84 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
 
     float2 acc[OT / 2];
 #pragma unroll
-    for (int q = 0; q < OT / 2; ++q) acc[q] = make_float2(0.0f, 0.0f);
+    for (int k = 0; k < OT / 2; ++k) acc[k] = make_float2(0.0f, 0.0f);
 
     const float* xlp = p.xl_t + b;
     const uint16_t* sgp = p.seg_t + b;
+    // coordinates of this thread's next input group, loaded one group ahead of use
     float xr[G];
     uint32_t sr[G];
+    auto fetch = [&](int base) {
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-        xr[k] = 0.0f;
-        sr[k] = HOL_SEG_INVALID;
-        if (k < p.I) {
-            xr[k] = __ldg(xlp + (int64_t)k * p.Bp);
-            sr[k] = __ldg(sgp + (int64_t)k * p.Bp);
+        for (int k = 0; k < G; ++k) {
+            const int ii = base + k;
+            xr[k] = 0.0f;
+            sr[k] = HOL_SEG_INVALID;
+            if (ii < p.I) {
+                xr[k] = __ldg(xlp + (int64_t)ii * p.Bp);
+                sr[k] = __ldg(sgp + (int64_t)ii * p.Bp);
+            }
         }
-    }
+    };
+    fetch(q * G);
 
     for (int c = 0; c < nchunks; ++c) {
         const int i0 = c * p.IC;
         const int ni = min(p.IC, p.I - i0);
         mbar_wait(&bars[c % p.nst], (uint32_t)((c / p.nst) & 1));
         const float* slab = slab0 + (size_t)(c % p.nst) * p.stage_floats;
-        for (int g0 = 0; g0 < ni; g0 += G) {
-            // after an input is consumed its registers are refilled with the coordinates of the
-            // same slot of the next group (possibly the head of the next chunk): the loads have a
-            // whole group of compute to land
-            const int nbase = (g0 + G < ni) ? i0 + g0 + G : i0 + ni;
+        for (int g0 = q * G; g0 < ni; g0 += G * IS) {
+            // the registers hold the coordinates of inputs i0 + g0 .. +G-1; after an input is consumed its slot is
+            // refilled with the same slot of this thread's next group (possibly in the next chunk)
+            const int nbase = (g0 + G * IS < ni) ? i0 + g0 + G * IS : i0 + ni + q * G;
 #pragma unroll
             for (int k = 0; k < G; ++k) {
                 if (g0 + k < ni) fwd_one<N, OT, ROT>(xr[k], sr[k], slab + (size_t)(g0 + k) * in_floats, acc, p, rot);
                 const int ii = nbase + k;
                 xr[k] = 0.0f;
                 sr[k] = HOL_SEG_INVALID;
-                if (ii < p.I) {
+                // a group of the next chunk is only this thread's if it starts inside that chunk
+                if (ii < p.I && (IS == 1 || nbase < i0 + ni || q * G < min(p.IC, p.I - (i0 + ni)))) {
                     xr[k] = __ldg(xlp + (int64_t)ii * p.Bp);
                     sr[k] = __ldg(sgp + (int64_t)ii * p.Bp);
                 }
             }
         }
+        if (IS > 1 && q * G >= ni) {
+            // no group of this chunk was this thread's (short last chunk): its registers may hold the head of a
+            // chunk it does not own either -- nothing to do, they are refetched when a group becomes due
+            if (c + 1 < nchunks && q * G < min(p.IC, p.I - (i0 + ni))) fetch(i0 + ni + q * G);
+        }
         __syncthreads();  // everyone is done with this stage before it is refilled
         if (tid == 0 && c + p.nst < nchunks) issue(c + p.nst);
     }
 
-    if (b < p.B) {
+    if (IS > 1) {  // combine the IS partial sums of a sample (adjacent lanes)
+#pragma unroll
+        for (int d = 1; d < IS; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < OT / 2; ++k) {
+                acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, d);
+                acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, d);
+            }
+        }
+    }
+    if (b < p.B && q == 0) {
         float* yrow = p.y + b * p.O + (int64_t)ot * OT;
         const int o0 = ot * OT;
         const bool vec = (p.O & 3) == 0;
 #pragma unroll
-        for (int q = 0; q < OT / 4; ++q) {
-            const int qc = ROT ? ((q + rot) & (OT / 4 - 1)) : q;  // output chunk held in slot q
+        for (int k = 0; k < OT / 4; ++k) {
+            const int qc = ROT ? ((k + rot) & (OT / 4 - 1)) : k;  // output chunk held in slot k
             const int o = o0 + 4 * qc;
             if (vec && o + 3 < p.O) {
                 *reinterpret_cast<float4*>(yrow + 4 * qc) =
-                    make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+                    make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
             } else {
-                if (o + 0 < p.O) yrow[4 * qc + 0] = acc[2 * q].x;
-                if (o + 1 < p.O) yrow[4 * qc + 1] = acc[2 * q].y;
-                if (o + 2 < p.O) yrow[4 * qc + 2] = acc[2 * q + 1].x;
-                if (o + 3 < p.O) yrow[4 * qc + 3] = acc[2 * q + 1].y;
+                if (o + 0 < p.O) yrow[4 * qc + 0] = acc[2 * k].x;
+                if (o + 1 < p.O) yrow[4 * qc + 1] = acc[2 * k].y;
+                if (o + 2 < p.O) yrow[4 * qc + 2] = acc[2 * k + 1].x;
+                if (o + 3 < p.O) yrow[4 * qc + 3] = acc[2 * k + 1].y;
             }
         }
     }
@@ -187,6 +213,18 @@ static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
     } else {
         BT = 512;
         while (BT > 128 && (s.Bp / BT) * s.nOT < 2 * 148) BT >>= 1;
+    }
+    if constexpr (OT <= 16 && !ROT) {
+        // a single narrow tile and at most one 128-sample CTA per SM: four lanes per sample
+        if (s.nOT == 1 && BT == 128 && s.Bp % 128 == 0 && (s.Bp / BT) <= 148 && s.I >= 16) {
+            auto kern4 = pw_fwd_kernel<N, OT, ROT, 4>;
+            static std::atomic<uint64_t> attr_done4{0};
+            cudaError_t e4 = hol_ensure_max_smem(kern4, attr_done4);
+            if (e4 != cudaSuccess) return (int)e4;
+            dim3 grid4((unsigned)(s.Bp / BT), 1u);
+            kern4<<<grid4, BT * 4, smem, st>>>(p);
+            return (int)cudaGetLastError();
+        }
     }
     auto kern = pw_fwd_kernel<N, OT, ROT>;
     static std::atomic<uint64_t> attr_done{0};

@@ -22,15 +22,23 @@ template <int KIND>
 __global__ void __launch_bounds__(256) pw_row_norm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                                               const float4* __restrict__ stats, float* __restrict__ dx,
                                                               int64_t B, int W, unsigned* absmax) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= B) return;
-    float amax = norm_row_backward<KIND>(gy + row * W, x + row * W, stats[row], dx + row * W, W, lane);
+    __shared__ unsigned s_max[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float amax = 0.0f;
+    // a few rows per warp: the grid stays within ~4 CTAs per SM, so the statistic costs a few hundred atomics
+    for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < B; row += (int64_t)gridDim.x * 8)
+        amax = fmaxf(amax, norm_row_backward<KIND>(gy + row * W, x + row * W, stats[row], dx + row * W, W, lane));
     if (absmax) {
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
-        const unsigned bits = __float_as_uint(amax);
-        if (lane == 0 && amax > 0.0f && bits > *reinterpret_cast<volatile unsigned*>(absmax)) atomicMax(absmax, bits);
+        if (lane == 0) s_max[wid] = amax > 0.0f ? __float_as_uint(amax) : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned bits = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bits = max(bits, s_max[k]);
+            if (bits > *reinterpret_cast<volatile unsigned*>(absmax)) atomicMax(absmax, bits);
+        }
     }
 }
 
@@ -47,7 +55,9 @@ int launch_row_norm_forward(int kind, const float* x, float* y, float* stats, in
 int launch_row_norm_backward(int kind, const float* gy, const float* x, const float* stats, float* dx, int64_t B, int W,
                              unsigned* absmax, cudaStream_t st) {
     if (B == 0) return HOL_OK;
-    const unsigned grid = (unsigned)((B + 7) / 8);
+    int64_t blocks = (B + 7) / 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const unsigned grid = (unsigned)blocks;
     const float4* s4 = reinterpret_cast<const float4*>(stats);
     if (kind == HOL_NORM_MAX_ABS) pw_row_norm_bwd_kernel<HOL_NORM_MAX_ABS><<<grid, 256, 0, st>>>(gy, x, s4, dx, B, W, absmax);
     if (kind == HOL_NORM_MAX_CENTER) pw_row_norm_bwd_kernel<HOL_NORM_MAX_CENTER><<<grid, 256, 0, st>>>(gy, x, s4, dx, B, W, absmax);

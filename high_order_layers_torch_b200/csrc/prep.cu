@@ -15,6 +15,8 @@ struct PrepConst {
     float length, half, Sf, half_per, two_per, per;
     float xl_limit;    // tensor-core plans: |xl| above this is flagged HOL_SEG_OUTLIER (INFINITY otherwise)
     float inv_length;  // 1 / length when that is exact (length a power of two: 2.0 for every FC layer), else 0
+    float inv_de;      // 1 / (eta(s+1) - eta(s)) when every segment has the same power-of-two width (S a power of
+                       // two: eta is exact then), else 0: dividing by a power of two is exactly a multiplication
     int S, periodic;
 };
 
@@ -31,6 +33,25 @@ static PrepConst make_prep_const(const PwShape& s) {
         int e;
         const float m = frexpf(s.length, &e);  // a power of two divides exactly like its reciprocal multiplies
         c.inv_length = (m == 0.5f && e > -100 && e < 100) ? 1.0f / s.length : 0.0f;
+    }
+    c.inv_de = 0.0f;
+    {
+        // eta(k) with the reference's three separately rounded fp32 operations (volatile: no host-side contraction)
+        auto eta_host = [&](int k) {
+            volatile float q = (float)k / (float)s.S;
+            volatile float m = q * 2.0f;
+            volatile float e = m - 1.0f;
+            return (float)e;
+        };
+        volatile float de0 = eta_host(1) - eta_host(0);
+        bool same = true;
+        for (int k = 1; k < s.S && same; ++k) {
+            volatile float de = eta_host(k + 1) - eta_host(k);
+            same = de == de0;
+        }
+        int e;
+        const float m = frexpf(de0, &e);
+        if (same && m == 0.5f && e > -100 && e < 100) c.inv_de = 1.0f / de0;
     }
     c.S = s.S;
     c.periodic = s.periodic;
@@ -67,9 +88,14 @@ __device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& x
     if (c.periodic) xv = fold_periodic(xv, c, flags);
     int s = segment_of(xv, c);
     float e0 = eta ? eta[s] : eta_of(s, c);
-    float e1 = eta ? eta[s + 1] : eta_of(s + 1, c);
-    float de = __fsub_rn(e1, e0);
-    xl = __fsub_rn(__fmul_rn(c.length, __fdiv_rn(__fsub_rn(xv, e0), de)), c.half);
+    float q;
+    if (c.inv_de != 0.0f) {
+        q = __fmul_rn(__fsub_rn(xv, e0), c.inv_de);
+    } else {
+        float e1 = eta ? eta[s + 1] : eta_of(s + 1, c);
+        q = __fdiv_rn(__fsub_rn(xv, e0), __fsub_rn(e1, e0));
+    }
+    xl = __fsub_rn(__fmul_rn(c.length, q), c.half);
     if (fabsf(xl) > c.xl_limit) flags |= HOL_SEG_OUTLIER;  // NaN is not an outlier: it propagates like in the reference
     sg = (uint32_t)s | flags;
 }
@@ -78,19 +104,28 @@ __device__ __forceinline__ void prep_elem(float xv, const PrepConst& c, float& x
 // largest |xl| among the elements that stay in the GEMM, and how many were flagged as outliers.
 // stats == nullptr on layers without a tensor-core pass.
 __device__ __forceinline__ void prep_stats(float amax, unsigned nout, unsigned* stats) {
-    if (!stats) return;
+    if (!stats) return;  // uniform over the grid
+    __shared__ unsigned s_max[8], s_out[8];  // CTAs of 256 threads; every thread of the CTA gets here
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
         nout += __shfl_xor_sync(0xffffffffu, nout, d);
     }
-    if ((threadIdx.x & 31) == 0) {
-        // Every warp of the grid would otherwise hit ONE address (half a million atomics at config 2:
-        // 0.5 ms of L2 serialisation).  The running maximum settles after the first few CTAs, so look
-        // before touching it: an atomic is only issued by a warp that actually raises the value.
-        const unsigned bits = __float_as_uint(amax);
-        if (amax > 0.0f && bits > *reinterpret_cast<volatile unsigned*>(stats + 0)) atomicMax(stats + 0, bits);  // TcScalars::max_xl
-        if (nout) atomicAdd(stats + 3, nout);                                                                      // TcScalars::n_outliers
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) {
+        s_max[tid >> 5] = amax > 0.0f ? __float_as_uint(amax) : 0u;
+        s_out[tid >> 5] = nout;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // One atomic per CTA, and only from a CTA that raises the value: every warp of the grid hitting ONE
+        // address was 0.5 ms of L2 serialisation at config 2 (half a million atomics), and still ~8 us on a
+        // single-wave grid of a small layer, where looking first does not help (all look at once).
+        unsigned bits = 0u, n = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bits = max(bits, s_max[k]), n += s_out[k];
+        if (bits > *reinterpret_cast<volatile unsigned*>(stats + 0)) atomicMax(stats + 0, bits);  // TcScalars::max_xl
+        if (n) atomicAdd(stats + 3, n);                                                          // TcScalars::n_outliers
     }
 }
 __device__ __forceinline__ void prep_track(float xl, uint32_t sg, float& amax, unsigned& nout) {
@@ -113,41 +148,63 @@ __global__ void __launch_bounds__(256) pw_segment_index_kernel(const float* __re
     }
 }
 
-// x[B, I] -> xl_t[I][Bp], seg_t[I][Bp] (transposed so that the contraction kernels, whose
-// lanes are samples, read them coalesced).  32x32 tile through shared memory.
+// x[B, I] -> xl_t[I][Bp], seg_t[I][Bp] (transposed so that the contraction kernels, whose lanes are
+// samples, read them coalesced).  64 x 64 tile through shared memory: 16 independent loads per thread, 256-byte
+// bursts both ways (the first version moved 32 x 32 tiles with 4 elements per thread and ran at 1.5 TB/s).
+#define PREP_T 64
 __global__ void __launch_bounds__(256) pw_prep_fc_kernel(const float* __restrict__ x, float* __restrict__ xl_t,
                                                          uint16_t* __restrict__ seg_t, int64_t B, int64_t Bp, int I,
                                                          PrepConst c, unsigned* stats) {
-    __shared__ float t_xl[32][33];
-    __shared__ uint16_t t_sg[32][34];
+    __shared__ float t_xl[PREP_T][PREP_T + 1];                     // [input][sample]
+    __shared__ __align__(4) uint16_t t_sg[PREP_T][PREP_T + 2];
     extern __shared__ float eta_tab[];  // [S + 1]
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int k = ty * 32 + tx; k <= c.S; k += 256) eta_tab[k] = eta_of(k, c);
-    __syncthreads();
-    const int64_t b0 = (int64_t)blockIdx.x * 32;
-    const int i0 = blockIdx.y * 32;
-    float amax = 0.0f;
-    unsigned nout = 0;
+    const int tid = threadIdx.x;
+    for (int k = tid; k <= c.S; k += 256) eta_tab[k] = eta_of(k, c);
+    const int64_t b0 = (int64_t)blockIdx.x * PREP_T;
+    const int i0 = blockIdx.y * PREP_T;
+    {
+        const int ci = tid & (PREP_T - 1), rb = tid >> 6;  // 4 sample rows at a time, 64 consecutive inputs each
+        const int i = i0 + ci;
+        float xv[PREP_T / 4];
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t b = b0 + r;
-        const int i = i0 + tx;
-        float xl = 0.0f;
-        uint32_t sg = HOL_SEG_INVALID;
-        if (i < I && b < B) prep_elem(x[b * I + i], c, xl, sg, eta_tab);
-        prep_track(xl, sg, amax, nout);
-        t_xl[tx][r] = xl;
-        t_sg[tx][r] = (uint16_t)sg;
+        for (int r = 0; r < PREP_T / 4; ++r) {
+            const int64_t b = b0 + rb + 4 * r;
+            xv[r] = (i < I && b < B) ? x[b * I + i] : 0.0f;
+        }
+        __syncthreads();  // eta table
+        float amax = 0.0f;
+        unsigned nout = 0;
+#pragma unroll
+        for (int r = 0; r < PREP_T / 4; ++r) {
+            const int64_t b = b0 + rb + 4 * r;
+            float xl = 0.0f;
+            uint32_t sg = HOL_SEG_INVALID;
+            if (i < I && b < B) prep_elem(xv[r], c, xl, sg, eta_tab);
+            prep_track(xl, sg, amax, nout);
+            t_xl[ci][rb + 4 * r] = xl;
+            t_sg[ci][rb + 4 * r] = (uint16_t)sg;
+        }
+        prep_stats(amax, nout, stats);  // (contains a __syncthreads when stats != nullptr)
     }
-    prep_stats(amax, nout, stats);
     __syncthreads();
+    {
+        const int cb = tid & (PREP_T - 1), ri = tid >> 6;
+        if (b0 + cb < Bp) {
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int i = i0 + r;
-        const int64_t b = b0 + tx;
-        if (i < I) {
-            xl_t[(int64_t)i * Bp + b] = t_xl[r][tx];
-            seg_t[(int64_t)i * Bp + b] = t_sg[r][tx];
+            for (int r = 0; r < PREP_T / 4; ++r) {
+                const int il = ri + 4 * r;
+                if (i0 + il < I) xl_t[(int64_t)(i0 + il) * Bp + b0 + cb] = t_xl[il][cb];
+            }
+        }
+        const int pb = tid & 31, rj = tid >> 5;  // two samples (one 32-bit word) per thread
+        if (b0 + 2 * pb < Bp) {                  // Bp is even: the pair is inside or outside as a whole
+#pragma unroll
+            for (int r = 0; r < PREP_T / 8; ++r) {
+                const int il = rj + 8 * r;
+                if (i0 + il < I)
+                    *reinterpret_cast<uint32_t*>(seg_t + (int64_t)(i0 + il) * Bp + b0 + 2 * pb) =
+                        *reinterpret_cast<const uint32_t*>(&t_sg[il][2 * pb]);
+            }
         }
     }
 }
@@ -441,8 +498,8 @@ int launch_segment_index(const float* x, int64_t* seg, int64_t count, const PwSh
 }
 
 int launch_prep_fc(const float* x, const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
-    dim3 grid((unsigned)(s.Bp / 32), (unsigned)((s.I + 31) / 32));
-    pw_prep_fc_kernel<<<grid, dim3(32, 8), (size_t)(s.S + 1) * sizeof(float), st>>>(
+    dim3 grid((unsigned)((s.Bp + PREP_T - 1) / PREP_T), (unsigned)((s.I + PREP_T - 1) / PREP_T));
+    pw_prep_fc_kernel<<<grid, 256, (size_t)(s.S + 1) * sizeof(float), st>>>(
         x, ws.xl_t, ws.seg_t, s.B, s.Bp, s.I, make_prep_const(s), (unsigned*)ws.tc_scalars);
     return (int)cudaGetLastError();
 }

@@ -34,22 +34,36 @@ __global__ void __launch_bounds__(256) pw_tc_expand_kernel(const float* __restri
     for (int q = 0; q < 8; ++q) mine4[q] = make_uint4(0u, 0u, 0u, 0u);
     const int c0 = kc * TC_BK + half * 32;  // first dense column of this thread's strip
     if (b < Bp) {
+        // every input with a column in this strip (the first and the last may belong to the neighbours as well);
+        // the loads of four inputs are issued together: the kernel is otherwise bound by their latency
         const int i_lo = c0 / Kin, i_hi = min(I - 1, (c0 + 31) / Kin);
-        for (int i = i_lo; i <= i_hi; ++i) {
-            const uint32_t sg = seg_t[(int64_t)i * Bp + b];
-            if (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) continue;
-            float phi[N];
-            lagrange_basis<N>(xl_t[(int64_t)i * Bp + b], tab, phi);
-            const int col = i * Kin + (int)(sg & HOL_SEG_MASK) * stride - c0;  // strip column of phi_0
+        for (int i4 = i_lo; i4 <= i_hi; i4 += 4) {
+            uint32_t sg4[4];
+            float xl4[4];
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const float a = phi[j] * scale;
-                const __half ha = __float2half_rn(a);
-                __half la = __float2half_rn(a - __half2float(ha));
-                // |a| < 2^-25 rounds to hi = lo = 0: keep the sign and the smallest subnormal (split_store8)
-                if (fabsf(a) <= 2.9802323e-8f && a != 0.0f) la = __ushort_as_half((unsigned short)(a > 0.0f ? 0x0001 : 0x8001));
-                if ((unsigned)(col + j) < 32u)
-                    mine[col + j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(la) << 16);
+            for (int u = 0; u < 4; ++u) {
+                const int64_t at = (int64_t)min(i4 + u, i_hi) * Bp + b;
+                sg4[u] = seg_t[at];
+                xl4[u] = xl_t[at];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i4 + u;
+                const uint32_t sg = sg4[u];
+                if (i > i_hi || (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER))) continue;
+                float phi[N];
+                lagrange_basis<N>(xl4[u], tab, phi);
+                const int col = i * Kin + (int)(sg & HOL_SEG_MASK) * stride - c0;  // strip column of phi_0
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const float a = phi[j] * scale;
+                    const __half ha = __float2half_rn(a);
+                    __half la = __float2half_rn(a - __half2float(ha));
+                    // |a| < 2^-25 rounds to hi = lo = 0: keep the sign and the smallest subnormal (split_store8)
+                    if (fabsf(a) <= 2.9802323e-8f && a != 0.0f) la = __ushort_as_half((unsigned short)(a > 0.0f ? 0x0001 : 0x8001));
+                    if ((unsigned)(col + j) < 32u)
+                        mine[col + j] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(la) << 16);
+                }
             }
         }
     }
@@ -130,12 +144,12 @@ __global__ void __launch_bounds__(256) pw_tc_pack_w_kernel(const float* __restri
         const int row = idx % BN, kgl = idx / BN;
         const int o = nt * BN + row;
         const int k0 = kc * TC_BK + kgl * 8;
-        const int i = k0 / Kin, v0 = k0 % Kin;
+        int i = k0 / Kin, col = k0 % Kin;  // the 8 columns may run over into the next input(s)
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int col = v0 + e;
             v[e] = (o < O && i < I && col < nb) ? w[((int64_t)o * I + i) * nb + col] : 0.0f;
+            if (++col == Kin) col = 0, ++i;
         }
         uint4* hi = reinterpret_cast<uint4*>(base + kgl * (BN * 16) + row * 16);
         uint4* lo = reinterpret_cast<uint4*>(base + img + kgl * (BN * 16) + row * 16);

@@ -83,24 +83,28 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     memset(&t, 0, sizeof(t));
     const uint32_t ovr = hol_plan_overrides();
     if (ovr & HOL_OVR_DISABLE_TC) return false;
-    t.Kin = (s.nb + 7) / 8 * 8;
-    if (s.O < 32 || s.I * (int64_t)t.Kin < 256) return false;  // too narrow to be worth a tile
+    // Dense columns per input.  Phi, the forward's W tiles and dW pack the inputs back to back (k = i*nb + v):
+    // padding every input to a multiple of 8 columns would add MMA work and Phi bytes for nothing (nb = 13 at
+    // config 3: 16 -> 13 is 19 % of both).  Only dX, whose epilogue wants whole inputs per thread, pads.
+    t.Kin = s.nb;
+    t.Kinx = (s.nb + 7) / 8 * 8;
+    if (s.O < 32 || s.I * (int64_t)t.Kinx < 256) return false;  // too narrow to be worth a tile
     // The dense form costs 3*Kin tensor MACs per n useful fp32 FMAs, so its time grows with Kin (i.e.
     // with the segment count) while the gather kernels' does not.  Cross-over points measured on
     // B200 (c5 sweep, profiles/r1c_sweep_c5.jsonl): forward/dX gather run at ~7-16 TFLOP/s useful, the
     // bucketed dW gather at ~25-40, the tensor path at ~1.3 PFLOP/s executed.
-    t.fwd = t.Kin <= 40 * s.n;
-    t.dx = t.fwd && t.Kin <= 128 && s.n > 1;  // the dX epilogue keeps whole inputs per thread (Kin <= 128)
-    t.dw = t.Kin <= 44 + 7 * s.n;
+    t.fwd = t.Kinx <= 40 * s.n;
+    t.dx = t.fwd && t.Kinx <= 128 && s.n > 1;  // the dX epilogue keeps whole inputs per thread (Kinx <= 128)
+    t.dw = t.Kinx <= 44 + 7 * s.n;
     if (!t.fwd && !t.dw) return false;
     const int64_t K = (int64_t)s.I * t.Kin;
     const int64_t mtiles_all = (s.Bp + TC_BM - 1) / TC_BM;
     t.nkc = (int)((K + TC_BK - 1) / TC_BK);
     t.BN = tc_bn_for(s.O, mtiles_all, true);
     t.nNT = (s.O + t.BN - 1) / t.BN;
-    // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kin (and of 16), <= 256
-    t.BNx = t.Kin <= 128 ? (256 / (2 * t.Kin)) * (2 * t.Kin) : 256;
-    t.nNTx = (int)((K + t.BNx - 1) / t.BNx);
+    // dX: N tile = whole inputs per epilogue half: a multiple of 2*Kinx (and of 16), <= 256
+    t.BNx = t.Kinx <= 128 ? (256 / (2 * t.Kinx)) * (2 * t.Kinx) : 256;
+    t.nNTx = (int)(((int64_t)s.I * t.Kinx + t.BNx - 1) / t.BNx);
     t.noc = (s.O + TC_BK - 1) / TC_BK;
     // dW: M tiles over the dense columns; when they are too few to fill the GPU the batch (K) is split
     t.nMTw = (int)((K + TC_BM - 1) / TC_BM);
@@ -137,7 +141,7 @@ bool tc_plan(const PwShape& s, TcPlan& t) {
     // the SMs (config 3: 64 tiles of 196 k-chunks) the k-chunks are split over 2-4 work items per tile; every
     // CTA is bound by its own shared-memory / L2 port, so the extra CTAs add bandwidth, not just issue slots
     t.fwd_ksplit = 1;
-    if (t.fwd && rows >= s.Bp) t.fwd_ksplit = pick_ksplit(mtiles_all, t.nNT, t.nkc, 16, 4);
+    if (t.fwd && rows >= s.Bp) t.fwd_ksplit = pick_ksplit(mtiles_all, t.nNT, t.nkc, 12, 4);
     const size_t mtiles = (size_t)(rows / TC_BM);
     const size_t bchunks = (size_t)((rows + TC_BK - 1) / TC_BK);
     size_t a = t.share_phi ? 0 : mtiles * t.nkc * 2 * TC_A_IMG;                    // Phi
@@ -471,7 +475,7 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         if (rc != HOL_OK) return rc;
     }
     dim3 pgrid((unsigned)t.nNTx, (unsigned)t.noc, (unsigned)((t.BNx * 8 + 255) / 256));
-    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, ws.tc_wmean, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kin, t.noc,
+    pw_tc_pack_wt_kernel<<<pgrid, 256, 0, st>>>(w, ws.tc_wmean, (unsigned char*)ws.tc_b, sc, s.I, s.O, s.nb, t.Kinx, t.noc,
                                                 t.BNx);
     rc = (int)cudaGetLastError();
     if (rc != HOL_OK) return rc;
@@ -491,6 +495,7 @@ int launch_backward_dx_tc(const PwShape& s, const PwWorkspace& ws, const TcPlan&
         p.n_valid = 0;
         p.ld = 0;
         p.nkc = t.noc;
+        p.Kin = t.Kinx;
         p.transposed = transposed;
 #define GEMM_DX(NN) launch_gemm<EPI_DX, NN, A_TILES>(p, rows / TC_BM, t.nNTx, 1, (TcProf*)ws.prof, st)
         DISPATCH_N(s.n, GEMM_DX)
