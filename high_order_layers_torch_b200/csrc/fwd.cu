@@ -70,8 +70,7 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
     const int nchunks = (p.I + p.IC - 1) / p.IC;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int k = 0; k < p.nst; ++k) mbar_init(&bars[k], 1);  // nst <= 16: the barriers own the first 128 bytes
         mbar_fence_init();
     }
     __syncthreads();
@@ -84,10 +83,8 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
         mbar_expect_tx(bar, bytes);
         bulk_g2s(slab0 + (size_t)stg * p.stage_floats, wk_ot + (int64_t)i0 * in_floats, bytes, bar);
     };
-    if (tid == 0) {
-        issue(0);
-        if (p.nst > 1 && nchunks > 1) issue(1);
-    }
+    if (tid == 0)
+        for (int c = 0; c < p.nst && c < nchunks; ++c) issue(c);
 
     float2 acc[OT / 2];
 #pragma unroll
@@ -215,14 +212,27 @@ static int launch_fwd_t(const PwShape& s, const PwWorkspace& ws, float* y, cudaS
         while (BT > 128 && (s.Bp / BT) * s.nOT < 2 * 148) BT >>= 1;
     }
     if constexpr (OT <= 16 && !ROT) {
-        // a single narrow tile and at most one 128-sample CTA per SM: four lanes per sample
+        // A single narrow tile and at most one 128-sample CTA per SM (the 128 -> 10 classifier head of config 3 at
+        // batch 8192: 64 CTAs).  The work is tiny, so what counts is (a) using every SM -- each (sample, input)
+        // pair reads n*OTP words of shared memory, 268 MB in all, which on 64 SMs alone is 17 us -- and (b) not
+        // paying one L2 round trip per chunk of weights: 32-sample CTAs with four lanes per sample, and every
+        // chunk of the layer's weights (they fit shared memory) requested up front.
         if (s.nOT == 1 && BT == 128 && s.Bp % 128 == 0 && (s.Bp / BT) <= 148 && s.I >= 16) {
             auto kern4 = pw_fwd_kernel<N, OT, ROT, 4>;
             static std::atomic<uint64_t> attr_done4{0};
             cudaError_t e4 = hol_ensure_max_smem(kern4, attr_done4);
             if (e4 != cudaSuccess) return (int)e4;
-            dim3 grid4((unsigned)(s.Bp / BT), 1u);
-            kern4<<<grid4, BT * 4, smem, st>>>(p);
+            int bt4 = 128;
+            while (bt4 > 32 && s.Bp / bt4 < 2 * 148) bt4 >>= 1;
+            const int nchunks = (s.I + IC - 1) / IC;
+            int nst4 = (int)((HOL_SMEM_BUDGET - 128) / ((size_t)p.stage_floats * 4));
+            if (nst4 > nchunks) nst4 = nchunks;
+            if (nst4 > 16) nst4 = 16;
+            if (nst4 < nst) nst4 = nst;
+            p.nst = nst4;
+            const size_t smem4 = 128 + (size_t)nst4 * p.stage_floats * 4;
+            dim3 grid4((unsigned)(s.Bp / bt4), 1u);
+            kern4<<<grid4, bt4 * 4, smem4, st>>>(p);
             return (int)cudaGetLastError();
         }
     }
