@@ -384,13 +384,15 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end through the public module API: pinned host inputs -> H2D -> fwd+bwd -> loss D2H
-    # Every step copies ITS inputs from pinned host memory and reads ITS loss back; the copy of step
-    # k+1 runs on a second stream into the other of two device buffers while step k computes (the
-    # usual input prefetch), the first copy and every read-back are exposed.
+    # Every step copies ITS inputs from pinned host memory and reads ITS loss back.  Two device input
+    # buffers and two pinned loss words: the copy of step k+1 runs on a second stream while step k
+    # computes (the usual input prefetch), and the host reads the loss of step k-1 while step k runs
+    # (the usual one-step-lagged logging read), so the host never idles the GPU between steps.  The
+    # first copy and the last read-back are exposed.
     e2e_steps, e2e_ms = 0, 0.0
     if with_e2e:
-        e2e_steps = max(1, min(steps, 10))
-        host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        e2e_steps = max(1, min(steps, 20))
+        host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         main_stream = torch.cuda.current_stream()
         copy_stream = torch.cuda.Stream()
         dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in wl["host"].items()}
@@ -420,6 +422,8 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         def run_e2e(nsteps):
             ready = [torch.cuda.Event(), torch.cuda.Event()]
             consumed = [None, None]
+            landed = [None, None]
+            losses = []
 
             def prefetch(slot):
                 with torch.cuda.stream(copy_stream):
@@ -430,7 +434,6 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                     ready[slot].record(copy_stream)
 
             prefetch(0)
-            last = None
             for k in range(nsteps):
                 slot = k & 1
                 if k + 1 < nsteps:
@@ -444,10 +447,17 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                 ev = torch.cuda.Event()
                 ev.record(main_stream)
                 consumed[slot] = ev
-                host_loss.copy_(loss.detach(), non_blocking=True)
-                main_stream.synchronize()
-                last = float(host_loss)
-            return last
+                host_loss[slot].copy_(loss.detach(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main_stream)
+                landed[slot] = ev
+                if k >= 1:  # the previous step's loss, read while this step runs
+                    landed[slot ^ 1].synchronize()
+                    losses.append(float(host_loss[slot ^ 1]))
+            landed[(nsteps - 1) & 1].synchronize()
+            losses.append(float(host_loss[(nsteps - 1) & 1]))
+            assert len(losses) == nsteps and all(v == v for v in losses), "e2e: a step's loss was not read back"
+            return losses[-1]
 
         run_e2e(2)
         barrier()
@@ -478,7 +488,8 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         res["e2e"] = {"value": wl["samples"] * world / (e2e_ms / e2e_steps / 1e3), "unit": "samples/s",
                       "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
                       "note": "module API; pinned-host inputs copied H2D and the loss read back D2H every step; "
-                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch)"
+                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch) and the host reads the "
+                              "loss of step k-1 while step k runs (one-step-lagged read, every step's loss is read)"
                               + ("; the step is replayed from a CUDA graph captured per input buffer" if graphed else "")}
     peaks = load_peaks()
     res["step_algorithmic"] = {

@@ -148,8 +148,10 @@ int reset_scalars(const PwShape& s, const PwWorkspace& ws, cudaStream_t st) {
 // dW runs first: under data parallelism its all-reduce can then start while dX is still computing.
 int backward_common(const PwShape& s, const PwWorkspace& ws, const float* gy, const float* w, float* dx,
                     int dx_transposed, float* dw, bool packed, bool prepared, bool gy_stats_valid, cudaStream_t st) {
-    const bool tc_dx = dx && s.n > 1 && s.tc.dx, tc_dw = dw && s.tc.dw;
-    if ((tc_dx || tc_dw) && !gy_stats_valid) HOL_TRY(launch_tc_gy_absmax(s, ws, gy, st));
+    // max|gy| is taken whenever the plan has a tensor-core backward pass at all, not only when THIS call runs
+    // one: a backward split into a dW call and a dX call (either order) hands HOL_GY_STATS_VALID to the second.
+    const bool tc_any = (s.n > 1 && s.tc.dx) || s.tc.dw;
+    if (tc_any && (dx || dw) && !gy_stats_valid) HOL_TRY(launch_tc_gy_absmax(s, ws, gy, st));
     if (dw) {
         if (s.tc.dw) {
             HOL_TRY(launch_backward_dw_tc(s, ws, s.tc, gy, dw, prepared && s.tc.fwd, st));
@@ -473,8 +475,8 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     if (kind == 0) return 1 + (s.tc.fwd ? tc_launch_count(s, s.tc, 0, false) : 2 + (fused_norm ? 1 : 0));
     int c = prepared ? 0 : 1;  // prep
     if (fused_norm) c += 1;    // normalisation backward (takes max|gy| along the way: HOL_GY_STATS_VALID)
-    const bool tc_dx = want_dx && n > 1 && s.tc.dx, tc_dw = want_dw && s.tc.dw;
-    if ((tc_dx || tc_dw) && !(flags & HOL_GY_STATS_VALID)) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
+    const bool tc_any = (n > 1 && s.tc.dx) || s.tc.dw;
+    if (tc_any && (want_dx || want_dw) && !(flags & HOL_GY_STATS_VALID)) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
     if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2);
     if (want_dw)
         c += s.tc.dw ? tc_launch_count(s, s.tc, 2, prepared)

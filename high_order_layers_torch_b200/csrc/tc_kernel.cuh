@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
     uint64_t* tmem_full = full + 16;                         // [2]
     uint64_t* tmem_empty = full + 18;                        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
+    // EPI_DX: d xl / d x per segment (the reference's length / (eta(s+1) - eta(s)), same fp32 op order), once
+    // per CTA: three IEEE divisions per (sample, input) in the epilogue's dependent chain otherwise
+    float* chain_tab = reinterpret_cast<float*>(smem_raw + 256);  // [nseg <= 128]
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,6 +223,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
         }
         mbar_fence_init();
+    }
+    if (EPI == EPI_DX && threadIdx.x >= 128 && (int)threadIdx.x - 128 < p.nseg && threadIdx.x < 128 + 160) {
+        const int s = (int)threadIdx.x - 128;
+        const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
+        const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
+        chain_tab[s] = __fdiv_rn(p.length, __fsub_rn(e1, e0));
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -387,24 +396,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
             float racc[TC_MAXHALF];
 #pragma unroll
             for (int e = 0; e < TC_MAXHALF; ++e) racc[e] = 0.0f;
-            // EPI_DX: fetch the coordinates of the first inputs of this thread's columns now, so the
+            // EPI_DX: fetch the coordinates of the first two inputs of this thread's columns now, so the
             // gather after the last drain does not wait on global memory while the MMA warp needs
             // the next drains
-            constexpr int PF = 4;
-            uint32_t pf_sg[PF];
-            float pf_xl[PF];
+            uint32_t cur_sg[2] = {HOL_SEG_INVALID, HOL_SEG_INVALID};
+            float cur_xl[2] = {0.0f, 0.0f};
             if (EPI == EPI_DX) {
                 const int64_t b = p.row0 + mt * TC_BM + rl;
                 const int i0 = (nt * BN + h * HALF) / p.Kin;
 #pragma unroll
-                for (int ii = 0; ii < PF; ++ii) {
-                    pf_sg[ii] = HOL_SEG_INVALID;
-                    pf_xl[ii] = 0.0f;
-                    if (tile_valid && b < p.Bp && i0 + ii < p.I) {
-                        pf_sg[ii] = p.seg_t[(int64_t)(i0 + ii) * p.Bp + b];
-                        pf_xl[ii] = p.xl_t[(int64_t)(i0 + ii) * p.Bp + b];
+                for (int u = 0; u < 2; ++u)
+                    if (tile_valid && b < p.Bp && i0 + u < p.I && (u + 1) * p.Kin <= HALF) {
+                        cur_sg[u] = p.seg_t[(int64_t)(i0 + u) * p.Bp + b];
+                        cur_xl[u] = p.xl_t[(int64_t)(i0 + u) * p.Bp + b];
                     }
-                }
             }
             for (int gg = 0; gg < ngroups; ++gg, ++g) {
                 const int acc = g & 1;
@@ -487,41 +492,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_tc_gemm_kernel(const __grid_
                 constexpr int NB = N > 0 ? N : 1;
                 const int64_t b = p.row0 + row;
                 const int ninp = HALF / p.Kin;
+                const int ibase = colbase / p.Kin;
                 if (b < p.Bp) {
+                    // Two inputs per trip, the coordinates of the next two requested before this pair is worked
+                    // on: with one input at a time the trip is one dependent chain (global load -> basis
+                    // derivative -> pick -> dot) and eight warps per SM cannot hide it -- at K = O = 128 the
+                    // epilogue, not the MMAs, set the time of the launch (config 3 layer 2: 27 k cycles per tile).
 #pragma unroll 1
-                    for (int ii = 0; ii < ninp; ++ii) {
-                        const int i = colbase / p.Kin + ii;
-                        if (i >= p.I) break;
-                        const int64_t idx = (int64_t)i * p.Bp + b;
-                        uint32_t sg;
-                        float xlv;
-                        if (ii < PF) {
-                            sg = pf_sg[0], xlv = pf_xl[0];
+                    for (int ii = 0; ii < ninp; ii += 2) {
+                        if (ibase + ii >= p.I) break;
+                        uint32_t nxt_sg[2] = {HOL_SEG_INVALID, HOL_SEG_INVALID};
+                        float nxt_xl[2] = {0.0f, 0.0f};
 #pragma unroll
-                            for (int qq = 1; qq < PF; ++qq)
-                                if (ii == qq) sg = pf_sg[qq], xlv = pf_xl[qq];
-                        } else {
-                            sg = p.seg_t[idx];
-                            xlv = p.xl_t[idx];
+                        for (int u = 0; u < 2; ++u) {
+                            const int in = ii + 2 + u;
+                            if (in < ninp && ibase + in < p.I) {
+                                nxt_sg[u] = p.seg_t[(int64_t)(ibase + in) * p.Bp + b];
+                                nxt_xl[u] = p.xl_t[(int64_t)(ibase + in) * p.Bp + b];
+                            }
                         }
-                        const int s = (int)(sg & HOL_SEG_MASK);
-                        float dphi[NB];
-                        lagrange_basis_derivative<NB>(xlv, p.tab, dphi);
-                        float tv[NB];
-                        dx_pick<NB>(racc, ii * p.Kin + s * p.stride, tv);
-                        float sum = 0.0f;
+                        float dphi[2][NB], tv[2][NB];
 #pragma unroll
-                        for (int j = 0; j < NB; ++j) sum = fmaf(dphi[j], tv[j], sum);
-                        const float e0 = __fsub_rn(__fmul_rn(__fdiv_rn((float)s, p.Sf), 2.0f), 1.0f);
-                        const float e1 = __fsub_rn(__fmul_rn(__fdiv_rn((float)(s + 1), p.Sf), 2.0f), 1.0f);
-                        float chain = __fdiv_rn(p.length, __fsub_rn(e1, e0));
-                        if (sg & HOL_SEG_MIRROR) chain = -chain;
-                        // outliers are written by the fp32 fix-up kernel after this launch
-                        const float outv = (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) ? 0.0f : sum * inv * chain;
-                        if (p.transposed)
-                            p.out[idx] = outv;
-                        else if (row < p.rows_valid)
-                            p.out[b * p.I + i] = outv;
+                        for (int u = 0; u < 2; ++u) lagrange_basis_derivative<NB>(cur_xl[u], p.tab, dphi[u]);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int s = (int)(cur_sg[u] & HOL_SEG_MASK);
+                            // (an input that does not exist carries HOL_SEG_INVALID with segment bits 0: base stays in range)
+                            dx_pick<NB>(racc, (ii + u < ninp ? ii + u : 0) * p.Kin + s * p.stride, tv[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = ibase + ii + u;
+                            if (ii + u < ninp && i < p.I) {
+                                const uint32_t sg = cur_sg[u];
+                                float sum = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < NB; ++j) sum = fmaf(dphi[u][j], tv[u][j], sum);
+                                float chain = chain_tab[min((int)(sg & HOL_SEG_MASK), p.nseg - 1)];
+                                if (sg & HOL_SEG_MIRROR) chain = -chain;
+                                // outliers are written by the fp32 fix-up kernel after this launch
+                                const float outv = (sg & (HOL_SEG_INVALID | HOL_SEG_OUTLIER)) ? 0.0f : sum * inv * chain;
+                                if (p.transposed)
+                                    p.out[(int64_t)i * p.Bp + b] = outv;
+                                else if (row < p.rows_valid)
+                                    p.out[b * p.I + i] = outv;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) cur_sg[u] = nxt_sg[u], cur_xl[u] = nxt_xl[u];
                     }
                 }
             }

@@ -236,7 +236,12 @@ def _layer_backward(ctx, gy, x, w, gy_stats_valid: bool):
     need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     dx = dw = None
     sink, out = _grad_sink(ctx.w_ref) if need_dw else (None, None)
-    if sink is not None:
+    if sink is not None and need_dx and sink.wants_deferred(ctx.w_ref):
+        # a larger gradient is still to come (parallel.py, "largest message first"): dX now, dW from finish()
+        dx = pw_backward(gy, x, w, ws, *ctx.args, True, False, True, gy_stats_valid)[0]
+        args, w_ref = ctx.args, ctx.w_ref
+        sink.defer(w_ref, lambda: pw_backward_dw_into(gy, x, w, ws, out, *args, True, True))
+    elif sink is not None:
         pw_backward_dw_into(gy, x, w, ws, out, *ctx.args, True, gy_stats_valid)
         sink.ready(ctx.w_ref)
         if need_dx:

@@ -9,6 +9,12 @@ gradient, started as soon as that layer's dW kernel has been queued.
   and calls ``ready(w)``.  dW is computed BEFORE dX (csrc/abi.cu), so the all-reduce of the slice is
   issued on a side stream while the dX kernels of the same layer -- and the whole backward of the
   layers below -- still run: the collective is hidden behind compute.
+* Largest message first: the backward reaches the layers last-to-first, so the FIRST layer's gradient
+  -- in an MLP by far the largest one (784 -> 128: 5.2 of 6.1 MB) -- is the last kernel of the backward
+  and its exchange would sit exposed behind it.  A layer whose dX is still needed, and that is followed by
+  a parameter with a larger gradient, therefore only computes dX in the backward and hands its dW launch to
+  ``defer()``; ``finish()`` runs the deferred dW launches (largest first), so they -- not idle time --
+  cover the exchange of the large slice.  With one process, or one layer, nothing is deferred.
 * Every other parameter (conv weights reached through a permuted view, ``nn.Linear``) accumulates
   through autograd as usual and is reduced by ``finish()`` in as few collectives as its slices allow.
 
@@ -41,7 +47,8 @@ def shard_range(total: int, rank: int, world: int):
 
 class FlatGradients:
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 average: bool = True, direct: bool = True, overlap: bool = True, collective: str = "auto"):
+                 average: bool = True, direct: bool = True, overlap: bool = True, collective: str = "auto",
+                 defer: bool = True):
         seen = set()
         self.params: List[torch.nn.Parameter] = []
         for p in params:  # HighOrderMLP registers its first/last layer twice: deduplicate
@@ -86,6 +93,8 @@ class FlatGradients:
         self._side_used = False
         self._done: set = set()
         self._direct_ids: set = set()  # parameters whose layers wrote into the sink in the last step
+        self.defer_dw = defer
+        self._deferred: list = []      # (numel, order, parameter, launch) of dW launches handed to defer()
 
     # -- plumbing -------------------------------------------------------------------------
     def _setup_p2p(self, dev) -> None:
@@ -174,6 +183,9 @@ class FlatGradients:
     def begin(self) -> None:
         """Start of a step: zero the slices that accumulate through autograd (the slices the layers
         overwrite through the sink need no fill) and forget the previous step's state."""
+        if self._deferred:
+            raise RuntimeError("FlatGradients.begin(): the previous backward left deferred dW launches behind; "
+                               "every backward must be followed by finish()")
         self._alias()
         keep = self._direct_ids if self.direct else set()
         for lo, hi in self._ranges(i for i in self._range if i not in keep):
@@ -193,7 +205,7 @@ class FlatGradients:
         lo, hi = self._range[id(p)]
         if g is None or g.data_ptr() != self.flat[lo:hi].data_ptr():
             return None
-        if id(p) in self._done:
+        if id(p) in self._done or self._is_deferred(p):
             raise RuntimeError("FlatGradients: a parameter received two gradients in one backward; build the "
                                "FlatGradients with direct=False for modules that are applied more than once")
         return g
@@ -215,8 +227,33 @@ class FlatGradients:
             self._side.wait_event(ev)
             self._reduce(lo, hi)
 
+    def wants_deferred(self, p: torch.nn.Parameter) -> bool:
+        """True if the layer owning `p` should compute only dX now and hand its dW launch to ``defer()``: the
+        exchange is overlapped (side stream, more than one process) and a parameter with a larger gradient
+        has not produced it yet -- that one's exchange is what the deferred dW kernels will cover."""
+        if not (self.defer_dw and self.direct and self._side is not None and self._world() > 1):
+            return False
+        n = p.numel()
+        return any(q.numel() > n and id(q) not in self._done and not self._is_deferred(q) and q is not p
+                   for q in self.params)
+
+    def _is_deferred(self, p: torch.nn.Parameter) -> bool:
+        return any(q is p for _n, _k, q, _f in self._deferred)
+
+    def defer(self, p: torch.nn.Parameter, launch) -> None:
+        """`launch()` queues the dW kernels of `p` (writing its slice); run by ``finish()``, then ``ready(p)``."""
+        self._deferred.append((p.numel(), len(self._deferred), p, launch))
+
+    def _run_deferred(self) -> None:
+        todo, self._deferred = sorted(self._deferred, key=lambda t: (-t[0], t[1])), []
+        for _n, _k, p, launch in todo:
+            launch()
+            self.ready(p)
+
     def finish(self) -> None:
-        """End of the backward: reduce what autograd accumulated and join the side stream."""
+        """End of the backward: run the deferred dW launches, reduce what autograd accumulated and join the
+        side stream."""
+        self._run_deferred()
         self._alias()
         rest = [i for i in self._range if i not in self._done]
         if self._world() > 1 and rest:

@@ -102,3 +102,50 @@ def test_shard_range_partitions_batch():
                 assert covered == list(range(total))
             else:
                 assert sum(covered) == total and max(covered) - min(covered) <= 1
+
+
+def test_largest_message_first_deferral_order(monkeypatch):
+    """parallel.FlatGradients: a layer that is followed (in backward order) by a parameter with a larger
+    gradient defers its dW launch; finish() runs the deferred launches largest first and starts each slice's
+    exchange right behind it.  Host logic only: the side stream / world size are stubbed."""
+    import torch
+
+    from high_order_layers_torch_b200.parallel import FlatGradients
+
+    w1 = torch.nn.Parameter(torch.zeros(128, 784, 13))   # config 3: 5.2 MB
+    w2 = torch.nn.Parameter(torch.zeros(128, 128, 13))
+    w3 = torch.nn.Parameter(torch.zeros(10, 128, 13))
+    flat = FlatGradients([w1, w2, w3])
+    log = []
+    monkeypatch.setattr(flat, "_world", lambda: 8)
+    monkeypatch.setattr(flat, "_reduce", lambda lo, hi: log.append(("reduce", hi - lo)))
+    flat._side = None
+    flat.begin()
+    assert not flat.wants_deferred(w3)            # no overlap stream: nothing to cover, nothing deferred
+    flat._side = object()
+    monkeypatch.setattr(flat, "ready", lambda p: (log.append(("ready", p.numel())), flat._done.add(id(p))))
+    # backward order: layer 3, layer 2, layer 1
+    assert flat.wants_deferred(w3) and flat.target(w3) is not None
+    flat.defer(w3, lambda: log.append(("dw", w3.numel())))
+    try:
+        flat.target(w3)
+        raise AssertionError("a second gradient for a deferred parameter must be refused")
+    except RuntimeError:
+        pass
+    assert flat.wants_deferred(w2)
+    flat.defer(w2, lambda: log.append(("dw", w2.numel())))
+    assert not flat.wants_deferred(w1)            # the largest one: computed and exchanged at once
+    flat.ready(w1)
+    flat._side = None                              # (finish() would join the stub stream)
+    flat.finish()
+    assert log == [("ready", w1.numel()), ("dw", w2.numel()), ("ready", w2.numel()),
+                   ("dw", w3.numel()), ("ready", w3.numel())], log
+    flat.begin()                                   # nothing left behind
+    # a single layer (config 2) or a single process never defers
+    solo = FlatGradients([torch.nn.Parameter(torch.zeros(4, 4, 5))])
+    solo._side = object()
+    monkeypatch.setattr(solo, "_world", lambda: 8)
+    assert not solo.wants_deferred(solo.params[0])
+    monkeypatch.setattr(flat, "_world", lambda: 1)
+    flat._side = object()
+    assert not flat.wants_deferred(w3)

@@ -865,6 +865,76 @@ def test_gradient_sink_writes_dw_into_the_flat_buffer():
         assert p.grad.data_ptr() >= flat.flat.data_ptr() and torch.equal(p.grad, g)
 
 
+def test_deferred_dw_order_gives_the_same_gradients(monkeypatch):
+    """Largest-message-first scheduling (parallel.FlatGradients.wants_deferred / defer): a layer followed by a
+    larger gradient computes dX in the backward and dW from finish().  Forced here on one process (the world
+    size is stubbed, the exchange itself is skipped): gradients equal the plain autograd route bit for bit,
+    for tensor-core layers with the folded normalisation, a gather layer, and a layer whose plan mixes a
+    gather dW with a tensor-core dX (max|gy| must be taken by whichever half runs first)."""
+    from high_order_layers_torch_b200.parallel import FlatGradients
+    torch.manual_seed(1)
+    net = hol.HighOrderMLP(layer_type="continuous", n=4, in_width=200, out_width=10, hidden_layers=1, hidden_width=128,
+                           in_segments=4, out_segments=4, hidden_segments=4,
+                           normalization=hol.MaxAbsNormalization, device=DEV)
+    for q in net.parameters():
+        with torch.no_grad():
+            q.uniform_(-1, 1)
+    x = torch.rand(1024, 200, device=DEV) * 2 - 1
+    tgt = torch.randint(0, 10, (1024,), device=DEV)
+    loss = lambda: torch.nn.functional.cross_entropy(net(x), tgt)
+    loss().backward()
+    params = []
+    for q in net.parameters():
+        if all(q is not r for r in params):
+            params.append(q)
+    want = [q.grad.clone() for q in params]
+    for q in params:
+        q.grad = None
+    flat = FlatGradients(params)
+    reduced = []
+    monkeypatch.setattr(flat, "_world", lambda: 2)
+    monkeypatch.setattr(flat, "_reduce", lambda lo, hi: reduced.append(hi - lo))
+    assert flat._side is not None
+    for step in range(2):
+        del reduced[:]
+        flat.begin()
+        loss().backward()
+        assert len(flat._deferred) == len(params) - 1     # all but the largest (first) layer wait for finish()
+        flat.finish()
+        torch.cuda.synchronize()
+        for q, g in zip(params, want):
+            assert torch.equal(q.grad, g), (step, tuple(q.shape))
+        assert reduced[0] == params[0].numel() and sorted(reduced[1:], reverse=True) == reduced[1:]
+    # a layer whose plan mixes a tensor-core dX with a gather dW (33 -> 65, n = 4, 32 segments: PLAN_CASES) behind a
+    # larger one, under the default planner, gather kernels only, and the chunked-Phi tensor-core variant
+    from high_order_layers_torch_b200 import _lib
+    for ovr in (0, _lib.HOL_PLAN_DISABLE_TENSOR_CORES, _lib.HOL_PLAN_NO_SHARED_PHI):
+        old = ops.set_plan_overrides(ovr)
+        try:
+            torch.manual_seed(2)
+            a = hol.PiecewisePolynomial(n=4, in_features=120, out_features=33, segments=32, device=DEV)
+            b = hol.PiecewisePolynomial(n=4, in_features=33, out_features=65, segments=32, device=DEV)
+            for q in (a.w, b.w):
+                with torch.no_grad():
+                    q.uniform_(-1, 1)
+            xx = torch.rand(300, 120, device=DEV) * 2 - 1
+            run = lambda: b(a(xx) * 0.02).square().sum().backward()
+            run()
+            wa, wb = a.w.grad.clone(), b.w.grad.clone()
+            a.w.grad = b.w.grad = None
+            fl = FlatGradients([a.w, b.w])
+            monkeypatch.setattr(fl, "_world", lambda: 2)
+            monkeypatch.setattr(fl, "_reduce", lambda lo, hi: None)
+            fl.begin()
+            run()
+            assert len(fl._deferred) == 1
+            fl.finish()
+            torch.cuda.synchronize()
+            assert torch.equal(a.w.grad, wa) and torch.equal(b.w.grad, wb), ovr
+        finally:
+            ops.set_plan_overrides(old)
+
+
 def test_round2_variants_golden():
     """SURVEY 8f-3, second batch (fixture variants2.npz from the unmodified reference): 1-d convolutions
     with zero padding / stride / dilation handled by the CUDA library's prep stage (no torch unfold),
