@@ -195,7 +195,7 @@ def build_workload(torch, cfg, device, rank, args):
             layer.w.uniform_(-1, 1)
         x = make_inputs(torch, (B, I), gen, device).requires_grad_(True)
         gy = torch.randn(B, O, generator=gen, device=device)
-        flat = FlatGradients(layer.parameters(), collective=args.collective)
+        flat = FlatGradients(layer.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
 
         def step():
             flat.begin()
@@ -236,7 +236,7 @@ def build_workload(torch, cfg, device, rank, args):
         target = (torch.randint(0, wd[-1], (B,), generator=gen, device=device) if classify
                   else torch.randn(B, wd[-1], generator=gen, device=device))
         lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
-        flat = FlatGradients(net.parameters(), collective=args.collective)
+        flat = FlatGradients(net.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
 
         def step():
             flat.begin()
@@ -293,7 +293,7 @@ def build_workload(torch, cfg, device, rank, args):
             net.conv2.conv.weight.uniform_(-0.2, 0.2)
         x = make_inputs(torch, (B, 3, 32, 32), gen, device)
         target = torch.randint(0, 100, (B,), generator=gen, device=device)
-        flat = FlatGradients(net.parameters(), collective=args.collective)
+        flat = FlatGradients(net.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
 
         def step():
             flat.begin()
@@ -583,7 +583,9 @@ def run_ours(args):
                        "allreduce": ("per-layer fp32 mean all-reduce of dW on a side stream, issued right after the layer's "
                                      "dW kernels and overlapped with the rest of the backward; " +
                                      ("own peer-memory kernels over NVLink (csrc/p2p.cu)" if head["collective"] == "p2p"
-                                      else "NCCL")) if world > 1 else "none", "cuda_graph": head["cuda_graph"]},
+                                      else "NCCL" if head["collective"] == "nccl"
+                                      else "SKIPPED (--collective none: diagnostic run, not a valid data-parallel number)"))
+                       if world > 1 else "none", "cuda_graph": head["cuda_graph"]},
             "e2e": head.get("e2e"),
             "gpu_launches": head["gpu_launches_per_step"] * steps,
             "gpu_launches_per_step": head["gpu_launches_per_step"],
@@ -1037,8 +1039,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's torch-CUDA leg")
-    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl", "none"],
                     help="dW all-reduce: our peer-memory kernels over NVLink (p2p; auto = p2p when available) or NCCL")
+    ap.add_argument("--no-defer", action="store_true",
+                    help="data parallel: every layer's dW in backward order (no largest-message-first deferral)")
+    ap.add_argument("--force-defer", action="store_true", help="defer dW even with one process (diagnostic)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the step in a CUDA graph (auto: MLP / conv workloads only)")
     args = ap.parse_args()

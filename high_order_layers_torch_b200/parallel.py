@@ -82,6 +82,8 @@ class FlatGradients:
                 self.flat = None
         if self.flat is None:
             self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        if collective == "none":
+            self.collective = "none"
         self._range: Dict[int, Tuple[int, int]] = {}
         off = 0
         for p in self.params:
@@ -154,7 +156,7 @@ class FlatGradients:
 
     def _reduce(self, lo: int, hi: int) -> None:
         world = self._world()
-        if world == 1:
+        if world == 1 or self.collective == "none":  # "none": diagnostic only (bench.py --collective none)
             return
         if self._p2p is not None:
             import ctypes
@@ -231,7 +233,9 @@ class FlatGradients:
         """True if the layer owning `p` should compute only dX now and hand its dW launch to ``defer()``: the
         exchange is overlapped (side stream, more than one process) and a parameter with a larger gradient
         has not produced it yet -- that one's exchange is what the deferred dW kernels will cover."""
-        if not (self.defer_dw and self.direct and self._side is not None and self._world() > 1):
+        if not (self.defer_dw and self.direct):
+            return False
+        if self.defer_dw != "always" and (self._side is None or self._world() == 1):
             return False
         n = p.numel()
         return any(q.numel() > n and id(q) not in self._done and not self._is_deferred(q) and q is not p

@@ -43,36 +43,40 @@ for it in range(3):
     if rank == 0:
         print(f"iter {it}: rel err vs NCCL {err:.2e}, identical on all ranks: {same}")
 flat.check()
-# graph capture + replay, timing against NCCL at the first-layer size (5.2 MB)
-n = 128 * 784 * 13
-buf_nccl = torch.randn(n, device=dev)
-torch.cuda.synchronize()
-dist.barrier()
-def p2p_step():
-    flat._reduce(0, n)
-g = torch.cuda.CUDAGraph()
-s = torch.cuda.Stream()
-s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    for _ in range(3):
-        p2p_step()
-torch.cuda.current_stream().wait_stream(s)
-torch.cuda.synchronize()
-with torch.cuda.graph(g):
-    p2p_step()
-for name, fn in (("p2p (graph replay)", g.replay), ("nccl all_reduce", lambda: dist.all_reduce(buf_nccl))):
-    for _ in range(5):
-        fn()
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(50):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    if rank == 0:
-        print(f"{name}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per all-reduce of {n * 4 / 1e6:.1f} MB on {world} GPUs")
+# graph capture + replay, timing against NCCL at the three gradient sizes of the config-3 MLP
+for n in (10 * 128 * 13, 128 * 128 * 13, 128 * 784 * 13):
+    buf_nccl = torch.randn(n, device=dev)
+    for mode, ovr in (("p2p (graph replay)", 0), ("nccl", None)):
+        if ovr is not None:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    flat._reduce(0, n)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            dist.barrier()
+            with torch.cuda.graph(g):
+                flat._reduce(0, n)
+            fn = g.replay
+        else:
+            fn = lambda: dist.all_reduce(buf_nccl)
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"{n * 4 / 1e6:6.2f} MB on {world} GPUs, {mode}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per all-reduce")
+        flat.check()
+        if ovr is not None:
+            del g
 flat.check()
 if rank == 0:
     print("P2P_CHECK", "OK" if ok else "FAILED")
