@@ -171,6 +171,11 @@ def tc_gemm_flops(kind, B, I, O, n, S, disc):
     return 3 * 2 * M * N * Kc
 
 
+def defer_mode(args):
+    """FlatGradients(defer=...): largest-message-first by default, off / forced for the diagnostics."""
+    return False if args.no_defer else ("always" if args.force_defer else True)
+
+
 def make_inputs(torch, shape, gen, device):
     """x = 2*rand-1 with 1 % of the entries drawn from uniform(-1.25, 1.25)."""
     x = torch.rand(shape, generator=gen, device=device) * 2 - 1
@@ -195,7 +200,7 @@ def build_workload(torch, cfg, device, rank, args):
             layer.w.uniform_(-1, 1)
         x = make_inputs(torch, (B, I), gen, device).requires_grad_(True)
         gy = torch.randn(B, O, generator=gen, device=device)
-        flat = FlatGradients(layer.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
+        flat = FlatGradients(layer.parameters(), collective=args.collective, defer=defer_mode(args))
 
         def step():
             flat.begin()
@@ -236,7 +241,7 @@ def build_workload(torch, cfg, device, rank, args):
         target = (torch.randint(0, wd[-1], (B,), generator=gen, device=device) if classify
                   else torch.randn(B, wd[-1], generator=gen, device=device))
         lossf = torch.nn.functional.cross_entropy if classify else torch.nn.functional.mse_loss
-        flat = FlatGradients(net.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
+        flat = FlatGradients(net.parameters(), collective=args.collective, defer=defer_mode(args))
 
         def step():
             flat.begin()
@@ -293,7 +298,7 @@ def build_workload(torch, cfg, device, rank, args):
             net.conv2.conv.weight.uniform_(-0.2, 0.2)
         x = make_inputs(torch, (B, 3, 32, 32), gen, device)
         target = torch.randint(0, 100, (B,), generator=gen, device=device)
-        flat = FlatGradients(net.parameters(), collective=args.collective, defer=(False if args.no_defer else ('always' if args.force_defer else True)))
+        flat = FlatGradients(net.parameters(), collective=args.collective, defer=defer_mode(args))
 
         def step():
             flat.begin()
@@ -384,31 +389,39 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end through the public module API: pinned host inputs -> H2D -> fwd+bwd -> loss D2H
-    # Every step copies ITS inputs from pinned host memory and reads ITS loss back.  Two device input
-    # buffers and two pinned loss words: the copy of step k+1 runs on a second stream while step k
-    # computes (the usual input prefetch), and the host reads the loss of step k-1 while step k runs
-    # (the usual one-step-lagged logging read), so the host never idles the GPU between steps.  The
-    # first copy and the last read-back are exposed.
+    # Every step copies ITS inputs from pinned host memory and reads ITS loss back.  Three device input
+    # buffers and three pinned loss words: the copies of steps k+1 and k+2 run on a second stream while step
+    # k computes (the usual input prefetch; with only two buffers the copy of step k+1 has to fit exactly
+    # inside step k, and under the step's own HBM traffic it does not: 0.47 ms alone, ~0.64 ms next to the
+    # 0.59 ms config-3 step), and the host reads the loss of step k-1 while step k runs (the usual
+    # one-step-lagged logging read) on a third stream, so neither the host nor a copy idles the GPU between
+    # steps.  The first copy and the last read-back are exposed.
     e2e_steps, e2e_ms = 0, 0.0
     if with_e2e:
-        e2e_steps = max(1, min(steps, 20))
-        host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        NBUF = 3
+        # launch-bound workloads (~1 ms steps): enough steps that the one exposed input copy at the start is not
+        # a tenth of the measurement
+        e2e_steps = max(steps, 50) if graphed else max(1, min(steps, 20))
+        host_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
         main_stream = torch.cuda.current_stream()
         copy_stream = torch.cuda.Stream()
+        d2h_stream = torch.cuda.Stream()   # the loss read-back: neither behind the next input copy nor in front of the next step
         dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in wl["host"].items()}
-                    for _ in range(2)]
+                    for _ in range(NBUF)]
 
         # launch-bound workloads replay the captured step here too: one graph per input buffer
         e2e_graphs = None
         if graphed:
             try:
                 e2e_graphs = []
-                for slot in (0, 1):
+                for slot in range(NBUF):
                     for k, v in wl["host"].items():
                         dev_bufs[slot][k].copy_(v)
                     torch.cuda.synchronize()
                     g2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g2):
+                    # the graphs never run concurrently: one memory pool, so the workspaces of a step sit at the
+                    # same addresses whichever input buffer it reads (what a training loop's allocator gives)
+                    with torch.cuda.graph(g2, pool=(e2e_graphs[0][0].pool() if e2e_graphs else None)):
                         loss2 = wl["e2e_compute"](dev_bufs[slot])
                     e2e_graphs.append((g2, loss2))
                 torch.cuda.synchronize()
@@ -420,9 +433,9 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                 e2e_graphs = None
 
         def run_e2e(nsteps):
-            ready = [torch.cuda.Event(), torch.cuda.Event()]
-            consumed = [None, None]
-            landed = [None, None]
+            ready = [torch.cuda.Event() for _ in range(NBUF)]
+            consumed = [None] * NBUF
+            landed = [None] * NBUF
             losses = []
 
             def prefetch(slot):
@@ -433,12 +446,15 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                         dev_bufs[slot][k].copy_(v, non_blocking=True)
                     ready[slot].record(copy_stream)
 
-            prefetch(0)
+            for k in range(min(NBUF - 1, nsteps)):
+                prefetch(k)
             for k in range(nsteps):
-                slot = k & 1
-                if k + 1 < nsteps:
-                    prefetch(slot ^ 1)
+                slot = k % NBUF
+                if k + NBUF - 1 < nsteps:
+                    prefetch((k + NBUF - 1) % NBUF)   # the buffer of step k-1, whose compute is already queued
                 main_stream.wait_event(ready[slot])
+                if landed[slot] is not None:   # the loss word of this slot's graph has been read (NBUF steps ago)
+                    main_stream.wait_event(landed[slot])
                 if e2e_graphs is not None:
                     e2e_graphs[slot][0].replay()
                     loss = e2e_graphs[slot][1]
@@ -447,15 +463,21 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
                 ev = torch.cuda.Event()
                 ev.record(main_stream)
                 consumed[slot] = ev
-                host_loss[slot].copy_(loss.detach(), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(main_stream)
-                landed[slot] = ev
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(ev)
+                    src = loss.detach()
+                    src.record_stream(d2h_stream)
+                    host_loss[slot].copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(d2h_stream)
+                    landed[slot] = ev
                 if k >= 1:  # the previous step's loss, read while this step runs
-                    landed[slot ^ 1].synchronize()
-                    losses.append(float(host_loss[slot ^ 1]))
-            landed[(nsteps - 1) & 1].synchronize()
-            losses.append(float(host_loss[(nsteps - 1) & 1]))
+                    prev = (k - 1) % NBUF
+                    landed[prev].synchronize()
+                    losses.append(float(host_loss[prev]))
+            last = (nsteps - 1) % NBUF
+            landed[last].synchronize()
+            losses.append(float(host_loss[last]))
             assert len(losses) == nsteps and all(v == v for v in losses), "e2e: a step's loss was not read back"
             return losses[-1]
 
@@ -465,6 +487,16 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
         run_e2e(e2e_steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        # the input copy alone (idle GPU): when it is as long as the step, the end-to-end rate is the PCIe rate
+        hc0, hc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            hc0.record(copy_stream)
+            for _ in range(4):
+                for k, v in wl["host"].items():
+                    dev_bufs[0][k].copy_(v, non_blocking=True)
+            hc1.record(copy_stream)
+        copy_stream.synchronize()
+        h2d_alone_ms = hc0.elapsed_time(hc1) / 4
         if e2e_graphs is not None:
             for g2, _ in e2e_graphs:
                 g2.reset()
@@ -487,8 +519,10 @@ def time_workload(torch, dist, key, cfg, device, rank, world, steps, warmup, arg
     if with_e2e:
         res["e2e"] = {"value": wl["samples"] * world / (e2e_ms / e2e_steps / 1e3), "unit": "samples/s",
                       "h2d_bytes_per_step": wl["h2d"], "d2h_bytes_per_step": wl["d2h"], "steps": e2e_steps,
+                      "ms_per_step": e2e_ms / e2e_steps, "h2d_ms_alone": h2d_alone_ms,
+                      "h2d_gbs_alone": wl["h2d"] / (h2d_alone_ms * 1e6),
                       "note": "module API; pinned-host inputs copied H2D and the loss read back D2H every step; "
-                              "the copy of step k+1 overlaps the compute of step k (double-buffered prefetch) and the host reads the "
+                              "the copies of steps k+1 / k+2 overlap the compute of step k (three input buffers) and the host reads the "
                               "loss of step k-1 while step k runs (one-step-lagged read, every step's loss is read)"
                               + ("; the step is replayed from a CUDA graph captured per input buffer" if graphed else "")}
     peaks = load_peaks()
@@ -533,6 +567,11 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
+    if args.plan_overrides:
+        from high_order_layers_torch_b200 import ops as _ops
+        _ops.set_plan_overrides(args.plan_overrides)
+        if rank == 0:
+            print(f"bench.py: planner overrides {args.plan_overrides:#x} (diagnostic run)", file=sys.stderr)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
     head_key = "c3" if args.config == "all" else args.config
@@ -1044,6 +1083,8 @@ def main():
     ap.add_argument("--no-defer", action="store_true",
                     help="data parallel: every layer's dW in backward order (no largest-message-first deferral)")
     ap.add_argument("--force-defer", action="store_true", help="defer dW even with one process (diagnostic)")
+    ap.add_argument("--plan-overrides", type=int, default=0,
+                    help="diagnostic HOL_PLAN_* mask for the library's planner (include/hol_b200.h), e.g. 32 = no auxiliary stream")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the step in a CUDA graph (auto: MLP / conv workloads only)")
     args = ap.parse_args()
