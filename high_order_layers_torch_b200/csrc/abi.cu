@@ -121,6 +121,7 @@ size_t carve(const PwShape& s, void* base, PwWorkspace& ws, int64_t conv_pixels)
     ws.tc_b = s.tc.enabled ? (void*)take(s.tc.b_bytes) : nullptr;
     ws.tc_scalars = s.tc.enabled ? (void*)take(256) : nullptr;
     ws.tc_wmean = (s.tc.enabled && s.tc.dx) ? (float*)take((size_t)s.O * s.I * sizeof(float)) : nullptr;
+    ws.gy_t = (s.n > 1 && s.OT >= 32 && !(s.tc.enabled && s.tc.dx)) ? (float*)take((size_t)s.nOT * s.OT * s.Bp * sizeof(float)) : nullptr;
     ws.prof = nullptr;
     ws.total = off;
     return off;
@@ -477,7 +478,7 @@ int hol_pw_launch_count(int kind, int64_t B, int32_t I, int32_t O, int32_t n, in
     if (fused_norm) c += 1;    // normalisation backward (takes max|gy| along the way: HOL_GY_STATS_VALID)
     const bool tc_any = (n > 1 && s.tc.dx) || s.tc.dw;
     if (tc_any && (want_dx || want_dw) && !(flags & HOL_GY_STATS_VALID)) c += tc_launch_count(s, s.tc, 3, prepared);  // max |gy|
-    if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2);
+    if (want_dx && n > 1) c += s.tc.dx ? tc_launch_count(s, s.tc, 1, prepared) : ((prepared && !s.tc.fwd) ? 1 : 2) + (s.OT >= 32 ? 1 : 0);  // [pack], [gy transpose: wide tiles], dX
     if (want_dw)
         c += s.tc.dw ? tc_launch_count(s, s.tc, 2, prepared)
                      : (s.dwd.enabled ? 1 + (s.dwd.ksplit > 1 ? 1 : 0) : 2 + (s.ksplit > 1 ? 1 : 0));

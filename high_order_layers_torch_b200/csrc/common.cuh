@@ -102,6 +102,7 @@ struct PwWorkspace {
     void* tc_b;       // tensor-core path: W tiles
     void* tc_scalars; // tensor-core path: device scalars (max |xl|, max |w|, max |gy|, outlier count)
     float* tc_wmean;  // tensor-core dX: mean weight of every link [O][I] (the W^T tiles hold w - mean)
+    float* gy_t;      // gather dX: upstream gradient transposed, [nOT*OT][Bp] (zero beyond O and B)
     void* prof;       // HOST pointer, normally null: hol_pw_profile_f32 collects per-GEMM events here
     size_t total;
 };

@@ -13,7 +13,8 @@ struct DxParams {
     const float* xl_t;
     const uint16_t* seg_t;
     const float* wk;
-    const float* gy;
+    const float* gy;    // [B][O] (narrow tiles, OT <= 16)
+    const float* gy_t;  // [nOT*OT][Bp] (OT >= 32): lanes (consecutive samples) read consecutive words
     float* dx;
     int64_t B, Bp;
     int I, O, R, nOT, stage_floats, srow, transposed, it_eff, nst;
@@ -26,8 +27,10 @@ struct DxParams {
 // column chunks of a tile in the rotated order ((qb + (l%8)/4) % (OT/16), (t + l%8) % 4), so the 8
 // lanes of a quarter warp always read 8 different bank groups whatever their segments are (see
 // fwd.cu); the matching gy chunk is loaded in the same order.
+// IT = 2 (layers whose packed rows only let two inputs share a stage: many segments): 16 + 2 running sums leave
+// room for 512-sample CTAs -- twice the warps per SM and half the weight traffic per sample.
 template <int N, int OT, int IT, bool ROT>
-__global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __grid_constant__ DxParams p) {
+__global__ void __launch_bounds__((IT <= 2 ? 512 : 256), (OT <= 16 && IT > 2 ? 2 : 1)) pw_dx_kernel(const __grid_constant__ DxParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -64,9 +67,15 @@ __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __
         if (p.nst > 1 && total_chunks > 1) issue(1);
     }
 
+    // Wide tiles read the TRANSPOSED upstream gradient (pw_transpose_gy_kernel): with the row-major gy every lane
+    // of a warp-wide LDG.128 touches its own 128-byte line -- 32 LSU wavefronts per load, as many per block as the
+    // weight reads themselves (config-5 sweep, n = 4, S = 64: dX 557 -> 398 ms).  Narrow tiles (OT <= 16: classifier
+    // heads, conv layers) are not LSU-bound; they keep the four vector loads and skip the transpose launch.
+    constexpr bool GT = OT >= 32;
     const bool rowok = b < p.B;
     const bool vec = (p.O & 3) == 0;
-    const float* gyrow = p.gy + (rowok ? b : 0) * p.O;
+    const float* gyrow = GT ? nullptr : p.gy + (rowok ? b : 0) * p.O;
+    const float* gyt = GT ? p.gy_t + b : nullptr;
     int rowoff[IT];
     float2 acc[IT][N];
     int i0 = 0, ni = 0;
@@ -91,21 +100,42 @@ __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __
 #pragma unroll 1
         for (int qb0 = 0; qb0 < OT / QW; ++qb0) {
             const int qb = ROT ? ((qb0 + (rot >> 2)) & (OT / QW - 1)) : qb0;
+            // The thread's QW upstream gradients of this block, from the TRANSPOSED gy: a warp-wide 4-byte load is
+            // one 128-byte line per group of lanes that works on the same block (two groups under ROT) -- the row-major
+            // gy cost 32 lines per LDG.128 (one per lane), as many LSU wavefronts as the weight reads themselves.
             float4 g[QW / 4];
+            if (!GT) {
 #pragma unroll
-            for (int t = 0; t < QW / 4; ++t) {
-                const int o = ot * OT + qb * QW + 4 * (ROT ? ((t + rot) & 3) : t);
-                g[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (rowok) {
-                    if (vec && o + 3 < p.O) {
-                        g[t] = __ldg(reinterpret_cast<const float4*>(gyrow + o));
-                    } else {
-                        if (o + 0 < p.O) g[t].x = __ldg(gyrow + o + 0);
-                        if (o + 1 < p.O) g[t].y = __ldg(gyrow + o + 1);
-                        if (o + 2 < p.O) g[t].z = __ldg(gyrow + o + 2);
-                        if (o + 3 < p.O) g[t].w = __ldg(gyrow + o + 3);
+                for (int t = 0; t < QW / 4; ++t) {
+                    const int o = ot * OT + qb * QW + 4 * t;
+                    g[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (rowok) {
+                        if (vec && o + 3 < p.O) {
+                            g[t] = __ldg(reinterpret_cast<const float4*>(gyrow + o));
+                        } else {
+                            if (o + 0 < p.O) g[t].x = __ldg(gyrow + o + 0);
+                            if (o + 1 < p.O) g[t].y = __ldg(gyrow + o + 1);
+                            if (o + 2 < p.O) g[t].z = __ldg(gyrow + o + 2);
+                            if (o + 3 < p.O) g[t].w = __ldg(gyrow + o + 3);
+                        }
                     }
                 }
+            } else {
+                const float* src = gyt + (int64_t)(ot * OT + qb * QW) * p.Bp;
+                float gn[QW];
+#pragma unroll
+                for (int e = 0; e < QW; ++e) gn[e] = __ldg(src + (int64_t)e * p.Bp);
+#pragma unroll
+                for (int t = 0; t < QW / 4; ++t) g[t] = make_float4(gn[4 * t], gn[4 * t + 1], gn[4 * t + 2], gn[4 * t + 3]);
+            }
+            if (ROT) {  // chunk t of this lane is output chunk (t + rot) & 3: rotate by rot & 3 in two select stages
+                static_assert(!ROT || QW == 16, "the rotated order walks four 16-byte chunks per block");
+                const bool r1 = (rot & 1) != 0, r2 = (rot & 2) != 0;
+                float4 h[QW / 4];
+#pragma unroll
+                for (int t = 0; t < QW / 4; ++t) h[t] = r1 ? g[(t + 1) & (QW / 4 - 1)] : g[t];
+#pragma unroll
+                for (int t = 0; t < QW / 4; ++t) g[t] = r2 ? h[(t + 2) & (QW / 4 - 1)] : h[t];
             }
             const float* slabq = slab + qb * QW;
 #pragma unroll
@@ -153,6 +183,28 @@ __global__ void __launch_bounds__(256, (OT <= 16 ? 2 : 1)) pw_dx_kernel(const __
     }
 }
 
+// gy[B][O] -> gy_t[Opad][Bp], zero beyond B and O (32 x 32 shared-memory tiles)
+__global__ void __launch_bounds__(256) pw_transpose_gy_kernel(const float* __restrict__ gy, float* __restrict__ gy_t, int64_t B,
+                                                              int64_t Bp, int O, int Opad) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int o0 = blockIdx.y * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t b = b0 + r;
+        const int o = o0 + tx;
+        tile[r][tx] = (b < B && o < O) ? __ldg(gy + b * O + o) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int o = o0 + r;
+        const int64_t b = b0 + tx;
+        if (o < Opad && b < Bp) gy_t[(int64_t)o * Bp + b] = tile[tx][r];
+    }
+}
+
 template <int N>
 struct DxTile {
     static constexpr int IT = N <= 2 ? 16 : (N <= 5 ? 8 : 4);
@@ -175,6 +227,7 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
     p.seg_t = ws.seg_t;
     p.wk = ws.wk;
     p.gy = gy;
+    p.gy_t = ws.gy_t;
     p.dx = dx;
     p.B = s.B;
     p.Bp = s.Bp;
@@ -191,12 +244,29 @@ static int launch_dx_t(const PwShape& s, const PwWorkspace& ws, const float* gy,
     p.length = s.length;
     p.Sf = (float)s.S;
     p.tab = s.tab;
+    if (OT >= 32) {
+        if (!ws.gy_t) return HOL_EINVAL;
+        const int Opad = s.nOT * OT;
+        dim3 tgrid((unsigned)((s.Bp + 31) / 32), (unsigned)((Opad + 31) / 32));
+        pw_transpose_gy_kernel<<<tgrid, 256, 0, st>>>(gy, ws.gy_t, s.B, s.Bp, s.O, Opad);
+        cudaError_t te = cudaGetLastError();
+        if (te != cudaSuccess) return (int)te;
+    }
     int BT;
     if (s.Bp % 512 != 0) {
         BT = (int)s.Bp;
     } else {
         BT = 256;
         if ((s.Bp / BT) * ((s.I + it_eff - 1) / it_eff) < 2 * 148) BT = 128;
+    }
+    if (IT > 2 && it_eff <= 2 && s.Bp % 512 == 0 && (s.Bp / 512) * ((s.I + it_eff - 1) / it_eff) >= 2 * 148) {
+        auto kern2 = pw_dx_kernel<N, OT, 2, ROT>;
+        static std::atomic<uint64_t> attr_done2{0};
+        cudaError_t e2 = hol_ensure_max_smem(kern2, attr_done2);
+        if (e2 != cudaSuccess) return (int)e2;
+        dim3 grid2((unsigned)(s.Bp / 512), (unsigned)((s.I + it_eff - 1) / it_eff));
+        kern2<<<grid2, 512, smem, st>>>(p);
+        return (int)cudaGetLastError();
     }
     auto kern = pw_dx_kernel<N, OT, IT, ROT>;
     static std::atomic<uint64_t> attr_done{0};

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(512, 1) pw_fwd_kernel(const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     float* slab0 = reinterpret_cast<float*>(smem_raw + 128);
     constexpr int OTP = ROT ? OT : OT + 4;
-    constexpr int G = 4;
+    // coordinate prefetch depth: with 64 accumulators under the 128-register cap of a 512-thread CTA a depth of 4
+    // spills inside the input loop for n <= 6 (n = 4, S = 64 of the config-5 sweep: 76 STL/LDL, 69 GB of
+    // spill traffic per forward at batch 8192; depth 2: 371 -> 297 ms); the larger bases spill less at depth 4
+    constexpr int G = (OT >= 64 && N <= 6) ? 2 : 4;
     const int tid = threadIdx.x;
     const int q = IS > 1 ? tid % IS : 0;                 // which share of the input groups
     const int rot = (tid / IS) & 7;
