@@ -653,13 +653,13 @@ def run_ours(args):
 # `ncu --set full` capture of the same command; keyed by (config, dominant pass).  None where no
 # capture exists.
 NCU_TRAFFIC = {
-    ("c2", "forward"): 20.051057e9 + 0.258172e9,
-    ("c2", "dw"): 19.402402e9 + 0.167457e9,
-    ("c2", "dx"): 4.371290e9 + 0.272215e9,
-    ("c3", "forward"): 417.521e6 + 3.513e6,   # layer 1 (784 -> 128), the layer the roofline block profiles
-    ("c3", "dw"): 419.554e6 + 11.534e6,
+    ("c2", "forward"): 20.051674e9 + 0.257603e9,
+    ("c2", "dw"): 20.371956e9 + 0.167338e9,
+    ("c2", "dx"): 4.371416e9 + 0.270849e9,
+    ("c3", "forward"): 340.866e6 + 12.938e6,   # layer 1 (784 -> 128), the layer the roofline block profiles
+    ("c3", "dw"): 347.057e6 + 30.321e6,
 }
-NCU_TRAFFIC_SOURCE = "profiles/r2_c2_ncu_full_summary.md / r2_c3_ncu_full_summary.md (ncu --set full, same command)"
+NCU_TRAFFIC_SOURCE = "profiles/r2_c2_ncu_full_summary_final.md / r2_c3_ncu_full_summary_final.md (ncu --set full, same command)"
 
 
 def load_peaks():
