@@ -345,3 +345,47 @@ def test_planner_sweep_is_consistent():
     for (Bi, C, H, W, O, K, st, pad, dil) in ((4, 3, 32, 32, 6, 5, 1, 0, 1), (2, 6, 14, 14, 16, 5, 1, 2, 1),
                                             (1, 1, 7, 9, 2, 3, 2, 1, 2)):
         assert lib.hol_pw_conv2d_workspace_bytes(Bi, C, H, W, O, K, st, pad, dil, 3, 4, 0) > 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times next to ours) runs without a GPU: the unmodified
+    reference from baseline/_ref when it is installed (kind "reference"), the numpy oracle port otherwise, and
+    prints ONE JSON line with the same metric / unit / config as our arm plus the keys the contract names."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fwd+bwd samples/sec" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("c3:")
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"]
+    assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    have_ref = os.path.isfile(os.path.join(root, "baseline", "_ref", "high_order_layers_torch", "PolynomialLayers.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    """There is no CPU path: without a CUDA device `bench.py` (our arm) exits with an error instead of timing
+    anything, and a layer called on CPU tensors raises."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+    assert not [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    layer = hol.PiecewisePolynomial(n=3, in_features=4, out_features=2, segments=2)
+    with pytest.raises((ValueError, RuntimeError)):
+        layer(torch.zeros(5, 4))
